@@ -1,0 +1,98 @@
+"""Pins the CPU oracle (oracle/oracle.py) to golden vectors minted from the live reference.
+
+Keypoints must be identical; float outputs are compared at 2e-6 abs (same ATen kernels, but the
+oracle may batch differently from the reference module, which can change oneDNN blocking).
+"""
+import hashlib
+
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests import golden_util as G
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", G.names("sparse"))
+def test_sparse_matcher(name):
+    g = G.load(name)
+    kw = g["kwargs"]
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = O.sparse_matcher(g["image1"], g["image2"], g["K"], return_descriptors=True, **kw)
+        sc = O.shi_tomasi_score(g["image1"], kw.get("block_size", 3)).squeeze(1)
+        mask = O.nms_mask(sc, kw.get("nms_radius", 3))
+    assert _sha(sc) == g["score_sha"]
+    assert _sha(mask) == g["mask_sha"]
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    assert (d1 - g["desc1"]).abs().max() <= 2e-6
+    assert (d2 - g["desc2"]).abs().max() <= 2e-6
+    K = g["K"]
+    assert (p - g["P"])[:, :K, :].abs().max() <= 2e-6
+    assert ((p - g["P"])[:, K, K].abs() / g["P"][:, K, K]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", G.names("angle"))
+def test_angle_matcher(name):
+    g = G.load(name)
+    kw = g["kwargs"]
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = O.angle_matcher(g["image1"], g["image2"], g["K"], return_descriptors=True, **kw)
+        a1 = O.angle_map(g["image1"])
+        dk, ds, dd = O.angle_detector(g["image1"], g["K"], **kw)
+    assert _sha(a1) == g["angle_sha"]
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    assert (d1 - g["desc1"]).abs().max() <= 2e-6
+    assert (d2 - g["desc2"]).abs().max() <= 2e-6
+    K = g["K"]
+    assert (p - g["P"])[:, :K, :].abs().max() <= 2e-6
+    assert torch.equal(dk, g["det_kpts"])
+    assert torch.equal(ds, g["det_scores"])
+    assert (dd - g["det_desc"]).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", G.names("dense"))
+def test_dense_matcher(name):
+    g = G.load(name)
+    kw = g["kwargs"]
+    with torch.no_grad():
+        k1, k2, p, d1, _ = O.dense_matcher(g["image1"], g["image2"], g["K"], return_descriptors=True, **kw)
+        dkw = {k: v for k, v in kw.items() if k in ("block_size", "num_pairs", "binarize", "soft_binarize", "temperature")}
+        sc, dmap = O.dense_detector(g["image1"], **dkw)
+    assert _sha(sc) == g["score_sha"]
+    assert _sha(dmap) == g["dmap_sha"]
+    pb, pp, py, px = g["probe_idx"]
+    assert torch.equal(dmap[pb, pp, py, px], g["probe_val"])
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    assert (d1 - g["desc1"]).abs().max() <= 2e-6
+    K = g["K"]
+    assert (p - g["P"])[:, :K, :].abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", G.names("sinkhorn"))
+def test_sinkhorn(name):
+    g = G.load(name)
+    with torch.no_grad():
+        p = O.sinkhorn(g["desc1"], g["desc2"], **g["kwargs"])
+    assert torch.equal(p, g["P"])
+
+
+def test_constant_image():
+    g = G.load("sparse_constant_image")
+    with torch.no_grad():
+        k1, k2, p = O.sparse_matcher(g["image1"], g["image1"], g["K"])
+    assert torch.equal(k1, g["kpts1"]) and (k1 == -1).all()
+    assert torch.equal(p, g["P"])
+
+
+def test_table_facts():
+    for n in (256, 512):
+        ox1, ox2, oy1, oy2, r, thr = O.bad_tables(n)
+        assert ox1.shape == (n,) and thr.shape == (n,)
+        assert int(r.min()) == 1 and int(r.max()) == 7
+        for o in (ox1, ox2, oy1, oy2):
+            assert o.min() >= -15 and o.max() <= 14
+    with pytest.raises(ValueError):
+        O.bad_tables(128)
