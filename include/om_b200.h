@@ -1,0 +1,208 @@
+/*
+ * om_b200.h -- C ABI of libom_b200.so: the B200 (sm_100a) implementation of the
+ * Shi-Tomasi -> NMS -> top-k -> BAD -> Sinkhorn feature-matching path of
+ * fateshelled/onnx_image_processing.
+ *
+ * The reference has no FFI: its boundary for this path is the Python nn.Module API under
+ * pytorch_model/{detector,descriptor,orientation,matching,utils,feature_detection}.  Each entry
+ * point below replaces the arithmetic of one of those modules/functions (cited as file:line in
+ * the reference checkout); onnx_image_processing_b200/ re-creates the nn.Module surface on top
+ * of these calls via ctypes + torch.library custom ops.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name starts with h_; tensors are dense,
+ *    row-major, float32 unless stated; images are (B,1,H,W) == (B,H,W).
+ *  - keypoints are (B,K,2) float32 in (y,x) order, (-1,-1) for padding entries
+ *    (utils/keypoint_utils.py:104-114).
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise,
+ *    never allocate: scratch memory comes from the caller (`ws`, size from the matching
+ *    *_workspace_bytes function).  They are CUDA-graph capturable.
+ *  - return value: OM_OK, an OM_ERR_* argument error, or OM_ERR_CUDA_BASE + cudaError_t.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef OM_B200_H
+#define OM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OM_OK 0
+#define OM_ERR_NULL 1        /* required pointer is NULL */
+#define OM_ERR_SHAPE 2       /* non-positive or inconsistent sizes, K > H*W, ... */
+#define OM_ERR_PARAM 3       /* unsupported parameter value (block size, radius, num_pairs, mode) */
+#define OM_ERR_WORKSPACE 4   /* ws is NULL or smaller than *_workspace_bytes reports */
+#define OM_ERR_LIMIT 5       /* size beyond an implementation limit (documented per call) */
+#define OM_ERR_CUDA_BASE 1000
+
+/* descriptor post-processing, descriptor/bad.py:214-218 and :562-567 */
+#define OM_DESC_RAW 0        /* centered = diff - threshold */
+#define OM_DESC_SOFT 1       /* sigmoid(-centered * temperature) */
+#define OM_DESC_HARD 2       /* (centered <= 0) as 0/1 */
+
+/* sampling of the box-average bank, descriptor/bad.py:538-551 */
+#define OM_SAMPLE_NEAREST 0
+#define OM_SAMPLE_BILINEAR 1
+
+/* where SparseBAD takes the keypoint orientation from */
+#define OM_THETA_NONE 0      /* non-oriented, descriptor/bad.py:518-525 */
+#define OM_THETA_MAP 1       /* nearest sample of a (B,H,W) orientation map, descriptor/bad.py:487-499 */
+#define OM_THETA_MOMENTS 2   /* evaluate orientation/angle_estimation.py:161-170 at the keypoints only */
+
+/* matcher flavours of om_match_pairs_f32 */
+#define OM_MATCH_SPARSE 0    /* feature_detection/shi_tomasi_sparse_bad_sinkhorn.py:134-182 */
+#define OM_MATCH_ANGLE 1     /* feature_detection/shi_tomasi_angle_sparse_bad_sinkhorn.py:132-180 */
+#define OM_MATCH_DENSE 2     /* feature_detection/shi_tomasi_bad_sinkhorn.py:162-219 */
+
+int om_version(void);
+/* The library links its own (static) CUDA runtime: select the device the caller's pointers and
+ * stream belong to before the first call on a thread (one process per GPU: once, at start-up). */
+int om_set_device(int device);
+const char* om_error_string(int status);
+/* Number of kernels launched by this library since load (all streams); bench.py reads it. */
+unsigned long long om_launch_count(void);
+
+/* Host-side copy of the learned BAD tables (descriptor/bad_params.py:4-1568).  h_boxes gets
+ * num_pairs*5 signed bytes {x1-16,x2-16,y1-16,y2-16,radius}; h_thresholds num_pairs floats. */
+int om_bad_table(int num_pairs, signed char* h_boxes, float* h_thresholds);
+
+/* ---- detector ---------------------------------------------------------------------------- */
+
+/* ShiTomasiScore.forward, detector/shi_tomasi.py:66-112.  block_size odd in [1,9]. */
+int om_shi_tomasi_score_f32(const float* image, int B, int H, int W, int block_size,
+                            float* score_map, void* stream);
+
+/* apply_nms_maxpool, utils/keypoint_utils.py:12-44.  nms_radius in [0,8]. mask is 0/1 floats. */
+int om_nms_mask_f32(const float* scores, int B, int H, int W, int nms_radius,
+                    float* mask, void* stream);
+
+size_t om_topk_workspace_bytes(int B, int H, int W, int K);
+
+/* select_topk_keypoints, utils/keypoint_utils.py:47-117, on caller-provided scores and mask.
+ * Ties between equal scores go to the lower flat index; output is sorted by descending score.
+ * Limit: K <= 16384. */
+int om_select_topk_f32(const float* scores, const float* mask, int B, int H, int W, int K,
+                       float score_threshold, int border_margin,
+                       float* kpts, float* kpt_scores, void* ws, size_t ws_bytes, void* stream);
+
+/* Fused ShiTomasiScore + apply_nms_maxpool + select_topk_keypoints (the three calls at
+ * feature_detection/shi_tomasi_sparse_bad_sinkhorn.py:156-173) without materialising the score
+ * or mask maps.  score_map may be NULL; if given it receives the full (B,H,W) score map.
+ * Workspace: om_topk_workspace_bytes. */
+int om_detect_f32(const float* image, int B, int H, int W, int block_size, int nms_radius,
+                  int border_margin, float score_threshold, int K,
+                  float* score_map, float* kpts, float* kpt_scores,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- orientation ------------------------------------------------------------------------- */
+
+/* AngleEstimator.forward, orientation/angle_estimation.py:123-172.  moment_kernels is the
+ * module's (2,1,ps,ps) buffer (x*g, y*g); patch_size odd <= 31.  Zero padding. */
+int om_angle_map_f32(const float* image, int B, int H, int W, const float* moment_kernels,
+                     int patch_size, float* angle_map, void* stream);
+
+/* ---- descriptors ------------------------------------------------------------------------- */
+
+/* pair_table: (P,6) floats {ox1, ox2, oy1, oy2, radius, threshold}, offsets relative to the
+ * keypoint (descriptor/bad.py:405-410), integer-valued, |offset| <= 15, radius in [0,7]. */
+
+/* SparseBAD.forward, descriptor/bad.py:436-576.  theta_mode selects the oriented branch
+ * (:487-517); `orientation` is the (B,H,W) map for OM_THETA_MAP; moment_kernels/patch_size are
+ * used by OM_THETA_MOMENTS (same result as running AngleEstimator on the whole image first). */
+int om_sparse_bad_f32(const float* image, int B, int H, int W, const float* kpts, int K,
+                      const float* pair_table, int P, int desc_mode, float temperature,
+                      int normalize, int sampling_mode,
+                      int theta_mode, const float* orientation,
+                      const float* moment_kernels, int patch_size,
+                      float* desc /* B,K,P */, void* stream);
+
+size_t om_dense_bad_workspace_bytes(int B, int H, int W);
+
+/* BADDescriptor.forward (non-oriented), descriptor/bad.py:62-110 and :189-218: the dense
+ * (B,P,H,W) map.  Emulates the reference's float32 integral image (double-accumulated cumsum,
+ * rounded once per pass) and its 4-tap order. */
+int om_dense_bad_f32(const float* image, int B, int H, int W, const float* pair_table, int P,
+                     int desc_mode, float temperature, float* desc_map /* B,P,H,W */,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* Dense BAD evaluated only where the dense matcher consumes it: bilinear gather at K keypoints,
+ * validity mask and optional L2 normalisation (descriptor/bad.py:277-333,
+ * feature_detection/shi_tomasi_bad_sinkhorn.py:120-160 and :212-214). */
+int om_dense_bad_at_kpts_f32(const float* image, int B, int H, int W, const float* kpts, int K,
+                             const float* pair_table, int P, int desc_mode, float temperature,
+                             int normalize, float* desc /* B,K,P */,
+                             void* ws, size_t ws_bytes, void* stream);
+
+/* extract_descriptors_at_keypoints (integer gather, descriptor/bad.py:221-274, subpixel=0) and
+ * extract_descriptors_at_keypoints_subpixel (bilinear, :277-333, subpixel=1) on a caller map. */
+int om_gather_descriptors_f32(const float* desc_map, int B, int D, int H, int W,
+                              const float* kpts, int K, int subpixel,
+                              float* desc /* B,K,D */, void* stream);
+
+/* ---- matching ---------------------------------------------------------------------------- */
+
+size_t om_sinkhorn_workspace_bytes(int B, int N, int M, int D);
+
+/* SinkhornMatcher.forward, matching/sinkhorn.py:149-208 (cost matrix :79-110, log-domain
+ * iterations :112-147).  distance_l1 = 0 -> squared L2, 1 -> L1.  P is (B,N+1,M+1). */
+int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M, int D,
+                    int iterations, float epsilon, float unused_score, int distance_l1,
+                    float* P, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused matcher ----------------------------------------------------------------------- */
+
+typedef struct om_match_params {
+    int flavour;            /* OM_MATCH_* */
+    int B, H, W, K;         /* pairs, image size, max_keypoints */
+    int block_size;         /* 3 (sparse/dense default) or 5 (angle default) */
+    int nms_radius;
+    int border_margin;      /* already resolved (None -> descriptor max radius = 7; dense: 0) */
+    float score_threshold;
+    int P;                  /* num_pairs: 256 or 512 */
+    int desc_mode;          /* OM_DESC_* */
+    float temperature;
+    int normalize;
+    int sampling_mode;      /* OM_SAMPLE_* (sparse/angle only) */
+    int patch_size;         /* angle only */
+    int iterations;
+    float epsilon;
+    float unused_score;
+    int distance_l1;
+} om_match_params;
+
+size_t om_match_workspace_bytes(const om_match_params* p);
+
+/* The whole forward of the three unified matcher modules: images in, (kpts1, kpts2, P) out.
+ * desc1/desc2 (B,K,P) are optional outputs (NULL: kept in the workspace only). */
+int om_match_pairs_f32(const om_match_params* p, const float* image1, const float* image2,
+                       const float* pair_table, const float* moment_kernels,
+                       float* kpts1, float* kpts2, float* probs /* B,K+1,K+1 */,
+                       float* desc1, float* desc2,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- test hooks ---------------------------------------------------------------------------- */
+
+/* Route every stencil launch through the generic (runtime block size / radius) kernel instead of
+ * the compile-time specialised one; lets the tests check the two against each other. */
+void om_debug_force_generic_stencil(int on);
+
+/* Route om_sinkhorn_f32 / the fused matcher through the generic global-memory Sinkhorn kernels
+ * instead of the cluster kernel. */
+void om_debug_force_generic_sinkhorn(int on);
+
+/* Single-kernel slices of om_detect_f32 / om_dense_bad_at_kpts_f32 so that bench.py can time each
+ * kernel with CUDA events.  stage 0 = first kernel(s), stage 1 = the last kernel (needs stage 0's
+ * workspace contents). */
+int om_debug_detect_stage(const float* image, int B, int H, int W, int block_size, int nms_radius,
+                          int border_margin, float score_threshold, int K, float* kpts, float* kpt_scores,
+                          void* ws, size_t ws_bytes, void* stream, int stage);
+int om_debug_dense_stage(const float* image, int B, int H, int W, const float* kpts, int K,
+                         const float* pair_table, int P, int desc_mode, float temperature, int normalize,
+                         float* desc, void* ws, size_t ws_bytes, void* stream, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OM_B200_H */

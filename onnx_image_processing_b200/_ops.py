@@ -1,0 +1,315 @@
+"""torch custom ops (namespace ``b200match``) over the C ABI of libom_b200.so.
+
+Each op passes raw device pointers and the current CUDA stream to one ``om_*`` entry point of
+include/om_b200.h.  The ops are registered for CUDA only: calling them with CPU tensors raises,
+there is no CPU implementation behind them.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as nat
+
+DESC_RAW, DESC_SOFT, DESC_HARD = 0, 1, 2
+SAMPLE_NEAREST, SAMPLE_BILINEAR = 0, 1
+THETA_NONE, THETA_MAP, THETA_MOMENTS = 0, 1, 2
+MATCH_SPARSE, MATCH_ANGLE, MATCH_DENSE = 0, 1, 2
+
+
+def desc_mode(binarize: bool, soft_binarize: bool) -> int:
+    if not binarize:
+        return DESC_RAW
+    return DESC_SOFT if soft_binarize else DESC_HARD
+
+
+def sampling_code(mode: str) -> int:
+    return SAMPLE_BILINEAR if mode == "bilinear" else SAMPLE_NEAREST
+
+
+def _f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: onnx_image_processing_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _begin(t: torch.Tensor):
+    nat.use_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return nat.lib(), ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ws(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _images(image: torch.Tensor, what: str) -> Tuple[torch.Tensor, int, int, int]:
+    if image.dim() == 4:
+        if image.shape[1] != 1:
+            raise RuntimeError(f"{what}: expected (B,1,H,W), got {tuple(image.shape)}")
+        B, _, H, W = image.shape
+    elif image.dim() == 3:
+        B, H, W = image.shape
+    else:
+        raise RuntimeError(f"{what}: expected (B,1,H,W) or (B,H,W), got {tuple(image.shape)}")
+    return _f32(image, what), B, H, W
+
+
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op("b200match::shi_tomasi_score", mutates_args=(), device_types="cuda")
+def shi_tomasi_score(image: torch.Tensor, block_size: int) -> torch.Tensor:
+    img, B, H, W = _images(image, "image")
+    lib, st = _begin(img)
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=img.device)
+    nat.check(lib.om_shi_tomasi_score_f32(_p(img), B, H, W, block_size, _p(out), st), "om_shi_tomasi_score_f32")
+    return out
+
+
+@shi_tomasi_score.register_fake
+def _(image, block_size):
+    return image.new_empty((image.shape[0], 1, image.shape[-2], image.shape[-1]), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::nms_mask", mutates_args=(), device_types="cuda")
+def nms_mask(scores: torch.Tensor, nms_radius: int) -> torch.Tensor:
+    sc, B, H, W = _images(scores, "scores")
+    lib, st = _begin(sc)
+    out = torch.empty((B, H, W), dtype=torch.float32, device=sc.device)
+    nat.check(lib.om_nms_mask_f32(_p(sc), B, H, W, nms_radius, _p(out), st), "om_nms_mask_f32")
+    return out
+
+
+@nms_mask.register_fake
+def _(scores, nms_radius):
+    return scores.new_empty(tuple(scores.shape), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::select_topk", mutates_args=(), device_types="cuda")
+def select_topk(scores: torch.Tensor, mask: torch.Tensor, max_keypoints: int, score_threshold: float,
+                border_margin: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    sc, B, H, W = _images(scores, "scores")
+    mk = _f32(mask, "nms_mask")
+    if mk.numel() != sc.numel():
+        raise RuntimeError("scores and nms_mask must have the same number of elements")
+    if max_keypoints > H * W:
+        raise RuntimeError("selected index k out of range")   # what torch.topk raises in the reference
+    lib, st = _begin(sc)
+    K = max_keypoints
+    kpts = torch.empty((B, K, 2), dtype=torch.float32, device=sc.device)
+    ks = torch.empty((B, K), dtype=torch.float32, device=sc.device)
+    nbytes = lib.om_topk_workspace_bytes(B, H, W, K)
+    ws = _ws(nbytes, sc)
+    nat.check(lib.om_select_topk_f32(_p(sc), _p(mk), B, H, W, K, float(score_threshold), int(border_margin), _p(kpts),
+                                     _p(ks), _p(ws), ws.numel(), st), "om_select_topk_f32")
+    return kpts, ks
+
+
+@select_topk.register_fake
+def _(scores, mask, max_keypoints, score_threshold, border_margin):
+    B = scores.shape[0]
+    return (scores.new_empty((B, max_keypoints, 2), dtype=torch.float32),
+            scores.new_empty((B, max_keypoints), dtype=torch.float32))
+
+
+@torch.library.custom_op("b200match::detect", mutates_args=(), device_types="cuda")
+def detect(image: torch.Tensor, max_keypoints: int, block_size: int, nms_radius: int, score_threshold: float,
+           border_margin: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    img, B, H, W = _images(image, "image")
+    if max_keypoints > H * W:
+        raise RuntimeError("selected index k out of range")
+    lib, st = _begin(img)
+    K = max_keypoints
+    kpts = torch.empty((B, K, 2), dtype=torch.float32, device=img.device)
+    ks = torch.empty((B, K), dtype=torch.float32, device=img.device)
+    ws = _ws(lib.om_topk_workspace_bytes(B, H, W, K), img)
+    nat.check(lib.om_detect_f32(_p(img), B, H, W, block_size, nms_radius, int(border_margin), float(score_threshold),
+                                K, _p(None), _p(kpts), _p(ks), _p(ws), ws.numel(), st), "om_detect_f32")
+    return kpts, ks
+
+
+@detect.register_fake
+def _(image, max_keypoints, block_size, nms_radius, score_threshold, border_margin):
+    B = image.shape[0]
+    return (image.new_empty((B, max_keypoints, 2), dtype=torch.float32),
+            image.new_empty((B, max_keypoints), dtype=torch.float32))
+
+
+@torch.library.custom_op("b200match::angle_map", mutates_args=(), device_types="cuda")
+def angle_map(image: torch.Tensor, moment_kernels: torch.Tensor) -> torch.Tensor:
+    img, B, H, W = _images(image, "image")
+    mk = _f32(moment_kernels, "moment_kernels")
+    ps = int(mk.shape[-1])
+    lib, st = _begin(img)
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=img.device)
+    nat.check(lib.om_angle_map_f32(_p(img), B, H, W, _p(mk), ps, _p(out), st), "om_angle_map_f32")
+    return out
+
+
+@angle_map.register_fake
+def _(image, moment_kernels):
+    return image.new_empty((image.shape[0], 1, image.shape[-2], image.shape[-1]), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::sparse_bad", mutates_args=(), device_types="cuda")
+def sparse_bad(image: torch.Tensor, keypoints: torch.Tensor, pair_table: torch.Tensor, mode: int, temperature: float,
+               normalize: bool, sampling: int, theta_mode: int, orientation: Optional[torch.Tensor],
+               moment_kernels: Optional[torch.Tensor]) -> torch.Tensor:
+    img, B, H, W = _images(image, "image")
+    kp = _f32(keypoints, "keypoints")
+    tb = _f32(pair_table, "pair_table")
+    K, P = int(kp.shape[1]), int(tb.shape[0])
+    ori = _f32(orientation, "orientation") if orientation is not None else None
+    mk = _f32(moment_kernels, "moment_kernels") if moment_kernels is not None else None
+    ps = int(mk.shape[-1]) if mk is not None else 0
+    lib, st = _begin(img)
+    out = torch.empty((B, K, P), dtype=torch.float32, device=img.device)
+    nat.check(lib.om_sparse_bad_f32(_p(img), B, H, W, _p(kp), K, _p(tb), P, mode, float(temperature), int(normalize),
+                                    sampling, theta_mode, _p(ori), _p(mk), ps, _p(out), st), "om_sparse_bad_f32")
+    return out
+
+
+@sparse_bad.register_fake
+def _(image, keypoints, pair_table, mode, temperature, normalize, sampling, theta_mode, orientation, moment_kernels):
+    return image.new_empty((keypoints.shape[0], keypoints.shape[1], pair_table.shape[0]), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::dense_bad", mutates_args=(), device_types="cuda")
+def dense_bad(image: torch.Tensor, pair_table: torch.Tensor, mode: int, temperature: float) -> torch.Tensor:
+    img, B, H, W = _images(image, "image")
+    tb = _f32(pair_table, "pair_table")
+    P = int(tb.shape[0])
+    lib, st = _begin(img)
+    out = torch.empty((B, P, H, W), dtype=torch.float32, device=img.device)
+    ws = _ws(lib.om_dense_bad_workspace_bytes(B, H, W), img)
+    nat.check(lib.om_dense_bad_f32(_p(img), B, H, W, _p(tb), P, mode, float(temperature), _p(out), _p(ws), ws.numel(),
+                                   st), "om_dense_bad_f32")
+    return out
+
+
+@dense_bad.register_fake
+def _(image, pair_table, mode, temperature):
+    return image.new_empty((image.shape[0], pair_table.shape[0], image.shape[-2], image.shape[-1]), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::dense_bad_at_keypoints", mutates_args=(), device_types="cuda")
+def dense_bad_at_keypoints(image: torch.Tensor, keypoints: torch.Tensor, pair_table: torch.Tensor, mode: int,
+                           temperature: float, normalize: bool) -> torch.Tensor:
+    img, B, H, W = _images(image, "image")
+    kp = _f32(keypoints, "keypoints")
+    tb = _f32(pair_table, "pair_table")
+    K, P = int(kp.shape[1]), int(tb.shape[0])
+    lib, st = _begin(img)
+    out = torch.empty((B, K, P), dtype=torch.float32, device=img.device)
+    ws = _ws(lib.om_dense_bad_workspace_bytes(B, H, W), img)
+    nat.check(lib.om_dense_bad_at_kpts_f32(_p(img), B, H, W, _p(kp), K, _p(tb), P, mode, float(temperature),
+                                           int(normalize), _p(out), _p(ws), ws.numel(), st),
+              "om_dense_bad_at_kpts_f32")
+    return out
+
+
+@dense_bad_at_keypoints.register_fake
+def _(image, keypoints, pair_table, mode, temperature, normalize):
+    return image.new_empty((keypoints.shape[0], keypoints.shape[1], pair_table.shape[0]), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::gather_descriptors", mutates_args=(), device_types="cuda")
+def gather_descriptors(descriptor_map: torch.Tensor, keypoints: torch.Tensor, subpixel: bool) -> torch.Tensor:
+    dm = _f32(descriptor_map, "descriptor_map")
+    kp = _f32(keypoints, "keypoints")
+    B, D, H, W = dm.shape
+    K = int(kp.shape[1])
+    lib, st = _begin(dm)
+    out = torch.empty((B, K, D), dtype=torch.float32, device=dm.device)
+    nat.check(lib.om_gather_descriptors_f32(_p(dm), B, D, H, W, _p(kp), K, int(subpixel), _p(out), st),
+              "om_gather_descriptors_f32")
+    return out
+
+
+@gather_descriptors.register_fake
+def _(descriptor_map, keypoints, subpixel):
+    return descriptor_map.new_empty((keypoints.shape[0], keypoints.shape[1], descriptor_map.shape[1]),
+                                    dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::sinkhorn", mutates_args=(), device_types="cuda")
+def sinkhorn(desc1: torch.Tensor, desc2: torch.Tensor, iterations: int, epsilon: float, unused_score: float,
+             distance_l1: bool) -> torch.Tensor:
+    d1 = _f32(desc1, "desc1")
+    d2 = _f32(desc2, "desc2")
+    B, N, D = d1.shape
+    M = int(d2.shape[1])
+    if d2.shape[0] != B or d2.shape[2] != D:
+        raise RuntimeError(f"descriptor shapes do not match: {tuple(d1.shape)} vs {tuple(d2.shape)}")
+    lib, st = _begin(d1)
+    out = torch.empty((B, N + 1, M + 1), dtype=torch.float32, device=d1.device)
+    ws = _ws(lib.om_sinkhorn_workspace_bytes(B, N, M, D), d1)
+    nat.check(lib.om_sinkhorn_f32(_p(d1), _p(d2), B, N, M, D, iterations, float(epsilon), float(unused_score),
+                                  int(distance_l1), _p(out), _p(ws), ws.numel(), st), "om_sinkhorn_f32")
+    return out
+
+
+@sinkhorn.register_fake
+def _(desc1, desc2, iterations, epsilon, unused_score, distance_l1):
+    return desc1.new_empty((desc1.shape[0], desc1.shape[1] + 1, desc2.shape[1] + 1), dtype=torch.float32)
+
+
+def make_match_params(flavour: int, B: int, H: int, W: int, K: int, block_size: int, nms_radius: int,
+                      border_margin: int, score_threshold: float, P: int, mode: int, temperature: float,
+                      normalize: bool, sampling: int, patch_size: int, iterations: int, epsilon: float,
+                      unused_score: float, distance_l1: bool) -> nat.MatchParams:
+    return nat.MatchParams(flavour, B, H, W, K, block_size, nms_radius, border_margin, score_threshold, P, mode,
+                           temperature, int(normalize), sampling, patch_size, iterations, epsilon, unused_score,
+                           int(distance_l1))
+
+
+@torch.library.custom_op("b200match::match_pairs", mutates_args=(), device_types="cuda")
+def match_pairs(image1: torch.Tensor, image2: torch.Tensor, pair_table: torch.Tensor,
+                moment_kernels: Optional[torch.Tensor], flavour: int, max_keypoints: int, block_size: int,
+                nms_radius: int, border_margin: int, score_threshold: float, mode: int, temperature: float,
+                normalize: bool, sampling: int, iterations: int, epsilon: float, unused_score: float,
+                distance_l1: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Whole matcher forward in one C call: (kpts1, kpts2, probs, desc1, desc2)."""
+    i1, B, H, W = _images(image1, "image1")
+    i2, B2, H2, W2 = _images(image2, "image2")
+    if (B, H, W) != (B2, H2, W2):
+        raise RuntimeError("image1 and image2 must have the same shape")
+    K = max_keypoints
+    if K > H * W:
+        raise RuntimeError("selected index k out of range")
+    tb = _f32(pair_table, "pair_table")
+    P = int(tb.shape[0])
+    mk = _f32(moment_kernels, "moment_kernels") if moment_kernels is not None else None
+    ps = int(mk.shape[-1]) if mk is not None else 0
+    lib, st = _begin(i1)
+    prm = make_match_params(flavour, B, H, W, K, block_size, nms_radius, border_margin, score_threshold, P, mode,
+                            temperature, normalize, sampling, ps, iterations, epsilon, unused_score, distance_l1)
+    dev = i1.device
+    k1 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    k2 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, K + 1, K + 1), dtype=torch.float32, device=dev)
+    d1 = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+    d2 = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+    nbytes = lib.om_match_workspace_bytes(ctypes.byref(prm))
+    if nbytes == 0:
+        raise RuntimeError("om_match_workspace_bytes rejected the parameters")
+    ws = _ws(nbytes, i1)
+    nat.check(lib.om_match_pairs_f32(ctypes.byref(prm), _p(i1), _p(i2), _p(tb), _p(mk), _p(k1), _p(k2), _p(probs),
+                                     _p(d1), _p(d2), _p(ws), ws.numel(), st), "om_match_pairs_f32")
+    return k1, k2, probs, d1, d2
+
+
+@match_pairs.register_fake
+def _(image1, image2, pair_table, moment_kernels, flavour, max_keypoints, block_size, nms_radius, border_margin,
+      score_threshold, mode, temperature, normalize, sampling, iterations, epsilon, unused_score, distance_l1):
+    B, K, P = image1.shape[0], max_keypoints, pair_table.shape[0]
+    f = dict(dtype=torch.float32)
+    return (image1.new_empty((B, K, 2), **f), image1.new_empty((B, K, 2), **f),
+            image1.new_empty((B, K + 1, K + 1), **f), image1.new_empty((B, K, P), **f),
+            image1.new_empty((B, K, P), **f))

@@ -1,0 +1,126 @@
+// Library-level entry points: version, error strings, launch counter, BAD tables, and the fused
+// matcher that chains the stage launchers on one stream (no host synchronisation in between).
+#include <string.h>
+
+#include "bad_tables.inc"
+#include "common.cuh"
+
+namespace om {
+unsigned long long g_launches = 0;
+}
+
+using namespace om;
+
+extern "C" int om_version(void) { return 100; }
+
+extern "C" int om_set_device(int device) {
+    OM_CUDA(cudaSetDevice(device));
+    return OM_OK;
+}
+
+extern "C" unsigned long long om_launch_count(void) { return __atomic_load_n(&om::g_launches, __ATOMIC_RELAXED); }
+
+extern "C" const char* om_error_string(int status) {
+    switch (status) {
+        case OM_OK: return "ok";
+        case OM_ERR_NULL: return "required pointer is NULL";
+        case OM_ERR_SHAPE: return "invalid or inconsistent sizes";
+        case OM_ERR_PARAM: return "unsupported parameter value";
+        case OM_ERR_WORKSPACE: return "workspace missing or too small";
+        case OM_ERR_LIMIT: return "size beyond an implementation limit";
+        default: break;
+    }
+    if (status >= OM_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(status - OM_ERR_CUDA_BASE));
+    return "unknown status";
+}
+
+extern "C" int om_bad_table(int num_pairs, signed char* h_boxes, float* h_thresholds) {
+    if (h_boxes == nullptr || h_thresholds == nullptr) return OM_ERR_NULL;
+    if (num_pairs == 256) {
+        memcpy(h_boxes, OM_BAD_BOX_256, sizeof(OM_BAD_BOX_256));
+        memcpy(h_thresholds, OM_BAD_THR_256, sizeof(OM_BAD_THR_256));
+        return OM_OK;
+    }
+    if (num_pairs == 512) {
+        memcpy(h_boxes, OM_BAD_BOX_512, sizeof(OM_BAD_BOX_512));
+        memcpy(h_thresholds, OM_BAD_THR_512, sizeof(OM_BAD_THR_512));
+        return OM_OK;
+    }
+    return OM_ERR_PARAM;   // descriptor/bad_params.py:1565 raises ValueError
+}
+
+namespace {
+
+struct MatchWs {
+    void* detect;  size_t detect_bytes;
+    float* desc1;  float* desc2;
+    void* dense;   size_t dense_bytes;
+    void* sink;    size_t sink_bytes;
+    size_t total;
+};
+
+int check_params(const om_match_params* p) {
+    if (p == nullptr) return OM_ERR_NULL;
+    if (p->flavour < OM_MATCH_SPARSE || p->flavour > OM_MATCH_DENSE) return OM_ERR_PARAM;
+    if (p->B <= 0 || p->H <= 1 || p->W <= 1 || p->K <= 0) return OM_ERR_SHAPE;
+    if (p->P != 256 && p->P != 512) return OM_ERR_PARAM;                 // descriptor/bad.py:385-388
+    return OM_OK;
+}
+
+MatchWs plan(const om_match_params* p, void* base) {
+    MatchWs w{};
+    char* c = (char*)base;
+    size_t off = 0;
+    w.detect_bytes = topk_workspace_bytes(p->B, p->H, p->W, p->K);
+    w.detect = c + off; off += align_up(w.detect_bytes);
+    const size_t db = align_up((size_t)p->B * p->K * p->P * sizeof(float));
+    w.desc1 = (float*)(c + off); off += db;
+    w.desc2 = (float*)(c + off); off += db;
+    w.dense_bytes = p->flavour == OM_MATCH_DENSE ? dense_bad_workspace_bytes(p->B, p->H, p->W) : 0;
+    w.dense = c + off; off += align_up(w.dense_bytes);
+    w.sink_bytes = sinkhorn_workspace_bytes(p->B, p->K, p->K, p->P);
+    w.sink = c + off; off += align_up(w.sink_bytes);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
+    if (check_params(p) != OM_OK) return 0;
+    return plan(p, nullptr).total;
+}
+
+extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1, const float* image2,
+                                  const float* pair_table, const float* moment_kernels, float* kpts1, float* kpts2,
+                                  float* probs, float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream) {
+    OM_TRY(check_params(p));
+    if (image1 == nullptr || image2 == nullptr || pair_table == nullptr || kpts1 == nullptr || kpts2 == nullptr ||
+        probs == nullptr)
+        return OM_ERR_NULL;
+    if (p->flavour == OM_MATCH_ANGLE && moment_kernels == nullptr) return OM_ERR_NULL;
+    if (ws == nullptr || ws_bytes < plan(p, nullptr).total) return OM_ERR_WORKSPACE;
+    const MatchWs w = plan(p, ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d1 = desc1 ? desc1 : w.desc1;
+    float* d2 = desc2 ? desc2 : w.desc2;
+    const DetectCfg dc{p->B, p->H, p->W, p->block_size, p->nms_radius, p->border_margin, p->score_threshold, p->K};
+    const float* images[2] = {image1, image2};
+    float* kp[2] = {kpts1, kpts2};
+    float* ds[2] = {d1, d2};
+    for (int s = 0; s < 2; ++s) {
+        // keypoint scores are discarded by the matcher modules (`keypoints1, _ = ...`)
+        OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect, w.detect_bytes, st));
+        if (p->flavour == OM_MATCH_DENSE) {
+            OM_TRY(dense_bad_at_kpts_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
+                                            p->temperature, p->normalize, ds[s], w.dense, w.dense_bytes, st));
+        } else {
+            const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
+            OM_TRY(sparse_bad_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
+                                     p->temperature, p->normalize, p->sampling_mode, theta, nullptr, moment_kernels,
+                                     p->patch_size, ds[s], st));
+        }
+    }
+    return sinkhorn_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
+                           probs, w.sink, w.sink_bytes, st);
+}

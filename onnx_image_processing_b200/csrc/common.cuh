@@ -1,0 +1,84 @@
+// Shared host/device helpers for libom_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/om_b200.h"
+
+namespace om {
+
+extern unsigned long long g_launches;  // defined in api.cu
+
+inline void count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+
+#define OM_CUDA(expr)                                                      \
+    do {                                                                   \
+        cudaError_t e__ = (expr);                                          \
+        if (e__ != cudaSuccess) return OM_ERR_CUDA_BASE + (int)e__;        \
+    } while (0)
+
+// after every <<<>>>: count the launch and surface configuration errors immediately
+#define OM_AFTER_LAUNCH()                                                  \
+    do {                                                                   \
+        om::count_launch();                                                \
+        cudaError_t e__ = cudaGetLastError();                              \
+        if (e__ != cudaSuccess) return OM_ERR_CUDA_BASE + (int)e__;        \
+    } while (0)
+
+#define OM_TRY(expr)                                                       \
+    do {                                                                   \
+        int s__ = (expr);                                                  \
+        if (s__ != OM_OK) return s__;                                      \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <typename K>
+inline int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return OM_ERR_CUDA_BASE + (int)e;
+    }
+    return OM_OK;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- internal stage launchers shared between the per-stage C ABI and the fused matcher -------
+struct DetectCfg {
+    int B, H, W;
+    int block_size, nms_radius, border_margin;
+    float score_threshold;
+    int K;
+};
+
+size_t topk_workspace_bytes(int B, int H, int W, int K);
+int detect_launch(const float* image, const DetectCfg& c, float* score_map, float* kpts, float* kpt_scores,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+
+int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
+                      int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
+                      const float* orientation, const float* moment_kernels, int patch_size, float* desc,
+                      cudaStream_t st);
+
+size_t dense_bad_workspace_bytes(int B, int H, int W);
+int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const float* kpts, int K,
+                             const float* pair_table, int P, int desc_mode, float temperature, int normalize,
+                             float* desc, void* ws, size_t ws_bytes, cudaStream_t st);
+
+size_t sinkhorn_workspace_bytes(int B, int N, int M, int D);
+int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
+                    float unused_score, int distance_l1, float* P, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace om

@@ -1,0 +1,529 @@
+// Matching stage: descriptor cost matrix + log-domain Sinkhorn with dustbins.
+//
+// Replaces matching/sinkhorn.py:149-208 (cost matrix :79-110, iterations :112-147).
+//
+// Two implementations of the same arithmetic:
+//
+//  * cluster path (sinkhorn_cluster_kernel): one 8-CTA thread-block cluster per descriptor pair.
+//    Each CTA computes a 64-row slab of the similarity GEMM with FP32 FFMA straight into its
+//    shared memory, so the (N+1)x(M+1) score matrix lives only in the cluster's distributed shared
+//    memory for all iterations.  Row updates are CTA-local; column updates exchange one partial
+//    sum per column per CTA through DSMEM (st to the peers' shared memory + one cluster barrier
+//    per iteration).  Only P is written to HBM.
+//    The duals are kept in the log domain (base 2), and every logsumexp is shifted by the dual
+//    of the previous half-step instead of by the running maximum:
+//        LSE_j(S_ij + v_j) = -u_i + log sum_j exp(S_ij + u_i + v_j)
+//    After the first half-step every such exponent is the log of an entry of a row- or
+//    column-normalised plan, hence bounded by log(N+M): no overflow, and the sums are bounded
+//    below by 1/(N+M): no underflow.  The same exponentials, rescaled by mu_i/rowsum_i, are the
+//    terms of the following column sum, so one exp per matrix entry per iteration suffices.
+//    Rows whose sum leaves [1e-30, 1e30] (first half-step with a huge unused_score/epsilon) are
+//    redone with the classic max shift.
+//    Limits: squared-L2 cost, N <= 512, M <= 512, D % 16 == 0.
+//
+//  * generic path (separate kernels, score matrix in the P buffer in global memory, classic
+//    max-shifted logsumexp): any N, M, D, L1 or L2 cost.  Used beyond the limits above
+//    (e.g. K = 2048) and as an in-library cross-check.
+#include <cooperative_groups.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace om {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// generic path
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* d, long long rows, int D, float* out) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* p = d + row * D;
+    float acc = 0.0f;
+    for (int k = threadIdx.x & 31; k < D; k += 32) acc = fmaf(p[k], p[k], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) out[row] = acc;
+}
+
+// S[b][i][j] = -clamp(n1_i + n2_j - 2 a_i.b_j, 0) / eps for i<N, j<M; dustbin elsewhere (sinkhorn.py:98-103, :178-187)
+__global__ void __launch_bounds__(256) cost_l2_kernel(const float* d1, const float* d2, const float* n1, const float* n2,
+                                                      int N, int M, int D, float eps, float dustbin, float* S) {
+    __shared__ __align__(16) float As[16][68];
+    __shared__ __align__(16) float Bs[16][68];
+    const int z = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const float* A = d1 + (size_t)z * N * D;
+    const float* Bm = d2 + (size_t)z * M * D;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < D; k0 += 16) {
+        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+            const int r = e / 16, k = e % 16;
+            As[k][r] = (i0 + r < N && k0 + k < D) ? A[(size_t)(i0 + r) * D + k0 + k] : 0.0f;
+            Bs[k][r] = (j0 + r < M && k0 + k < D) ? Bm[(size_t)(j0 + r) * D + k0 + k] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+    float* Sz = S + (size_t)z * (N + 1) * (M + 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty * 4 + r;
+        if (i > N) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx * 4 + c;
+            if (j > M) continue;
+            float v = dustbin;
+            if (i < N && j < M) {
+                const float cost = fmaxf(__fsub_rn(__fadd_rn(n1[(size_t)z * N + i], n2[(size_t)z * M + j]),
+                                                   __fmul_rn(2.0f, acc[r][c])), 0.0f);
+                v = __fdiv_rn(-cost, eps);
+            }
+            Sz[(size_t)i * (M + 1) + j] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cost_l1_kernel(const float* d1, const float* d2, int N, int M, int D, float eps,
+                                                      float dustbin, float* S) {
+    const int z = blockIdx.z;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i > N || j > M) return;
+    float v = dustbin;
+    if (i < N && j < M) {
+        const float* a = d1 + ((size_t)z * N + i) * D;
+        const float* b = d2 + ((size_t)z * M + j) * D;
+        float acc = 0.0f;
+        for (int k = 0; k < D; ++k) acc += fabsf(a[k] - b[k]);            // sinkhorn.py:106-108
+        v = __fdiv_rn(-acc, eps);
+    }
+    S[(size_t)z * (N + 1) * (M + 1) + (size_t)i * (M + 1) + j] = v;
+}
+
+// u_i = log_mu_i - logsumexp_j(S_ij + v_j)   (sinkhorn.py:140), one warp per row
+__global__ void __launch_bounds__(256) row_pass_kernel(const float* S, const float* v, float* u, int N, int M,
+                                                       float log_m) {
+    const int z = blockIdx.y;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i > N) return;
+    const float* row = S + (size_t)z * (N + 1) * (M + 1) + (size_t)i * (M + 1);
+    const float* vz = v + (size_t)z * (M + 1);
+    float m = -CUDART_INF_F;
+    for (int j = lane; j <= M; j += 32) m = fmaxf(m, row[j] + vz[j]);
+    m = warp_max(m);
+    float s = 0.0f;
+    for (int j = lane; j <= M; j += 32) s += expf((row[j] + vz[j]) - m);
+    s = warp_sum(s);
+    if (lane == 0) u[(size_t)z * (N + 1) + i] = (i == N ? log_m : 0.0f) - (logf(s) + m);
+}
+
+// v_j = log_nu_j - logsumexp_i(S_ij + u_i)   (sinkhorn.py:142); 32 columns x 8 row slices per CTA
+__global__ void __launch_bounds__(256) col_pass_kernel(const float* S, const float* u, float* v, int N, int M,
+                                                       float log_n) {
+    __shared__ float sm[8][32], ss[8][32];
+    const int z = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    const float* Sz = S + (size_t)z * (N + 1) * (M + 1);
+    const float* uz = u + (size_t)z * (N + 1);
+    float m = -CUDART_INF_F, s = 0.0f;
+    if (j <= M) {
+        for (int i = ty; i <= N; i += 8) {
+            const float t = Sz[(size_t)i * (M + 1) + j] + uz[i];
+            if (t > m) { s = s * expf(m - t) + 1.0f; m = t; }
+            else s += expf(t - m);
+        }
+    }
+    sm[ty][tx] = m;
+    ss[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j <= M) {
+        float mm = sm[0][tx];
+        for (int k = 1; k < 8; ++k) mm = fmaxf(mm, sm[k][tx]);
+        float tot = 0.0f;
+        for (int k = 0; k < 8; ++k)
+            if (ss[k][tx] > 0.0f) tot += ss[k][tx] * expf(sm[k][tx] - mm);
+        v[(size_t)z * (M + 1) + j] = (j == M ? log_n : 0.0f) - (logf(tot) + mm);
+    }
+}
+
+// P = exp(S + u + v) in place (sinkhorn.py:145, :206)
+__global__ void __launch_bounds__(256) finalize_kernel(float* S, const float* u, const float* v, int N, int M) {
+    const int z = blockIdx.y;
+    const size_t n = (size_t)(N + 1) * (M + 1);
+    float* Sz = S + (size_t)z * n;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (size_t)gridDim.x * 256) {
+        const int i = (int)(e / (M + 1)), j = (int)(e % (M + 1));
+        Sz[e] = expf((Sz[e] + u[(size_t)z * (N + 1) + i]) + v[(size_t)z * (M + 1) + j]);
+    }
+}
+
+struct SkWs {
+    float *n1, *n2, *u, *v;
+};
+
+SkWs carve_sk(void* ws, int B, int N, int M) {
+    SkWs w;
+    char* p = (char*)ws;
+    w.n1 = (float*)p; p += align_up((size_t)B * N * sizeof(float));
+    w.n2 = (float*)p; p += align_up((size_t)B * M * sizeof(float));
+    w.u = (float*)p;  p += align_up((size_t)B * (N + 1) * sizeof(float));
+    w.v = (float*)p;
+    return w;
+}
+
+int sinkhorn_generic(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
+                     float dustbin, int l1, float* P, void* ws, cudaStream_t st) {
+    const SkWs w = carve_sk(ws, B, N, M);
+    if (l1) {
+        cost_l1_kernel<<<dim3((M + 32) / 32, (N + 8) / 8, B), 256, 0, st>>>(d1, d2, N, M, D, eps, dustbin, P);
+        OM_AFTER_LAUNCH();
+    } else {
+        sqnorm_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, st>>>(d1, (long long)B * N, D, w.n1);
+        OM_AFTER_LAUNCH();
+        sqnorm_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(d2, (long long)B * M, D, w.n2);
+        OM_AFTER_LAUNCH();
+        cost_l2_kernel<<<dim3((M + 64) / 64, (N + 64) / 64, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, P);
+        OM_AFTER_LAUNCH();
+    }
+    OM_CUDA(cudaMemsetAsync(w.v, 0, (size_t)B * (M + 1) * sizeof(float), st));
+    const float log_m = (float)log((double)M), log_n = (float)log((double)N);       // sinkhorn.py:197-198
+    for (int it = 0; it < iterations; ++it) {
+        row_pass_kernel<<<dim3((N + 8) / 8, B), 256, 0, st>>>(P, w.v, w.u, N, M, log_m);
+        OM_AFTER_LAUNCH();
+        col_pass_kernel<<<dim3((M + 32) / 32, B), 256, 0, st>>>(P, w.u, w.v, N, M, log_n);
+        OM_AFTER_LAUNCH();
+    }
+    const size_t n = (size_t)(N + 1) * (M + 1);
+    finalize_kernel<<<dim3((unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), B), 256, 0, st>>>(P, w.u, w.v, N, M);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// cluster path
+// ------------------------------------------------------------------------------------------
+constexpr int CL = 8;              // CTAs per cluster == per descriptor pair
+constexpr int CNT = 256;           // threads per CTA
+constexpr int RPC = 64;            // real rows per CTA
+constexpr int MAXM = 512;
+constexpr int SPITCH = 516;        // floats per score row (513 used)
+constexpr int NCOL = 544;          // 17 columns per lane
+constexpr int CPL = NCOL / 32;     // 17
+constexpr int KC = 16;             // GEMM k chunk
+constexpr int AP = 68;             // pitch of the A chunk [KC][64]
+constexpr int BP = 516;            // pitch of the B chunk [KC][512]
+
+// shared-memory plan (floats)
+constexpr int OFF_S = 0;                                   // (RPC+1) x SPITCH
+constexpr int OFF_U = OFF_S + (RPC + 1) * SPITCH;          // u2 per local row (+pad)
+constexpr int OFF_V = OFF_U + 72;                          // v2 per column
+constexpr int OFF_CP = OFF_V + NCOL;                       // this CTA's partial column sums
+constexpr int OFF_RECV = OFF_CP + NCOL;                    // [2][CL][NCOL] partials received from the cluster
+constexpr int OFF_X = OFF_RECV + 2 * CL * NCOL;            // union: GEMM chunks | per-warp column accumulators
+constexpr int X_GEMM = KC * AP + KC * BP + 64 + MAXM;      // A chunk, B chunk, n1, n2
+constexpr int X_ITER = (CNT / 32) * NCOL;
+constexpr int X_SIZE = X_GEMM > X_ITER ? X_GEMM : X_ITER;
+constexpr int CLUSTER_SMEM_FLOATS = OFF_X + X_SIZE;
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct ClusterArgs {
+    const float* d1;
+    const float* d2;
+    int N, M, D;
+    int iterations;
+    float scale2;       // log2(e)/eps: cost -> base-2 log score
+    float dustbin2;     // (-unused/eps) * log2(e)
+    float* P;
+};
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cluster_kernel(ClusterArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int z = blockIdx.x / CL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.N, M = a.M, D = a.D;
+
+    float* sS = sm + OFF_S;
+    float* sU = sm + OFF_U;
+    float* sV = sm + OFF_V;
+    float* sCP = sm + OFF_CP;
+    float* sRecv = sm + OFF_RECV;
+    float* sX = sm + OFF_X;
+
+    const int r0 = rank * RPC;                                  // first real row of this CTA
+    const int nreal = max(0, min(RPC, N - r0));                 // real rows held here
+    const bool has_dust = rank == CL - 1;                       // dustbin row lives in the last CTA
+    const int nloc = nreal + (has_dust ? 1 : 0);
+
+    // ---------------- similarity GEMM: sS[li][j] = -max(n1+n2-2 a.b, 0) * scale2 -------------------
+    {
+        float* sA = sX;                    // [KC][AP]
+        float* sB = sA + KC * AP;          // [KC][BP]
+        float* sN1 = sB + KC * BP;         // [64]
+        float* sN2 = sN1 + 64;             // [512]
+        const float* A = a.d1 + ((size_t)z * N + r0) * D;
+        const float* Bm = a.d2 + (size_t)z * M * D;
+        const int tr = warp, tc = lane;    // 8 rows x 16 cols per thread
+        float acc[8][16];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[r][c] = 0.0f;
+        const int lrow = tid >> 2, lkq = tid & 3;               // loader coordinates
+        float na = 0.0f, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k0 = 0; k0 < D; k0 += KC) {
+            {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lrow < nreal) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)lrow * D + k0 + 4 * lkq));
+                na = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, na))));
+                sA[(4 * lkq + 0) * AP + lrow] = v.x; sA[(4 * lkq + 1) * AP + lrow] = v.y;
+                sA[(4 * lkq + 2) * AP + lrow] = v.z; sA[(4 * lkq + 3) * AP + lrow] = v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int j = lrow + 64 * q;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < M) v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)j * D + k0 + 4 * lkq));
+                nb[q] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, nb[q]))));
+                sB[(4 * lkq + 0) * BP + j] = v.x; sB[(4 * lkq + 1) * BP + j] = v.y;
+                sB[(4 * lkq + 2) * BP + j] = v.z; sB[(4 * lkq + 3) * BP + j] = v.w;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int k = 0; k < KC; ++k) {
+                const float4 a0 = *reinterpret_cast<const float4*>(sA + k * AP + tr * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(sA + k * AP + tr * 8 + 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = *reinterpret_cast<const float4*>(sB + k * BP + 128 * q + 4 * tc);
+                    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[r][4 * q + c] = fmaf(av[r], bv[c], acc[r][4 * q + c]);
+                }
+            }
+            __syncthreads();
+        }
+        // squared norms: 4 loader threads share a row (sinkhorn.py:98-99)
+        na += __shfl_xor_sync(0xffffffffu, na, 1);
+        na += __shfl_xor_sync(0xffffffffu, na, 2);
+        if (lkq == 0) sN1[lrow] = na;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v = nb[q];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (lkq == 0) sN2[lrow + 64 * q] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int li = tr * 8 + r;
+            if (li >= nreal) continue;
+            const float n1 = sN1[li];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = 128 * q + 4 * tc;
+                float o[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float cost = fmaxf(__fsub_rn(__fadd_rn(n1, sN2[j + c]), __fmul_rn(2.0f, acc[r][4 * q + c])), 0.0f);
+                    o[c] = __fmul_rn(-cost, a.scale2);
+                }
+                *reinterpret_cast<float4*>(sS + li * SPITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncthreads();
+        // dustbin column / row (sinkhorn.py:182-187)
+        for (int li = tid; li < nreal; li += CNT) sS[li * SPITCH + M] = a.dustbin2;
+        if (has_dust)
+            for (int j = tid; j <= M; j += CNT) sS[nreal * SPITCH + j] = a.dustbin2;
+    }
+    for (int i = tid; i < 72; i += CNT) sU[i] = 0.0f;
+    for (int i = tid; i < NCOL; i += CNT) sV[i] = 0.0f;
+    __syncthreads();
+
+    const float log2_m = log2f((float)M), log2_n = log2f((float)N);
+    float* sCW = sX;                                              // [8 warps][NCOL], aliases the GEMM chunks
+    float vreg[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) vreg[k] = 0.0f;
+
+    // make sure every CTA of the cluster is running before the first DSMEM store
+    cluster.sync();
+
+    for (int it = 0; it < a.iterations; ++it) {
+        float colacc[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) colacc[k] = 0.0f;
+        for (int li = warp; li < nloc; li += CNT / 32) {
+            const bool dust_row = has_dust && li == nreal;
+            const float mu = dust_row ? (float)M : 1.0f;
+            const float u_old = sU[li];
+            const float* row = sS + li * SPITCH;
+            float e[CPL];
+            float rs = 0.0f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int c = lane + 32 * k;
+                e[k] = (c <= M) ? ex2((row[c] + vreg[k]) + u_old) : 0.0f;
+                rs += e[k];
+            }
+            rs = warp_sum(rs);
+            float u_new, f;
+            if (rs >= 1e-30f && rs <= 1e30f) {
+                f = __fdividef(mu, rs);
+                u_new = u_old + ((dust_row ? log2_m : 0.0f) - lg2(rs));
+            } else {
+                // classic max-shifted logsumexp for this row (sinkhorn.py:140)
+                float m = -CUDART_INF_F;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c <= M) m = fmaxf(m, row[c] + vreg[k]);
+                }
+                m = warp_max(m);
+                rs = 0.0f;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int c = lane + 32 * k;
+                    e[k] = (c <= M) ? ex2((row[c] + vreg[k]) - m) : 0.0f;
+                    rs += e[k];
+                }
+                rs = warp_sum(rs);
+                f = __fdividef(mu, rs);
+                u_new = (dust_row ? log2_m : 0.0f) - (m + lg2(rs));
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) colacc[k] = fmaf(e[k], f, colacc[k]);   // exp2(S + u_new + v)
+            if (lane == 0) sU[li] = u_new;
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) sCW[warp * NCOL + lane + 32 * k] = colacc[k];
+        __syncthreads();
+        // CTA partial per column, pushed into every cluster member's receive slot for this rank
+        float* recv = sRecv + (it & 1) * CL * NCOL;
+        for (int c = tid; c < NCOL; c += CNT) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < CNT / 32; ++w) s += sCW[w * NCOL + c];
+            sCP[c] = s;
+        }
+        __syncthreads();
+        for (int e2 = tid; e2 < CL * NCOL; e2 += CNT) {
+            const int dst = e2 / NCOL, c = e2 % NCOL;
+            float* remote = cluster.map_shared_rank(recv + rank * NCOL, dst);
+            remote[c] = sCP[c];
+        }
+        cluster.sync();
+        // v_j += log_nu_j - log(colsum_j)   (sinkhorn.py:142 with the shift -v_j)
+        for (int c = tid; c <= M; c += CNT) {
+            float s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < CL; ++r) s += recv[r * NCOL + c];
+            sV[c] = sV[c] + ((c == M ? log2_n : 0.0f) - lg2(s));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) vreg[k] = sV[lane + 32 * k];
+    }
+
+    // P = exp(S + u + v) (sinkhorn.py:145, :206)
+    float* Pz = a.P + (size_t)z * (N + 1) * (M + 1);
+    for (int li = warp; li < nloc; li += CNT / 32) {
+        const bool dust_row = has_dust && li == nreal;
+        const int gi = dust_row ? N : r0 + li;
+        const float u = sU[li];
+        const float* row = sS + li * SPITCH;
+        float* out = Pz + (size_t)gi * (M + 1);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int c = lane + 32 * k;
+            if (c <= M) out[c] = ex2((row[c] + u) + vreg[k]);
+        }
+    }
+    // no CTA may exit while a peer can still write into its shared memory
+    cluster.sync();
+}
+
+int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
+                     float unused, float* P, cudaStream_t st) {
+    ClusterArgs a{};
+    a.d1 = d1; a.d2 = d2; a.N = N; a.M = M; a.D = D; a.iterations = iterations; a.P = P;
+    const double log2e = 1.4426950408889634;
+    a.scale2 = (float)(log2e / (double)eps);
+    a.dustbin2 = (float)((-(double)unused / (double)eps) * log2e);
+    const size_t smem = (size_t)CLUSTER_SMEM_FLOATS * sizeof(float);
+    OM_TRY(set_smem(sinkhorn_cluster_kernel, smem));
+    sinkhorn_cluster_kernel<<<B * CL, CNT, smem, st>>>(a);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+int g_force_generic_sinkhorn = 0;
+
+}  // namespace
+
+size_t sinkhorn_workspace_bytes(int B, int N, int M, int D) {
+    (void)D;
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    return align_up((size_t)B * N * sizeof(float)) + align_up((size_t)B * M * sizeof(float)) +
+           align_up((size_t)B * (N + 1) * sizeof(float)) + align_up((size_t)B * (M + 1) * sizeof(float));
+}
+
+int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
+                    float unused_score, int distance_l1, float* P, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (d1 == nullptr || d2 == nullptr || P == nullptr) return OM_ERR_NULL;
+    if (B <= 0 || N <= 0 || M <= 0 || D <= 0) return OM_ERR_SHAPE;
+    if (iterations <= 0 || !(epsilon > 0.0f)) return OM_ERR_PARAM;        // sinkhorn.py:66-69
+    if (B > 65535) return OM_ERR_LIMIT;
+    const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && !g_force_generic_sinkhorn &&
+                      (long long)B * CL < (1ll << 31);
+    if (fast) return sinkhorn_cluster(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
+    if (ws == nullptr || ws_bytes < sinkhorn_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    // dustbin score is computed in double by the reference (python floats) and cast once, sinkhorn.py:182
+    const float dustbin = (float)(-(double)unused_score / (double)epsilon);
+    return sinkhorn_generic(d1, d2, B, N, M, D, iterations, epsilon, dustbin, distance_l1, P, ws, st);
+}
+
+}  // namespace om
+
+using namespace om;
+
+extern "C" void om_debug_force_generic_sinkhorn(int on) { g_force_generic_sinkhorn = on; }
+
+extern "C" size_t om_sinkhorn_workspace_bytes(int B, int N, int M, int D) { return sinkhorn_workspace_bytes(B, N, M, D); }
+
+extern "C" int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M, int D, int iterations,
+                               float epsilon, float unused_score, int distance_l1, float* P, void* ws,
+                               size_t ws_bytes, void* stream) {
+    return sinkhorn_launch(desc1, desc2, B, N, M, D, iterations, epsilon, unused_score, distance_l1, P, ws, ws_bytes,
+                           (cudaStream_t)stream);
+}

@@ -1,0 +1,11 @@
+from .shi_tomasi_bad import ShiTomasiBADDetector
+from .shi_tomasi_bad_sinkhorn import ShiTomasiBADSinkhornMatcher
+from .shi_tomasi_sparse_bad_sinkhorn import ShiTomasiSparseBADSinkhornMatcher
+from .shi_tomasi_angle import ShiTomasiWithAngle, ShiTomasiAngleSparseBAD, ShiTomasiAngleSparseBADDetector
+from .shi_tomasi_angle_sparse_bad_sinkhorn import ShiTomasiAngleSparseBADSinkhornMatcher
+
+__all__ = [
+    "ShiTomasiBADDetector", "ShiTomasiBADSinkhornMatcher", "ShiTomasiSparseBADSinkhornMatcher",
+    "ShiTomasiWithAngle", "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector",
+    "ShiTomasiAngleSparseBADSinkhornMatcher",
+]

@@ -1,0 +1,85 @@
+"""Host-side plumbing around the matcher modules: chunked H2D -> kernels -> D2H pipelining on a
+ring of CUDA streams, and contiguous sharding of a batch of image pairs over ranks (one process
+per GPU, no collective on the data path -- image pairs are independent).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_pairs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of the pair batch owned by `rank`; sizes differ by at most one."""
+    if world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank/world_size: {rank}/{world_size}")
+    base, extra = divmod(num_pairs, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_to_rank0(local: Sequence[torch.Tensor], group=None) -> List[torch.Tensor] | None:
+    """Host gather of per-rank result tensors (CPU tensors, ragged along dim 0).  Rank 0 gets the
+    concatenation in rank order, other ranks get None.  This is the only cross-rank step of the path."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return list(local)
+    world = dist.get_world_size(group)
+    parts = [None] * world if dist.get_rank(group) == 0 else None
+    dist.gather_object([t.cpu() for t in local], parts, dst=0, group=group)
+    if parts is None:
+        return None
+    return [torch.cat([p[i] for p in parts], dim=0) for i in range(len(local))]
+
+
+class HostBatchMatcher:
+    """Run a matcher module over HOST-resident image pairs.
+
+    The batch is cut into chunks; chunk c uses stream c % n_streams, so the H2D copy of one chunk,
+    the kernels of the previous one and the D2H copy of the one before overlap.  Inputs should be
+    pinned (they are pinned on first use otherwise); outputs are pinned host tensors.
+    """
+
+    def __init__(self, model: torch.nn.Module, chunk: int = 16, n_streams: int = 3, device=None):
+        self.model = model
+        self.chunk = int(chunk)
+        self.device = torch.device(device) if device is not None else next(model.buffers()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("HostBatchMatcher needs the model on a CUDA device (no CPU path)")
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        self._out = None
+
+    def _outputs(self, B: int, K: int):
+        if self._out is None or self._out[0].shape[0] != B or self._out[0].shape[1] != K:
+            self._out = (torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
+                         torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
+                         torch.empty((B, K + 1, K + 1), dtype=torch.float32).pin_memory())
+        return self._out
+
+    @torch.no_grad()
+    def __call__(self, image1: torch.Tensor, image2: torch.Tensor):
+        if image1.is_cuda or image2.is_cuda:
+            raise RuntimeError("HostBatchMatcher takes host tensors; call the module directly for device tensors")
+        if not image1.is_pinned():
+            image1 = image1.pin_memory()
+        if not image2.is_pinned():
+            image2 = image2.pin_memory()
+        B = image1.shape[0]
+        K = int(self.model.max_keypoints)
+        o1, o2, op = self._outputs(B, K)
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for ci, lo in enumerate(range(0, B, self.chunk)):
+            hi = min(lo + self.chunk, B)
+            s = self.streams[ci % len(self.streams)]
+            with torch.cuda.stream(s):
+                d1 = image1[lo:hi].to(self.device, non_blocking=True)
+                d2 = image2[lo:hi].to(self.device, non_blocking=True)
+                k1, k2, p = self.model(d1, d2)
+                o1[lo:hi].copy_(k1, non_blocking=True)
+                o2[lo:hi].copy_(k2, non_blocking=True)
+                op[lo:hi].copy_(p, non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        return o1, o2, op

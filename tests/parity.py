@@ -1,0 +1,64 @@
+"""Parity metrics shared by the GPU tests and tools/gpu_diag.py.
+
+Tolerances are the north star's (BASELINE.json): keypoints identical except exact score ties;
+descriptors <= 1e-5 abs (L2-normalised output; raw output relative to its magnitude);
+match probabilities <= 1e-4 abs on the core block and the dustbin row/column, relative 1e-4 on
+the dustbin/dustbin corner (a value of ~240-510); row-argmax agreement >= 99.9 %.
+"""
+from __future__ import annotations
+
+import torch
+
+DESC_TOL = 1e-5
+PROB_TOL = 1e-4
+ARGMAX_MIN = 0.999
+
+
+def keypoint_mismatches(k_test: torch.Tensor, k_ref: torch.Tensor, s_ref: torch.Tensor | None = None) -> int:
+    """Number of keypoint slots that differ and are not excused by an exact score tie."""
+    k_test, k_ref = k_test.cpu(), k_ref.cpu()
+    diff = (k_test != k_ref).any(dim=-1)
+    if s_ref is None or not diff.any():
+        return int(diff.sum())
+    s_ref = s_ref.cpu()
+    bad = 0
+    for b in range(k_ref.shape[0]):
+        idx = diff[b].nonzero().flatten()
+        for i in idx.tolist():
+            tied = (s_ref[b] == s_ref[b, i]).sum() > 1 and s_ref[b, i] > 0
+            if not tied:
+                bad += 1
+            else:
+                # the tied group must hold the same SET of coordinates
+                grp = (s_ref[b] == s_ref[b, i])
+                a = {tuple(v) for v in k_test[b][grp].tolist()}
+                r = {tuple(v) for v in k_ref[b][grp].tolist()}
+                bad += int(a != r)
+    return bad
+
+
+def desc_metrics(d_test: torch.Tensor, d_ref: torch.Tensor) -> dict:
+    d_test, d_ref = d_test.cpu(), d_ref.cpu()
+    err = (d_test - d_ref).abs()
+    scale = d_ref.abs().amax().clamp_min(1.0)
+    row_ok = (err.amax(dim=-1) <= DESC_TOL * scale)
+    return dict(max_abs=float(err.max()), max_rel_to_scale=float(err.max() / scale),
+                rows_within=float(row_ok.float().mean()), elems_over=float((err > DESC_TOL * scale).float().mean()))
+
+
+def prob_metrics(p_test: torch.Tensor, p_ref: torch.Tensor) -> dict:
+    p_test, p_ref = p_test.cpu(), p_ref.cpu()
+    N, M = p_ref.shape[1] - 1, p_ref.shape[2] - 1
+    err = (p_test - p_ref).abs()
+    core = float(err[:, :N, :].max()) if N > 0 else 0.0
+    dust_row = float(err[:, N, :M].max()) if M > 0 else 0.0
+    corner_rel = float((err[:, N, M] / p_ref[:, N, M].abs().clamp_min(1e-30)).max())
+    am_t = p_test[:, :N, :].argmax(dim=-1)
+    am_r = p_ref[:, :N, :].argmax(dim=-1)
+    return dict(core=core, dust_row=dust_row, corner_rel=corner_rel, argmax=float((am_t == am_r).float().mean()),
+                finite=bool(torch.isfinite(p_test).all()))
+
+
+def probs_ok(m: dict) -> bool:
+    return (m["finite"] and m["core"] <= PROB_TOL and m["dust_row"] <= PROB_TOL and m["corner_rel"] <= PROB_TOL
+            and m["argmax"] >= ARGMAX_MIN)

@@ -1,0 +1,362 @@
+"""GPU parity tests: the CUDA path (module API -> custom op -> C ABI -> sm_100a kernels) against
+(a) the golden vectors minted from the live reference and (b) the CPU oracle on seeded inputs.
+Run on the B200 box with `pytest -m gpu`.
+"""
+import pytest
+import torch
+
+import onnx_image_processing_b200 as om
+from onnx_image_processing_b200 import _native, _ops
+from oracle import oracle as O
+from tests import golden_util as G
+from tests import parity as PR
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cuda(*ts):
+    return [t.to(DEV) for t in ts]
+
+
+# ------------------------------------------------------------------------------------------
+# stage level
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("block_size", [1, 3, 5, 7, 9])
+@pytest.mark.parametrize("shape", [(2, 96, 128), (1, 67, 93), (1, 33, 65), (1, 480, 640)])
+def test_score_map_bit_exact(block_size, shape):
+    """Integer-valued images: every intermediate is an exact integer, so the score map must be
+    bit-identical to the reference's (trap 1)."""
+    B, H, W = shape
+    img = O.noise_images(B, H, W, seed=block_size * 100 + H)
+    ref = O.shi_tomasi_score(img, block_size)
+    got = om.ShiTomasiScore(block_size).to(DEV)(img.to(DEV)).cpu()
+    assert got.shape == ref.shape
+    nbad = int((got != ref).sum())
+    assert nbad == 0, f"{nbad} of {ref.numel()} score pixels differ, max abs {float((got - ref).abs().max())}"
+
+
+@pytest.mark.parametrize("block_size,nms_radius", [(3, 3), (3, 5), (5, 3), (5, 5)])
+def test_fast_and_generic_stencil_agree(block_size, nms_radius):
+    img, _ = O.texture_images(2, 150, 210, seed=7)
+    lib = _native.lib()
+    outs = []
+    for force in (0, 1):
+        lib.om_debug_force_generic_stencil(force)
+        try:
+            sc = om.ShiTomasiScore(block_size).to(DEV)(img.to(DEV))
+            k, s = _ops.detect(img.to(DEV), 300, block_size, nms_radius, 0.0, 4)
+        finally:
+            lib.om_debug_force_generic_stencil(0)
+        outs.append((sc.cpu(), k.cpu(), s.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("nms_radius", [0, 1, 2, 3, 5, 8])
+def test_nms_mask_exact(nms_radius):
+    img, _ = O.texture_images(2, 90, 130, seed=3)
+    sc = O.shi_tomasi_score(img, 3).squeeze(1)
+    sc[0, 10:14, 20:25] = sc.max() + 1.0          # plateau: every member must survive (>= test)
+    ref = O.nms_mask(sc, nms_radius)
+    got = om.apply_nms_maxpool(sc.to(DEV), nms_radius).cpu()
+    assert torch.equal(got, ref), f"{int((got != ref).sum())} mask pixels differ"
+
+
+@pytest.mark.parametrize("K,thr,margin", [(50, 0.0, 0), (400, 0.0, 7), (64, 2000.0, 3), (1000, 0.0, 0)])
+def test_select_topk_matches_oracle(K, thr, margin):
+    img, _ = O.texture_images(2, 96, 128, seed=11)
+    sc = O.shi_tomasi_score(img, 3).squeeze(1)
+    mask = O.nms_mask(sc, 3)
+    kr, sr = O.select_topk(sc, mask, K, thr, margin)
+    kg, sg = om.select_topk_keypoints(sc.to(DEV), mask.to(DEV), K, thr, margin)
+    assert torch.equal(sg.cpu(), sr)
+    assert PR.keypoint_mismatches(kg, kr, sr) == 0
+
+
+def test_topk_ties_take_lowest_index():
+    sc = torch.zeros(1, 40, 50)
+    pos = [(5, 7), (5, 30), (20, 3), (33, 44), (39, 49), (0, 0)]
+    for y, x in pos:
+        sc[0, y, x] = 3.5
+    sc[0, 10, 10] = 9.0
+    kg, sg = om.select_topk_keypoints(sc.to(DEV), torch.ones_like(sc).to(DEV), 4, 0.0, 0)
+    assert sg.cpu().tolist() == [[9.0, 3.5, 3.5, 3.5]]
+    assert kg.cpu().tolist() == [[[10.0, 10.0], [0.0, 0.0], [5.0, 7.0], [5.0, 30.0]]]
+
+
+def test_topk_k_larger_than_image_raises():
+    sc = torch.rand(1, 8, 8).to(DEV)
+    with pytest.raises(RuntimeError):
+        om.select_topk_keypoints(sc, torch.ones_like(sc), 65)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(), dict(num_pairs=512), dict(binarize=True), dict(binarize=True, soft_binarize=False),
+    dict(sampling_mode="bilinear"), dict(normalize_descriptors=False),
+])
+def test_sparse_bad_matches_oracle(kw):
+    img, _ = O.texture_images(2, 120, 160, seed=21)
+    k, _ = O.detect(img, 150, 3, 3, 0.0, 0)        # margin 0: boxes reach over the border
+    k[1, -5:] = -1.0                                # invalid rows -> zero descriptors
+    ref = O.sparse_bad(img, k, None, **kw)
+    got = om.SparseBAD(**kw).to(DEV)(img.to(DEV), k.to(DEV))
+    m = PR.desc_metrics(got, ref)
+    if kw.get("binarize") and not kw.get("soft_binarize", True):
+        assert m["elems_over"] <= 1e-4, m           # a hard bit may flip when |centered| < 1e-5
+    else:
+        assert m["max_rel_to_scale"] <= PR.DESC_TOL, m
+    assert float(got[1, -5:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("sampling_mode", ["nearest", "bilinear"])
+def test_oriented_sparse_bad(sampling_mode):
+    """theta taken from a map (module API) and from the in-kernel moments must both match the
+    oracle except for the documented rounding flips (trap 5)."""
+    img, _ = O.texture_images(2, 120, 160, seed=31)
+    k, _ = O.detect(img, 128, 5, 3, 0.0, 7)
+    ang = O.angle_map(img)
+    ref = O.sparse_bad(img, k, ang, sampling_mode=sampling_mode)
+    sb = om.SparseBAD(sampling_mode=sampling_mode).to(DEV)
+    got_map = sb(img.to(DEV), k.to(DEV), ang.to(DEV))
+    m1 = PR.desc_metrics(got_map, ref)
+    assert m1["rows_within"] >= 0.99, m1
+    mk = om.AngleEstimator().to(DEV).moment_kernels
+    got_mom = _ops.sparse_bad(img.to(DEV), k.to(DEV), sb._pair_table, 0, 10.0, True, _ops.sampling_code(sampling_mode),
+                              _ops.THETA_MOMENTS, None, mk)
+    m2 = PR.desc_metrics(got_mom, ref)
+    assert m2["rows_within"] >= 0.97, m2
+
+
+def test_angle_map_matches_oracle():
+    img, _ = O.texture_images(2, 70, 100, seed=5)
+    ref = O.angle_map(img)
+    got = om.AngleEstimator().to(DEV)(img.to(DEV)).cpu()
+    d = (got - ref).abs()
+    d = torch.minimum(d, (2 * torch.pi - d).abs())
+    assert float(d.median()) <= 1e-6 and float((d > 1e-3).float().mean()) <= 1e-3, (float(d.median()), float(d.max()))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(num_pairs=512, binarize=True), dict(binarize=True, soft_binarize=False)])
+def test_dense_bad_map(kw):
+    img, _ = O.texture_images(1, 48, 72, seed=41)
+    ref = O.dense_bad(img, **kw)
+    got = om.BADDescriptor(**kw).to(DEV)(img.to(DEV)).cpu()
+    if not kw.get("binarize"):
+        nbad = int((got != ref).sum())
+        assert nbad == 0, f"{nbad}/{ref.numel()} dense values differ, max {float((got - ref).abs().max())}"
+    else:
+        assert float((got - ref).abs().max()) <= 1e-6
+
+
+def test_gather_functions():
+    g = torch.Generator().manual_seed(3)
+    dm = torch.randn(2, 16, 30, 40, generator=g)
+    kp = torch.stack([torch.randint(0, 30, (2, 25), generator=g), torch.randint(0, 40, (2, 25), generator=g)], -1).float()
+    from onnx_image_processing_b200.descriptor import extract_descriptors_at_keypoints as e0
+    from onnx_image_processing_b200.descriptor import extract_descriptors_at_keypoints_subpixel as e1
+    # integer gather == indexing
+    ref0 = dm[torch.arange(2)[:, None], :, kp[..., 0].long(), kp[..., 1].long()]
+    assert torch.equal(e0(dm.to(DEV), kp.to(DEV)).cpu(), ref0)
+    kf = kp + torch.rand(2, 25, 2, generator=g) * 0.9
+    kf[..., 0].clamp_(0, 29)
+    kf[..., 1].clamp_(0, 39)
+    ref1 = O.gather_subpixel(dm, kf)
+    assert float((e1(dm.to(DEV), kf.to(DEV)).cpu() - ref1).abs().max()) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# Sinkhorn
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.names("sinkhorn"))
+@pytest.mark.parametrize("generic", [0, 1])
+def test_sinkhorn_golden(name, generic):
+    g = G.load(name)
+    lib = _native.lib()
+    lib.om_debug_force_generic_sinkhorn(generic)
+    try:
+        got = om.SinkhornMatcher(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"]))
+    finally:
+        lib.om_debug_force_generic_sinkhorn(0)
+    m = PR.prob_metrics(got, g["P"])
+    assert PR.probs_ok(m), m
+    m64 = PR.prob_metrics(got, g["P64"].float())
+    assert m64["core"] <= PR.PROB_TOL, m64
+
+
+@pytest.mark.parametrize("N,M,eps,unused", [(512, 512, 1.0, 1.0), (512, 512, 0.05, 1.0), (300, 512, 0.1, 0.5),
+                                            (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0)])
+def test_sinkhorn_cluster_vs_oracle(N, M, eps, unused):
+    g = torch.Generator().manual_seed(N * 7 + M)
+    d1 = torch.nn.functional.normalize(torch.randn(2, N, 256, generator=g), dim=-1)
+    pick = (torch.randperm(max(N, M), generator=g) % N)[:M]
+    d2 = torch.nn.functional.normalize(d1[:, pick] + 0.25 * torch.randn(2, M, 256, generator=g), dim=-1)
+    if N > 4:
+        d1[:, -2:] = 0.0
+    ref = O.sinkhorn(d1.double(), d2.double(), 20, eps, unused).float()      # fp64 truth
+    got = om.SinkhornMatcher(20, eps, unused).to(DEV)(*_cuda(d1, d2))
+    m = PR.prob_metrics(got, ref)
+    assert PR.probs_ok(m), m
+    # marginals: real rows sum to ~1 only at convergence; the column sums are exact after the last half-step
+    cs = got.sum(dim=1).cpu()
+    assert float((cs[:, :M] - 1.0).abs().max()) <= 1e-3, float((cs[:, :M] - 1.0).abs().max())
+
+
+def test_sinkhorn_large_k_generic_path():
+    g = torch.Generator().manual_seed(5)
+    d1 = torch.nn.functional.normalize(torch.randn(1, 700, 256, generator=g), dim=-1)
+    d2 = torch.nn.functional.normalize(d1[:, torch.randperm(700, generator=g)] + 0.2 * torch.randn(1, 700, 256, generator=g), dim=-1)
+    ref = O.sinkhorn(d1, d2, 20, 0.05)
+    got = om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2))
+    m = PR.prob_metrics(got, ref)
+    assert PR.probs_ok(m), m
+
+
+# ------------------------------------------------------------------------------------------
+# unified modules against golden vectors from the live reference
+# ------------------------------------------------------------------------------------------
+def _check_matcher(g, k1, k2, p, d1=None, d2=None, desc_rows=1.0):
+    assert PR.keypoint_mismatches(k1, g["kpts1"]) == 0
+    assert PR.keypoint_mismatches(k2, g["kpts2"]) == 0
+    if d1 is not None and "desc1" in g:
+        m = PR.desc_metrics(d1, g["desc1"])
+        assert m["rows_within"] >= desc_rows, m
+    if d2 is not None and "desc2" in g:
+        m = PR.desc_metrics(d2, g["desc2"])
+        assert m["rows_within"] >= desc_rows, m
+    m = PR.prob_metrics(p, g["P"])
+    return m
+
+
+@pytest.mark.parametrize("name", G.names("sparse"))
+def test_sparse_matcher_golden(name):
+    g = G.load(name)
+    model = om.ShiTomasiSparseBADSinkhornMatcher(g["K"], **g["kwargs"]).to(DEV).eval()
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
+        k1b, k2b, pb = model(*_cuda(g["image1"], g["image2"]))
+    assert torch.equal(k1, k1b) and torch.equal(p, pb)
+    hard = g["kwargs"].get("binarize") and not g["kwargs"].get("soft_binarize", True)
+    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=0.98 if hard else 1.0)
+    if hard:
+        assert m["core"] <= 5e-3 and m["argmax"] >= 0.99, m       # a flipped bit moves one row of P
+    else:
+        assert PR.probs_ok(m), m
+    # stage modules of the same model reproduce the fused path
+    sc = model.corner_detector(g["image1"].to(DEV)).squeeze(1)
+    kk, ks = om.select_topk_keypoints(sc, om.apply_nms_maxpool(sc, model.nms_radius), g["K"],
+                                      model.score_threshold, model.border_margin)
+    assert torch.equal(kk, k1)
+    assert torch.equal(ks.cpu(), g["kpt_scores1"])
+    assert torch.equal(model.descriptor(g["image1"].to(DEV), kk), d1)
+
+
+def test_constant_image_has_no_keypoints():
+    g = G.load("sparse_constant_image")
+    model = om.ShiTomasiSparseBADSinkhornMatcher(g["K"]).to(DEV)
+    k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image1"]))
+    assert bool((k1 == -1).all()) and bool((k2 == -1).all())
+    assert float(d1.abs().max()) == 0.0
+    m = PR.prob_metrics(p, g["P"])
+    assert PR.probs_ok(m), m
+
+
+@pytest.mark.parametrize("name", G.names("angle"))
+def test_angle_matcher_golden(name):
+    g = G.load(name)
+    model = om.ShiTomasiAngleSparseBADSinkhornMatcher(g["K"], **g["kwargs"]).to(DEV).eval()
+    k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
+    # orientation rounding flips touch ~0.1 % of rows (SURVEY.md section 0 trap 5); report, bound loosely
+    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=0.97)
+    assert m["finite"] and m["argmax"] >= 0.99 and m["core"] <= 2e-2, m
+    det = om.ShiTomasiAngleSparseBADDetector(g["K"], **{k: v for k, v in g["kwargs"].items()
+                                                        if k not in ("epsilon", "sinkhorn_iterations")}).to(DEV)
+    dk, dsc, dd = det(g["image1"].to(DEV))
+    assert PR.keypoint_mismatches(dk, g["det_kpts"], g["det_scores"]) == 0
+    assert torch.equal(dsc.cpu(), g["det_scores"])
+    assert PR.desc_metrics(dd, g["det_desc"])["rows_within"] >= 0.97
+
+
+@pytest.mark.parametrize("name", G.names("dense"))
+def test_dense_matcher_golden(name):
+    g = G.load(name)
+    model = om.ShiTomasiBADSinkhornMatcher(g["K"], **g["kwargs"]).to(DEV).eval()
+    k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
+    m = _check_matcher(g, k1, k2, p, d1, None)
+    assert PR.probs_ok(m), m
+    # the dense module itself against the probes of the reference's dense map
+    det = model.detector
+    sc, dmap = det(g["image1"].to(DEV))
+    pb, pp, py, px = g["probe_idx"]
+    probe = dmap.cpu()[pb, pp, py, px]
+    if not g["kwargs"].get("binarize"):
+        assert torch.equal(probe, g["probe_val"])
+    else:
+        assert float((probe - g["probe_val"]).abs().max()) <= 1e-6
+    # bilinear gather from that map == the keypoint-only evaluation
+    dg = model._extract_descriptors_at_keypoints_batched(dmap, k1)
+    dg = torch.nn.functional.normalize(dg, p=2, dim=-1) if model.normalize_descriptors else dg
+    assert float((dg - d1).abs().max()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (sizes of BASELINE.json configs 2-4)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flavour", ["sparse", "dense", "angle"])
+def test_full_size_batch_properties(flavour):
+    B = 6
+    i1, i2 = O.texture_images(B, 480, 640, seed=100)
+    cls = dict(sparse=om.ShiTomasiSparseBADSinkhornMatcher, dense=om.ShiTomasiBADSinkhornMatcher,
+               angle=om.ShiTomasiAngleSparseBADSinkhornMatcher)[flavour]
+    model = cls(512).to(DEV)
+    k1, k2, p, d1, d2 = model.match(*_cuda(i1, i2))
+    assert p.shape == (B, 513, 513) and bool(torch.isfinite(p).all())
+    # batch independence: each pair alone gives bit-identical results (what sharding over GPUs relies on)
+    for b in (0, B - 1):
+        s1, s2, sp, _, _ = model.match(i1[b:b + 1].to(DEV), i2[b:b + 1].to(DEV))
+        assert torch.equal(s1, k1[b:b + 1]) and torch.equal(s2, k2[b:b + 1]) and torch.equal(sp, p[b:b + 1])
+    # keypoints are sorted by score, inside the margin, unique
+    margin = 0 if flavour == "dense" else 7
+    v = k1[..., 0] >= 0
+    assert bool(v.all())
+    assert float(k1[..., 0].min()) >= margin and float(k1[..., 0].max()) <= 479 - margin
+    flat = (k1[..., 0] * 640 + k1[..., 1]).long()
+    assert all(flat[b].unique().numel() == 512 for b in range(B))
+    # descriptors are unit norm, column marginals hold exactly after the last half-step
+    assert float((d1.norm(dim=-1) - 1).abs().max()) <= 1e-5
+    assert float((p.sum(dim=1)[:, :512] - 1).abs().max()) <= 1e-3
+    # image2 is image1 rolled by (3,5): most keypoints must be matched to their shifted twin
+    if flavour != "angle":
+        am = p[:, :512, :512].argmax(dim=-1)
+        tgt = torch.gather(k2, 1, am.unsqueeze(-1).expand(-1, -1, 2))
+        hit = ((tgt - k1) == torch.tensor([3.0, 5.0], device=DEV)).all(dim=-1).float().mean()
+        assert float(hit) >= 0.60, float(hit)
+
+
+def test_sparse_full_size_vs_oracle():
+    i1, i2 = O.texture_images(1, 480, 640, seed=123)
+    with torch.no_grad():
+        rk1, rk2, rp, rd1, rd2 = O.sparse_matcher(i1, i2, 512, return_descriptors=True)
+    k1, k2, p, d1, d2 = om.ShiTomasiSparseBADSinkhornMatcher(512).to(DEV).match(*_cuda(i1, i2))
+    assert PR.keypoint_mismatches(k1, rk1) == 0 and PR.keypoint_mismatches(k2, rk2) == 0
+    assert PR.desc_metrics(d1, rd1)["max_abs"] <= PR.DESC_TOL
+    m = PR.prob_metrics(p, rp)
+    assert PR.probs_ok(m), m
+
+
+def test_large_image_k2048_generic_sinkhorn():
+    """BASELINE config 5 shape: 1080x1920, K=2048 (beyond the cluster kernel's K<=512)."""
+    i1, i2 = O.texture_images(1, 1080, 1920, seed=9)
+    model = om.ShiTomasiSparseBADSinkhornMatcher(2048).to(DEV)
+    k1, k2, p, d1, d2 = model.match(*_cuda(i1, i2))
+    rk1, _ = O.detect(i1, 2048, 3, 3, 0.0, 7)
+    assert PR.keypoint_mismatches(k1, rk1) == 0
+    ref = O.sinkhorn(d1.cpu(), d2.cpu(), 20, 1.0)
+    m = PR.prob_metrics(p, ref)
+    assert PR.probs_ok(m), m
+
+
+def test_library_reports_launches():
+    n0 = _native.launch_count()
+    om.ShiTomasiScore(3).to(DEV)(torch.zeros(1, 1, 32, 32, device=DEV))
+    assert _native.launch_count() == n0 + 1
