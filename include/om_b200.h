@@ -191,6 +191,8 @@ void om_debug_force_generic_stencil(int on);
 /* Route om_sinkhorn_f32 / the fused matcher through the generic global-memory Sinkhorn kernels
  * instead of the cluster kernel. */
 void om_debug_force_generic_sinkhorn(int on);
+/* 0: tcgen05/TMEM cluster kernel (default), 1: FP32-FFMA cluster kernel, 2: generic kernels. */
+void om_debug_sinkhorn_variant(int variant);
 
 /* Single-kernel slices of om_detect_f32 / om_dense_bad_at_kpts_f32 so that bench.py can time each
  * kernel with CUDA events.  stage 0 = first kernel(s), stage 1 = the last kernel (needs stage 0's

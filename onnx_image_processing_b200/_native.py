@@ -64,6 +64,7 @@ SIGNATURES = {
                                      c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "om_debug_force_generic_stencil": (None, [c_int]),
     "om_debug_force_generic_sinkhorn": (None, [c_int]),
+    "om_debug_sinkhorn_variant": (None, [c_int]),
 }
 
 

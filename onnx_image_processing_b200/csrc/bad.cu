@@ -112,15 +112,22 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) 
     const int iy0 = (int)nearbyintf(yc), ix0 = (int)nearbyintf(xc);
     const int py0 = iy0 - HS, px0 = ix0 - HS;                               // global coords of patch (0,0)
 
-    // replicate-clamped patch (bad.py:474-478 pads the image, grid_sample clamps the centre)
-    for (int i = t; i < (S + 1) * (S + 1); i += TPG) {
-        const int dy = i / (S + 1), dx = i % (S + 1);
-        double v = 0.0;
-        if (dy > 0 && dx > 0) {
-            const int gy = clampi(py0 + dy - 1, 0, H - 1), gx = clampi(px0 + dx - 1, 0, W - 1);
-            v = (double)__ldg(img + (size_t)gy * W + gx);
+    // replicate-clamped patch (bad.py:474-478 pads the image, grid_sample clamps the centre).
+    // Thread t owns integral column t (patch column t-1): its clamped global column is fixed, rows
+    // are independent loads.  Row 0 / column 0 of the integral are zero.
+    static_assert(S + 1 <= TPG, "one thread per integral column");
+    if (t <= S) {
+        double* col = D + t;
+        col[0] = 0.0;
+        if (t == 0) {
+#pragma unroll 4
+            for (int dy = 1; dy <= S; ++dy) col[dy * PD] = 0.0;
+        } else {
+            const float* src = img + clampi(px0 + t - 1, 0, W - 1);
+#pragma unroll 8
+            for (int dy = 1; dy <= S; ++dy)
+                col[dy * PD] = (double)__ldg(src + (size_t)clampi(py0 + dy - 1, 0, H - 1) * W);
         }
-        D[dy * PD + dx] = v;
     }
     __syncthreads();
 
@@ -425,9 +432,11 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(DenseKpArgs
     const int ys = min(iy0 + 1, H - 1), xe = min(ix0 + 1, W - 1);
     const int oy = iy0 - LO, ox = ix0 - LO;     // integral coords of L(0,0)
 
-    for (int i = t; i < SPAN * SPAN; i += TPG) {
-        const int dy = i / SPAN, dx = i % SPAN;
-        L[i] = __ldg(Iz + (size_t)clampi(oy + dy, 0, Hi - 1) * Wi + clampi(ox + dx, 0, Wi - 1));
+    static_assert(SPAN <= TPG, "one thread per window column");
+    if (t < SPAN) {
+        const float* src = Iz + clampi(ox + t, 0, Wi - 1);
+#pragma unroll 8
+        for (int dy = 0; dy < SPAN; ++dy) L[dy * SPAN + t] = __ldg(src + (size_t)clampi(oy + dy, 0, Hi - 1) * Wi);
     }
     __syncthreads();
 

@@ -77,6 +77,10 @@ int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const floa
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                              float* desc, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// tcgen05 / TMEM cluster kernel (sinkhorn_tc.cu); limits: L2 cost, N <= 512, M <= 512, D % 16 == 0
+int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
+                        float unused, float* P, cudaStream_t st);
+
 size_t sinkhorn_workspace_bytes(int B, int N, int M, int D);
 int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
                     float unused_score, int distance_l1, float* P, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -220,8 +220,8 @@ constexpr int CL = 8;              // CTAs per cluster == per descriptor pair
 constexpr int CNT = 256;           // threads per CTA
 constexpr int RPC = 64;            // real rows per CTA
 constexpr int MAXM = 512;
-constexpr int SPITCH = 516;        // floats per score row (513 used)
 constexpr int NCOL = 544;          // 17 columns per lane
+constexpr int SPITCH = NCOL;       // floats per score row: M+1 used, the rest is -inf padding (exp -> 0)
 constexpr int CPL = NCOL / 32;     // 17
 constexpr int KC = 16;             // GEMM k chunk
 constexpr int AP = 68;             // pitch of the A chunk [KC][64]
@@ -231,8 +231,7 @@ constexpr int BP = 516;            // pitch of the B chunk [KC][512]
 constexpr int OFF_S = 0;                                   // (RPC+1) x SPITCH
 constexpr int OFF_U = OFF_S + (RPC + 1) * SPITCH;          // u2 per local row (+pad)
 constexpr int OFF_V = OFF_U + 72;                          // v2 per column
-constexpr int OFF_CP = OFF_V + NCOL;                       // this CTA's partial column sums
-constexpr int OFF_RECV = OFF_CP + NCOL;                    // [2][CL][NCOL] partials received from the cluster
+constexpr int OFF_RECV = OFF_V + NCOL;                     // [2][CL][NCOL] partials received from the cluster
 constexpr int OFF_X = OFF_RECV + 2 * CL * NCOL;            // union: GEMM chunks | per-warp column accumulators
 constexpr int X_GEMM = KC * AP + KC * BP + 64 + MAXM;      // A chunk, B chunk, n1, n2
 constexpr int X_ITER = (CNT / 32) * NCOL;
@@ -271,7 +270,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cl
     float* sS = sm + OFF_S;
     float* sU = sm + OFF_U;
     float* sV = sm + OFF_V;
-    float* sCP = sm + OFF_CP;
     float* sRecv = sm + OFF_RECV;
     float* sX = sm + OFF_X;
 
@@ -361,10 +359,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cl
             }
         }
         __syncthreads();
-        // dustbin column / row (sinkhorn.py:182-187)
-        for (int li = tid; li < nreal; li += CNT) sS[li * SPITCH + M] = a.dustbin2;
+        // dustbin column / row (sinkhorn.py:182-187); columns beyond M are -inf so that they drop
+        // out of every sum without a predicate
+        for (int e2 = tid; e2 < nloc * (NCOL - M); e2 += CNT) {
+            const int li = e2 / (NCOL - M), j = M + e2 % (NCOL - M);
+            sS[li * SPITCH + j] = (j == M) ? a.dustbin2 : -CUDART_INF_F;
+        }
         if (has_dust)
-            for (int j = tid; j <= M; j += CNT) sS[nreal * SPITCH + j] = a.dustbin2;
+            for (int j = tid; j < M; j += CNT) sS[nreal * SPITCH + j] = a.dustbin2;
     }
     for (int i = tid; i < 72; i += CNT) sU[i] = 0.0f;
     for (int i = tid; i < NCOL; i += CNT) sV[i] = 0.0f;
@@ -375,6 +377,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cl
     float vreg[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) vreg[k] = 0.0f;
+
+    // where this rank's partial sums land in each peer's receive buffer (parity 0)
+    float* peer_slot[CL];
+#pragma unroll
+    for (int dst = 0; dst < CL; ++dst) peer_slot[dst] = cluster.map_shared_rank(sRecv + rank * NCOL, dst);
 
     // make sure every CTA of the cluster is running before the first DSMEM store
     cluster.sync();
@@ -392,8 +399,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cl
             float rs = 0.0f;
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
-                const int c = lane + 32 * k;
-                e[k] = (c <= M) ? ex2((row[c] + vreg[k]) + u_old) : 0.0f;
+                e[k] = ex2((row[lane + 32 * k] + vreg[k]) + u_old);
                 rs += e[k];
             }
             rs = warp_sum(rs);
@@ -405,16 +411,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cl
                 // classic max-shifted logsumexp for this row (sinkhorn.py:140)
                 float m = -CUDART_INF_F;
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    const int c = lane + 32 * k;
-                    if (c <= M) m = fmaxf(m, row[c] + vreg[k]);
-                }
+                for (int k = 0; k < CPL; ++k) m = fmaxf(m, row[lane + 32 * k] + vreg[k]);
                 m = warp_max(m);
                 rs = 0.0f;
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
-                    const int c = lane + 32 * k;
-                    e[k] = (c <= M) ? ex2((row[c] + vreg[k]) - m) : 0.0f;
+                    e[k] = ex2((row[lane + 32 * k] + vreg[k]) - m);
                     rs += e[k];
                 }
                 rs = warp_sum(rs);
@@ -428,22 +430,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CNT, 1) sinkhorn_cl
 #pragma unroll
         for (int k = 0; k < CPL; ++k) sCW[warp * NCOL + lane + 32 * k] = colacc[k];
         __syncthreads();
-        // CTA partial per column, pushed into every cluster member's receive slot for this rank
-        float* recv = sRecv + (it & 1) * CL * NCOL;
-        for (int c = tid; c < NCOL; c += CNT) {
-            float s = 0.0f;
+        // CTA partial per column, pushed as float4 into every cluster member's receive slot for this
+        // rank (DSMEM stores; the peers' base addresses were mapped once before the loop)
+        if (tid < NCOL / 4) {
+            float4 s4 = *reinterpret_cast<const float4*>(sCW + 4 * tid);
 #pragma unroll
-            for (int w = 0; w < CNT / 32; ++w) s += sCW[w * NCOL + c];
-            sCP[c] = s;
-        }
-        __syncthreads();
-        for (int e2 = tid; e2 < CL * NCOL; e2 += CNT) {
-            const int dst = e2 / NCOL, c = e2 % NCOL;
-            float* remote = cluster.map_shared_rank(recv + rank * NCOL, dst);
-            remote[c] = sCP[c];
+            for (int w = 1; w < CNT / 32; ++w) {
+                const float4 t4 = *reinterpret_cast<const float4*>(sCW + w * NCOL + 4 * tid);
+                s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
+            }
+            const int off = (it & 1) * CL * NCOL + 4 * tid;
+#pragma unroll
+            for (int dst = 0; dst < CL; ++dst) *reinterpret_cast<float4*>(peer_slot[dst] + off) = s4;
         }
         cluster.sync();
         // v_j += log_nu_j - log(colsum_j)   (sinkhorn.py:142 with the shift -v_j)
+        const float* recv = sRecv + (it & 1) * CL * NCOL;
         for (int c = tid; c <= M; c += CNT) {
             float s = 0.0f;
 #pragma unroll
@@ -487,7 +489,7 @@ int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int 
     return OM_OK;
 }
 
-int g_force_generic_sinkhorn = 0;
+int g_sinkhorn_variant = 0;   // 0: tcgen05 cluster kernel, 1: FFMA cluster kernel, 2: generic kernels
 
 }  // namespace
 
@@ -504,8 +506,10 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
     if (B <= 0 || N <= 0 || M <= 0 || D <= 0) return OM_ERR_SHAPE;
     if (iterations <= 0 || !(epsilon > 0.0f)) return OM_ERR_PARAM;        // sinkhorn.py:66-69
     if (B > 65535) return OM_ERR_LIMIT;
-    const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && !g_force_generic_sinkhorn &&
+    const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && g_sinkhorn_variant != 2 &&
                       (long long)B * CL < (1ll << 31);
+    if (fast && g_sinkhorn_variant == 0)
+        return sinkhorn_cluster_tc(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
     if (fast) return sinkhorn_cluster(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
     if (ws == nullptr || ws_bytes < sinkhorn_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
     // dustbin score is computed in double by the reference (python floats) and cast once, sinkhorn.py:182
@@ -517,7 +521,8 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
 
 using namespace om;
 
-extern "C" void om_debug_force_generic_sinkhorn(int on) { g_force_generic_sinkhorn = on; }
+extern "C" void om_debug_force_generic_sinkhorn(int on) { g_sinkhorn_variant = on ? 2 : 0; }
+extern "C" void om_debug_sinkhorn_variant(int variant) { g_sinkhorn_variant = variant; }
 
 extern "C" size_t om_sinkhorn_workspace_bytes(int B, int N, int M, int D) { return sinkhorn_workspace_bytes(B, N, M, D); }
 

@@ -59,7 +59,13 @@ _SOBEL = torch.tensor([[[[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]]],
                        [[[-1., -2., -1.], [0., 0., 0.], [1., 2., 1.]]]])  # shi_tomasi.py:45-59
 
 
-def shi_tomasi_score(image: torch.Tensor, block_size: int = 3) -> torch.Tensor:
+def shi_tomasi_score(image: torch.Tensor, block_size: int = 3, ieee_sqrt: bool = False) -> torch.Tensor:
+    """ieee_sqrt=False is the reference verbatim.  NOTE: torch.sqrt on CPU goes through MKL VML
+    (vsSqrt, HA mode), which is NOT correctly rounded: it differs from IEEE-754 sqrt by 1 ulp on
+    ~0.6 % of inputs, and the pattern depends on the MKL code path of the host CPU.  The reference's
+    score map is therefore not reproducible to the last bit even between two x86 hosts.
+    ieee_sqrt=True swaps in the correctly rounded sqrt (numpy) -- the variant a CUDA kernel using
+    sqrt.rn.f32 must match bit-for-bit on integer-valued images."""
     img = image.float()                                                   # :78
     g = F.conv2d(F.pad(img, (1, 1, 1, 1), mode="replicate"), _SOBEL)      # :82-83 (cross-correlation)
     ix, iy = g[:, 0:1], g[:, 1:2]
@@ -71,7 +77,9 @@ def shi_tomasi_score(image: torch.Tensor, block_size: int = 3) -> torch.Tensor:
     half_trace = (a + c) / 2                                              # :102
     diff_half = (a - c) / 2                                               # :103
     disc = diff_half * diff_half + bb * bb                                # :104
-    lam = half_trace - torch.sqrt(disc + 1e-10)                           # :105-107
+    arg = disc + 1e-10                                                    # :105
+    root = torch.from_numpy(np.sqrt(arg.numpy())) if ieee_sqrt else torch.sqrt(arg)
+    lam = half_trace - root                                               # :105-107
     return torch.clamp(lam, min=0.0)                                      # :110
 
 

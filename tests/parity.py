@@ -10,8 +10,19 @@ from __future__ import annotations
 import torch
 
 DESC_TOL = 1e-5
+# soft binarisation is sigmoid(-10 * centered): it multiplies the reference's own conv2d rounding
+# noise on the box means (up to 2e-4 abs) by 2.5, so agreement with ANY exact
+# box-mean implementation is limited to ~5e-5 on the normalised descriptor
+DESC_TOL_SOFT = 1e-4
 PROB_TOL = 1e-4
 ARGMAX_MIN = 0.999
+SCORE_REL_TOL = 4e-7      # keypoint scores: the reference's MKL sqrt is off by <= 1 ulp of the sqrt term
+
+
+def scores_close(s_test: torch.Tensor, s_ref: torch.Tensor) -> bool:
+    s_test, s_ref = s_test.cpu(), s_ref.cpu()
+    return bool(((s_test - s_ref).abs() <= SCORE_REL_TOL * 64 * s_ref.abs().clamp_min(1.0)).all()) and \
+        bool(((s_test > 0) == (s_ref > 0)).all())
 
 
 def keypoint_mismatches(k_test: torch.Tensor, k_ref: torch.Tensor, s_ref: torch.Tensor | None = None) -> int:
@@ -37,13 +48,13 @@ def keypoint_mismatches(k_test: torch.Tensor, k_ref: torch.Tensor, s_ref: torch.
     return bad
 
 
-def desc_metrics(d_test: torch.Tensor, d_ref: torch.Tensor) -> dict:
+def desc_metrics(d_test: torch.Tensor, d_ref: torch.Tensor, tol: float = DESC_TOL) -> dict:
     d_test, d_ref = d_test.cpu(), d_ref.cpu()
     err = (d_test - d_ref).abs()
     scale = d_ref.abs().amax().clamp_min(1.0)
-    row_ok = (err.amax(dim=-1) <= DESC_TOL * scale)
+    row_ok = (err.amax(dim=-1) <= tol * scale)
     return dict(max_abs=float(err.max()), max_rel_to_scale=float(err.max() / scale),
-                rows_within=float(row_ok.float().mean()), elems_over=float((err > DESC_TOL * scale).float().mean()))
+                rows_within=float(row_ok.float().mean()), elems_over=float((err > tol * scale).float().mean()))
 
 
 def prob_metrics(p_test: torch.Tensor, p_ref: torch.Tensor) -> dict:
