@@ -193,6 +193,9 @@ void om_debug_force_generic_stencil(int on);
 void om_debug_force_generic_sinkhorn(int on);
 /* 0: tcgen05/TMEM cluster kernel (default), 1: FP32-FFMA cluster kernel, 2: generic kernels. */
 void om_debug_sinkhorn_variant(int variant);
+/* Device buffer of (B*8 CTAs) x 12 int64: the tcgen05 kernel stores clock64 stamps of its phases there
+ * (NULL switches tracing off).  Used by tools/sinkhorn_trace.py only. */
+void om_debug_sinkhorn_trace(long long* device_buffer);
 
 /* Single-kernel slices of om_detect_f32 / om_dense_bad_at_kpts_f32 so that bench.py can time each
  * kernel with CUDA events.  stage 0 = first kernel(s), stage 1 = the last kernel (needs stage 0's

@@ -28,8 +28,9 @@ namespace om {
 namespace {
 
 constexpr int CL = 8;               // CTAs per cluster == per descriptor pair
-constexpr int NT = 512;             // threads per CTA
-constexpr int NW = NT / 32;
+constexpr int NW = 16;              // producer / sweep warps
+constexpr int NP = NW * 32;         // producer threads (stage the GEMM operands, run the Sinkhorn sweep)
+constexpr int NT = NP + 32;         // + one warp whose lane 0 issues the tcgen05.mma stream
 constexpr int RPC = 64;             // real score rows per CTA
 constexpr int MAXM = 512;
 constexpr int NCOL = 544;           // 17 columns per lane; columns beyond M hold -inf
@@ -54,10 +55,13 @@ constexpr int OFF_RECV = OFF_V + NCOL;                     // [2][CL][NCOL] colu
 constexpr int OFF_CW = OFF_RECV + 2 * CL * NCOL;           // [NW][NCOL] per-warp column accumulators
 constexpr int OFF_N1 = OFF_CW + NW * NCOL;                 // squared norms of the local d1 rows
 constexpr int OFF_N2 = OFF_N1 + 64;                        // squared norms of all d2 rows
-constexpr int OFF_BAR = OFF_N2 + MAXM;                     // 3 mbarriers + TMEM base address
-constexpr int SMEM_FLOATS = OFF_BAR + 8;
+constexpr int OFF_CP = OFF_N2 + MAXM;                      // [2][NCOL] this CTA's column partials (bulk-copy source)
+constexpr int OFF_BAR = OFF_CP + 2 * NCOL;                 // 7 mbarriers + TMEM base address
+constexpr int SMEM_FLOATS = OFF_BAR + 16;
+constexpr uint32_t PART_BYTES = NCOL * 4;                  // one rank's partial column sums
 static_assert(2 * STAGE_BYTES <= OFF_N1 * 4, "staging must not reach the norms / barriers");
-static_assert((OFF_BAR * 4) % 8 == 0 && (OFF_RECV * 4) % 16 == 0 && (OFF_CW * 4) % 16 == 0, "alignment");
+static_assert((OFF_BAR * 4) % 8 == 0 && (OFF_RECV * 4) % 16 == 0 && (OFF_CW * 4) % 16 == 0 && (OFF_CP * 4) % 16 == 0,
+              "alignment");
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -82,6 +86,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// DSMEM bulk copy: local shared memory -> a peer CTA's shared memory, completion on the PEER's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 // UMMA shared-memory descriptor, no swizzle, K-major (cute/arch/mma_sm100_desc.hpp layout)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -134,7 +154,13 @@ struct TcArgs {
     float scale2;       // log2(e)/eps
     float dustbin2;     // (-unused/eps) * log2(e)
     float* P;
+    long long* trace;   // optional (debug): per CTA 8 clock64 stamps
 };
+
+#define OM_STAMP(slot)                                                                   \
+    do {                                                                                 \
+        if (a.trace != nullptr && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); \
+    } while (0)
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_kernel(TcArgs a) {
     extern __shared__ __align__(128) float sm[];
@@ -151,8 +177,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
     float* sCW = sm + OFF_CW;
     float* sN1 = sm + OFF_N1;
     float* sN2 = sm + OFF_N2;
+    float* sCP = sm + OFF_CP;
+    // [0,1] stage free (MMAs done), [2] GEMM done, [3,4] partials landed, [5,6] stage full (operands stored)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int r0 = rank * RPC;
     const int nreal = max(0, min(RPC, N - r0));
@@ -164,6 +192,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         mbar_init(smem_u32(&bars[0]), 1);
         mbar_init(smem_u32(&bars[1]), 1);
         mbar_init(smem_u32(&bars[2]), 1);
+        mbar_init(smem_u32(&bars[3]), 1);
+        mbar_init(smem_u32(&bars[4]), 1);
+        mbar_init(smem_u32(&bars[5]), NP);
+        mbar_init(smem_u32(&bars[6]), NP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -175,6 +207,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    OM_STAMP(0);
 
     // ---------------- similarity GEMM on tcgen05 -------------------------------------------------
     {
@@ -184,31 +217,59 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         const int lrow = tid >> 2, lkq = tid & 3;                   // loader: row (+128q), 16-byte K unit
         float nb[4] = {0.f, 0.f, 0.f, 0.f}, na = 0.f;
         const int nchunks = D / KC;
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c & 1;
-            if (c >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 done
-            char* st = reinterpret_cast<char*>(sm) + s * STAGE_BYTES;
+        if (warp < NW) {
+            // ===== producers: global -> registers (two chunks ahead) -> hi/lo split -> UMMA layout in smem =====
+            float4 pa[4], pb = make_float4(0.f, 0.f, 0.f, 0.f);      // chunk c+1
+            float4 qa[4], qb = make_float4(0.f, 0.f, 0.f, 0.f);      // chunk c+2
+            auto fetch = [&](int c, float4 (&ra)[4], float4& rb) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int j = lrow + 128 * q;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
-                if (j < M) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)j * D + c * KC + 4 * lkq));
-                nb[q] = sq4(v, nb[q]);
-                split_tf32(v, hi, lo);
-                *reinterpret_cast<float4*>(st + lkq * A_LBO + j * 16) = hi;
-                *reinterpret_cast<float4*>(st + A_TILE + lkq * A_LBO + j * 16) = lo;
+                for (int q = 0; q < 4; ++q) {
+                    const int j = lrow + 128 * q;
+                    ra[q] = (j < M && c < nchunks)
+                                ? __ldg(reinterpret_cast<const float4*>(A + (size_t)j * D + c * KC + 4 * lkq))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (tid < 4 * B_ROWS)
+                    rb = (lrow < nreal && c < nchunks)
+                             ? __ldg(reinterpret_cast<const float4*>(Bm + (size_t)lrow * D + c * KC + 4 * lkq))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            fetch(0, pa, pb);
+            fetch(1, qa, qb);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c & 1;
+                const float4 va[4] = {pa[0], pa[1], pa[2], pa[3]};
+                const float4 vb = pb;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pa[q] = qa[q];
+                pb = qb;
+                if (c >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 done
+                char* st = reinterpret_cast<char*>(sm) + s * STAGE_BYTES;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = lrow + 128 * q;
+                    float4 hi, lo;
+                    nb[q] = sq4(va[q], nb[q]);
+                    split_tf32(va[q], hi, lo);
+                    *reinterpret_cast<float4*>(st + lkq * A_LBO + j * 16) = hi;
+                    *reinterpret_cast<float4*>(st + A_TILE + lkq * A_LBO + j * 16) = lo;
+                }
+                if (tid < 4 * B_ROWS) {
+                    float4 hi, lo;
+                    na = sq4(vb, na);
+                    split_tf32(vb, hi, lo);
+                    *reinterpret_cast<float4*>(st + 2 * A_TILE + lkq * B_LBO + lrow * 16) = hi;
+                    *reinterpret_cast<float4*>(st + 2 * A_TILE + B_TILE + lkq * B_LBO + lrow * 16) = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
+                mbar_arrive(smem_u32(&bars[5 + s]));                            // stage s is full
+                fetch(c + 2, qa, qb);
             }
-            if (tid < 4 * B_ROWS) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
-                if (lrow < nreal) v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)lrow * D + c * KC + 4 * lkq));
-                na = sq4(v, na);
-                split_tf32(v, hi, lo);
-                *reinterpret_cast<float4*>(st + 2 * A_TILE + lkq * B_LBO + lrow * 16) = hi;
-                *reinterpret_cast<float4*>(st + 2 * A_TILE + B_TILE + lkq * B_LBO + lrow * 16) = lo;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
-            __syncthreads();
-            if (tid == 0) {
+        } else if (lane == 0) {
+            // ===== MMA issuer: one thread drives the tensor core, never touches the operands itself =====
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c & 1;
+                mbar_wait(smem_u32(&bars[5 + s]), (uint32_t)((c >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = stage0 + s * STAGE_BYTES;
 #pragma unroll
@@ -225,32 +286,35 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                         umma_tf32(d, alo, bhi, 1u);
                     }
                 }
-                umma_commit(smem_u32(&bars[s]));
+                umma_commit(smem_u32(&bars[s]));                    // frees stage s when these MMAs retire
                 if (c == nchunks - 1) umma_commit(smem_u32(&bars[2]));
             }
         }
+        __syncwarp();
         // squared norms (4 loader threads share a row), sinkhorn.py:98-99
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v = nb[q];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (lkq == 0) sN2[lrow + 128 * q] = v;
+            if (lkq == 0 && warp < NW) sN2[lrow + 128 * q] = v;
         }
         na += __shfl_xor_sync(0xffffffffu, na, 1);
         na += __shfl_xor_sync(0xffffffffu, na, 2);
         if (lkq == 0 && tid < 4 * B_ROWS) sN1[lrow] = na;
 
+        OM_STAMP(1);                                                // all chunks staged, last MMAs in flight
         mbar_wait(smem_u32(&bars[2]), 0u);                          // every MMA has completed
+        OM_STAMP(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         __syncthreads();                                            // norms visible; staging area is dead
 
         // epilogue: warp (mb, q) reads TMEM lanes 32q..32q+31 of M-block mb: lane = column j, regs = rows i
-        const int mb = warp >> 2, q = warp & 3;
+        const int mb = (warp >> 2) & 3, q = warp & 3;
         const int j = 128 * mb + 32 * q + lane;
         const float n2j = sN2[j];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 2 && warp < NW; ++half) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(mb * 64 + 32 * half), r);
 #pragma unroll
@@ -275,6 +339,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         if (has_dust)
             for (int jj = tid; jj < M; jj += NT) sS[nreal * SPITCH + jj] = a.dustbin2;
     }
+    OM_STAMP(3);                                                    // epilogue done
     for (int i = tid; i < 72; i += NT) sU[i] = 0.0f;
     for (int i = tid; i < NCOL; i += NT) sV[i] = 0.0f;
     __syncthreads();
@@ -284,32 +349,43 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
     float vreg[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) vreg[k] = 0.0f;
-    float* peer_slot[CL];
+    // peers' receive slots for this rank and their "partials landed" barriers, as shared::cluster addresses
+    uint32_t peer_slot[CL], peer_bar[CL];
 #pragma unroll
-    for (int dst = 0; dst < CL; ++dst) peer_slot[dst] = cluster.map_shared_rank(sRecv + rank * NCOL, dst);
-    cluster.sync();      // every CTA of the cluster is past its GEMM (its staging aliased sRecv) before any DSMEM store
+    for (int dst = 0; dst < CL; ++dst) {
+        peer_slot[dst] = mapa_u32(smem_u32(sRecv + rank * NCOL), (uint32_t)dst);
+        peer_bar[dst] = mapa_u32(smem_u32(&bars[3]), (uint32_t)dst);
+    }
+    // every CTA of the cluster is past its GEMM (its staging aliased sRecv) and has initialised its barriers
+    cluster.sync();
 
+    OM_STAMP(4);                                                    // cluster is ready
+    long long t_wait = 0, t_sweep = 0, t_red = 0, t_vup = 0;
+    const bool tr = a.trace != nullptr;
     for (int it = 0; it < a.iterations; ++it) {
+        const int par = it & 1;
+        const long long ts0 = tr ? clock64() : 0;
         float colacc[CPL];
 #pragma unroll
         for (int k = 0; k < CPL; ++k) colacc[k] = 0.0f;
         for (int li = warp; li < nloc; li += NW) {
             const bool dust_row = has_dust && li == nreal;
             const float mu = dust_row ? (float)M : 1.0f;
-            const float u_old = sU[li];
             const float* row = sS + li * SPITCH + lane;
+            // exp(S_ij + v_j) without the u_i shift: the row factor 2^u_i cancels in mu_i / rowsum, so it is
+            // only needed for range -- and the range check below falls back to the max shift when it matters
             float e[CPL];
-            float rs = 0.0f;
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                e[k] = ex2((row[32 * k] + vreg[k]) + u_old);
-                rs += e[k];
-            }
+            for (int k = 0; k < CPL; ++k) e[k] = ex2(row[32 * k] + vreg[k]);
+            float r0s = e[0], r1s = e[1], r2s = e[2], r3s = e[3];
+#pragma unroll
+            for (int k = 4; k + 3 < CPL; k += 4) { r0s += e[k]; r1s += e[k + 1]; r2s += e[k + 2]; r3s += e[k + 3]; }
+            float rs = ((r0s + r1s) + (r2s + r3s)) + e[CPL - 1];
             rs = warp_sum(rs);
             float u_new, f;
             if (rs >= 1e-30f && rs <= 1e30f) {
                 f = __fdividef(mu, rs);
-                u_new = u_old + ((dust_row ? log2_m : 0.0f) - lg2(rs));
+                u_new = (dust_row ? log2_m : 0.0f) - lg2(rs);
             } else {
                 float m = -CUDART_INF_F;                              // classic max shift, sinkhorn.py:140
 #pragma unroll
@@ -331,20 +407,34 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         }
 #pragma unroll
         for (int k = 0; k < CPL; ++k) sCW[warp * NCOL + lane + 32 * k] = colacc[k];
+        const long long ts1 = tr ? clock64() : 0;
         __syncthreads();
-        if (tid < NCOL / 4) {
-            float4 s4 = *reinterpret_cast<const float4*>(sCW + 4 * tid);
+        // CTA partial per column -> local staging buffer (double buffered by parity)
+        for (int c = tid; c < NCOL; c += NT) {
+            float s0 = sCW[c], s1 = sCW[NCOL + c], s2 = sCW[2 * NCOL + c], s3 = sCW[3 * NCOL + c];
 #pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const float4 t4 = *reinterpret_cast<const float4*>(sCW + w * NCOL + 4 * tid);
-                s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
+            for (int w = 4; w < NW; w += 4) {
+                s0 += sCW[w * NCOL + c]; s1 += sCW[(w + 1) * NCOL + c];
+                s2 += sCW[(w + 2) * NCOL + c]; s3 += sCW[(w + 3) * NCOL + c];
             }
-            const int off = (it & 1) * CL * NCOL + 4 * tid;
-#pragma unroll
-            for (int dst = 0; dst < CL; ++dst) *reinterpret_cast<float4*>(peer_slot[dst] + off) = s4;
+            sCP[par * NCOL + c] = (s0 + s1) + (s2 + s3);
         }
-        cluster.sync();
-        const float* recv = sRecv + (it & 1) * CL * NCOL;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // bulk copy (async proxy) reads it next
+        __syncthreads();
+        // one thread: arm this CTA's barrier for the 8 incoming partials, then push ours to every CTA of the
+        // cluster (incl. ourselves) with DSMEM bulk copies that complete on the receivers' barriers
+        if (tid == 0) {
+            mbar_arrive_expect_tx(smem_u32(&bars[3 + par]), CL * PART_BYTES);
+            const uint32_t src = smem_u32(sCP + par * NCOL);
+#pragma unroll
+            for (int dst = 0; dst < CL; ++dst)
+                bulk_copy_to_peer(peer_slot[dst] + par * CL * PART_BYTES, src, PART_BYTES, peer_bar[dst] + par * 8);
+        }
+        const long long tw0 = tr ? clock64() : 0;
+        mbar_wait(smem_u32(&bars[3 + par]), (uint32_t)((it >> 1) & 1));
+        const long long tw1 = tr ? clock64() : 0;
+        // v_j += log_nu_j - log(colsum_j)   (sinkhorn.py:142 with the shift -v_j)
+        const float* recv = sRecv + par * CL * NCOL;
         for (int c = tid; c <= M; c += NT) {
             float s = 0.0f;
 #pragma unroll
@@ -354,8 +444,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < CPL; ++k) vreg[k] = sV[lane + 32 * k];
+        if (tr) {
+            const long long te = clock64();
+            t_sweep += ts1 - ts0; t_red += tw0 - ts1; t_wait += tw1 - tw0; t_vup += te - tw1;
+        }
     }
 
+    OM_STAMP(5);                                                    // iterations done
+    if (tr && tid == 0) {
+        // packed: 4 x 16-bit-shifted averages would lose precision; store wait in slot 7, others after the stamps
+        a.trace[(size_t)blockIdx.x * 8 + 7] = t_wait;
+        a.trace[(size_t)gridDim.x * 8 + (size_t)blockIdx.x * 4 + 0] = t_sweep;
+        a.trace[(size_t)gridDim.x * 8 + (size_t)blockIdx.x * 4 + 1] = t_red;
+        a.trace[(size_t)gridDim.x * 8 + (size_t)blockIdx.x * 4 + 2] = t_vup;
+    }
     // P = exp(S + u + v) (sinkhorn.py:145, :206)
     float* Pz = a.P + (size_t)z * (N + 1) * (M + 1);
     for (int li = warp; li < nloc; li += NW) {
@@ -370,14 +472,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
             if (c <= M) out[c] = ex2((row[c] + u) + vreg[k]);
         }
     }
+    OM_STAMP(6);
     cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
 }
 
 }  // namespace
 
+long long* g_tc_trace = nullptr;   // debug: device buffer of B*8 CTAs x 8 stamps, set through om_debug_sinkhorn_trace
+
 int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                         float unused, float* P, cudaStream_t st) {
     TcArgs a{};
+    a.trace = g_tc_trace;
     a.d1 = d1; a.d2 = d2; a.N = N; a.M = M; a.D = D; a.iterations = iterations; a.P = P;
     const double log2e = 1.4426950408889634;
     a.scale2 = (float)(log2e / (double)eps);
@@ -390,3 +496,5 @@ int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, i
 }
 
 }  // namespace om
+
+extern "C" void om_debug_sinkhorn_trace(long long* device_buffer) { om::g_tc_trace = device_buffer; }
