@@ -204,11 +204,13 @@ def per_kernel_times(model, workload, i1, i2, steps, warmup):
         mk = model.detector.angle_estimator.moment_kernels if workload == "angle" else None
         ps = int(mk.shape[-1]) if mk is not None else 0
 
+        bws = torch.empty(lib.om_sparse_bad_workspace_bytes(B, H, W, theta), dtype=torch.uint8, device=dev)
+
         def sb():
             nat.check(lib.om_sparse_bad_f32(ptr(i1), B, H, W, ptr(kp), K, ptr(table), P, mode, float(d.temperature),
                                             int(d.normalize_descriptors), _ops.sampling_code(d.sampling_mode), theta,
                                             ctypes.c_void_p(0), ptr(mk) if mk is not None else ctypes.c_void_p(0), ps,
-                                            ptr(desc), sp), "om_sparse_bad_f32")
+                                            ptr(desc), ptr(bws), bws.numel(), sp), "om_sparse_bad_f32")
         out["sparse_bad_kernel"] = dict(ms=event_time_ms(sb, steps, warmup, st), per_step=2,
                                         bytes=B * (K * 8 + K * P * 4))
     d2 = torch.nn.functional.normalize(torch.randn((B, K, P), device=dev), dim=-1)

@@ -108,15 +108,19 @@ int om_angle_map_f32(const float* image, int B, int H, int W, const float* momen
 /* pair_table: (P,6) floats {ox1, ox2, oy1, oy2, radius, threshold}, offsets relative to the
  * keypoint (descriptor/bad.py:405-410), integer-valued, |offset| <= 15, radius in [0,7]. */
 
+size_t om_sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode);
+
 /* SparseBAD.forward, descriptor/bad.py:436-576.  theta_mode selects the oriented branch
  * (:487-517); `orientation` is the (B,H,W) map for OM_THETA_MAP; moment_kernels/patch_size are
- * used by OM_THETA_MOMENTS (same result as running AngleEstimator on the whole image first). */
+ * used by OM_THETA_MOMENTS (same result as running AngleEstimator on the whole image first).
+ * The workspace holds the exact integral image of the padded image (built once per call, sampled
+ * at the keypoints only) -- instead of the reference's 8-channel box-average bank. */
 int om_sparse_bad_f32(const float* image, int B, int H, int W, const float* kpts, int K,
                       const float* pair_table, int P, int desc_mode, float temperature,
                       int normalize, int sampling_mode,
                       int theta_mode, const float* orientation,
                       const float* moment_kernels, int patch_size,
-                      float* desc /* B,K,P */, void* stream);
+                      float* desc /* B,K,P */, void* ws, size_t ws_bytes, void* stream);
 
 size_t om_dense_bad_workspace_bytes(int B, int H, int W);
 

@@ -43,8 +43,10 @@ SIGNATURES = {
     "om_detect_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size_t, c_void_p]),
     "om_angle_map_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "om_sparse_bad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "om_sparse_bad_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float,
-                                  c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                                  c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "om_dense_bad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "om_dense_bad_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),

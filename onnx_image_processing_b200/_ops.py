@@ -170,8 +170,10 @@ def sparse_bad(image: torch.Tensor, keypoints: torch.Tensor, pair_table: torch.T
     ps = int(mk.shape[-1]) if mk is not None else 0
     lib, st = _begin(img)
     out = torch.empty((B, K, P), dtype=torch.float32, device=img.device)
+    ws = _ws(lib.om_sparse_bad_workspace_bytes(B, H, W, theta_mode), img)
     nat.check(lib.om_sparse_bad_f32(_p(img), B, H, W, _p(kp), K, _p(tb), P, mode, float(temperature), int(normalize),
-                                    sampling, theta_mode, _p(ori), _p(mk), ps, _p(out), st), "om_sparse_bad_f32")
+                                    sampling, theta_mode, _p(ori), _p(mk), ps, _p(out), _p(ws), ws.numel(), st),
+              "om_sparse_bad_f32")
     return out
 
 

@@ -7,7 +7,35 @@
 
 namespace om {
 unsigned long long g_launches = 0;
+
+// cuTensorMapEncodeTiled lives in libcuda; the library links the runtime statically and does not link the
+// driver, so the entry point is resolved through the runtime the first time a tensor map is needed.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_3d(CUtensorMap* map, bool is_float, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t pitch_elems, uint32_t box0, uint32_t box1) {
+    static EncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        OM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return OM_ERR_CUDA_BASE + (int)cudaErrorNotSupported;
+        encode = (EncodeTiledFn)fn;
+    }
+    if (pitch_elems % 4 != 0 || ((uintptr_t)base & 15) != 0 || box0 % 4 != 0 || box0 > 256 || box1 > 256) return OM_ERR_PARAM;
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {pitch_elems * 4, pitch_elems * 4 * d1};     // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {box0, box1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(map, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
+                              const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? OM_OK : OM_ERR_CUDA_BASE + (int)cudaErrorInvalidValue;
 }
+}  // namespace om
 
 using namespace om;
 
@@ -76,7 +104,10 @@ MatchWs plan(const om_match_params* p, void* base) {
     const size_t db = align_up((size_t)p->B * p->K * p->P * sizeof(float));
     w.desc1 = (float*)(c + off); off += db;
     w.desc2 = (float*)(c + off); off += db;
-    w.dense_bytes = p->flavour == OM_MATCH_DENSE ? dense_bad_workspace_bytes(p->B, p->H, p->W) : 0;
+    w.dense_bytes = p->flavour == OM_MATCH_DENSE
+                        ? dense_bad_workspace_bytes(p->B, p->H, p->W)
+                        : sparse_bad_workspace_bytes(p->B, p->H, p->W,
+                                                     p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE);
     w.dense = c + off; off += align_up(w.dense_bytes);
     w.sink_bytes = sinkhorn_workspace_bytes(p->B, p->K, p->K, p->P);
     w.sink = c + off; off += align_up(w.sink_bytes);
@@ -118,7 +149,7 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
             const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
             OM_TRY(sparse_bad_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
                                      p->temperature, p->normalize, p->sampling_mode, theta, nullptr, moment_kernels,
-                                     p->patch_size, ds[s], st));
+                                     p->patch_size, ds[s], w.dense, w.dense_bytes, st));
         }
     }
     return sinkhorn_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,

@@ -18,6 +18,8 @@
 // to ~1 grey level and parity is against the reference, not the maths.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace om {
@@ -26,6 +28,10 @@ namespace {
 
 constexpr int TPG = 64;          // threads per keypoint group
 constexpr int MAXR = 7;          // largest box radius in the tables
+
+// row pitch (elements) of an integral image with replicate padding `pad` and the zero column: a multiple of 4
+// so that rows are 16-byte aligned and a keypoint's window is one TMA box
+__host__ __device__ inline int ipitch(int W, int pad) { return (W + 2 * pad + 1 + 3) / 4 * 4; }
 
 struct PairRow {
     float ox1, ox2, oy1, oy2, r, thr;
@@ -58,15 +64,6 @@ __device__ __forceinline__ float finish_value(float diff, float thr, int mode, f
     return centered <= 0.0f ? 1.0f : 0.0f;
 }
 
-// sum of `v` over the TPG threads of one keypoint group (2 warps); red is per-CTA scratch [groups][2]
-__device__ __forceinline__ float group_sum(float v, float* red, int g, int t) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((t & 31) == 0) red[g * 2 + (t >> 5)] = v;
-    __syncthreads();
-    return red[g * 2] + red[g * 2 + 1];
-}
-
 struct SparseArgs {
     const float* image;
     int B, H, W;
@@ -84,57 +81,130 @@ struct SparseArgs {
     int patch_size;
     float* desc;
     float sy, sx;              // float32(2/(dim-1+1e-8)), bad.py:469-470
+    const unsigned int* flags; // per image: 1 = has a pixel that is not an integer in [0,65535]
+    int pad;                   // replicate padding baked into the uint32 integral (window kernel)
 };
 
-// HS: patch half size; GROUPS keypoints per CTA
-template <int HS, int GROUPS>
+// ---- sparse BAD, general kernel (any float image) ----------------------------------------------
+// Used for the images the exact-uint32 window kernel below cannot take (flags[image] set).
+// One 64-thread group (two warps, own named barrier) per keypoint, GROUPS keypoints per CTA.
+//   1. patch -> exact integral image in shared memory (fp64: exact for integer AND float images).
+//      Non-oriented: thread t owns patch column t, adds its S pixels top-down straight from global
+//      memory (column prefix), then thread t owns row t (row prefix).  Oriented: the raw patch is
+//      stored first because the 15x15 moments at the keypoint need the pixels themselves.
+//   2. interior fast path (non-oriented, nearest, integer keypoint, patch fully inside the image --
+//      ~88 % of keypoints at 480x640 with the default margin): nothing clamps, so the 8 integral taps
+//      of every pair sit at keypoint-independent shared-memory offsets, precomputed once per CTA.
+//      Everything else goes through the coordinate pipeline of grid_sample (general path).
+//   3. box mean = float(exact sum) * float(1/area): the reference's bank weights are exactly
+//      float(1/area) (bad.py:426-434), so this is its arithmetic with an exact accumulator.
+// HS: patch half size.  Nearest / bilinear sample centres are at most 16 px from the rounded
+// keypoint (15 offset + two roundings), + radius 7 -> HS = 23; rotated offsets reach 22 + 7 -> 30.
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TPG) : "memory"); }
+
+// sum of `v` over the TPG threads of one keypoint group; red is per-CTA scratch [groups][2]
+__device__ __forceinline__ float group_sum(float v, float* red, int g, int t) {
+    v = warp_sum(v);
+    group_bar(g);
+    if ((t & 31) == 0) red[g * 2 + (t >> 5)] = v;
+    group_bar(g);
+    return red[g * 2] + red[g * 2 + 1];
+}
+
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
 __global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) {
     constexpr int S = 2 * HS + 1;       // patch side
-    constexpr int PD = S + 2;           // odd pitch (in doubles) of the (S+1)x(S+1) integral
+    constexpr int PD = (S + 1) | 1;     // odd pitch (in doubles) of the (S+1)x(S+1) integral
+    constexpr bool FAST = !ORIENTED && !BILINEAR;
     extern __shared__ __align__(16) double sD[];
     __shared__ float red[GROUPS * 2];
     __shared__ float sTheta[GROUPS];
+    // fast-path tables, one entry per pair: 8 integral offsets (uint16) and {threshold, 1/area}
+    uint4* sTap = reinterpret_cast<uint4*>(sD + (size_t)GROUPS * (S + 1) * PD);
+    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));
 
     const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    if (FAST) {
+        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+            const PairRow row = load_pair(a.table, p);
+            const int r = (int)row.r;
+            const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
+            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * PD + x); };
+            uint4 tp;
+            tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
+            tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
+            tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
+            tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
+            sTap[p] = tp;
+            const float side = (float)(2 * r + 1);
+            sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
+        }
+        __syncthreads();
+    }
+
     const long long total = (long long)a.B * a.K;
-    long long kidx = (long long)blockIdx.x * GROUPS + g;
-    const bool live = kidx < total;
-    if (!live) kidx = total - 1;
+    const long long kidx = (long long)blockIdx.x * GROUPS + g;
+    if (kidx >= total) return;          // whole group leaves: later barriers are per group
     const int z = (int)(kidx / a.K);
+    if (a.flags != nullptr && a.flags[z] == 0u) return;   // integer-valued image: sparse_win_kernel did this keypoint
     const int H = a.H, W = a.W;
     const float* img = a.image + (size_t)z * H * W;
     double* D = sD + (size_t)g * (S + 1) * PD;
+    float* out = a.desc + (size_t)kidx * a.P;
 
     const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
-    const float valid = ky >= 0.0f ? 1.0f : 0.0f;                          // bad.py:461
+    if (!(ky >= 0.0f)) {                                                    // bad.py:461, :570 -> the row is all zeros
+        for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
+        return;
+    }
     const float yc = fminf(fmaxf(ky, 0.0f), (float)(H - 1));               // bad.py:464-465
     const float xc = fminf(fmaxf(kx, 0.0f), (float)(W - 1));
     const int iy0 = (int)nearbyintf(yc), ix0 = (int)nearbyintf(xc);
     const int py0 = iy0 - HS, px0 = ix0 - HS;                               // global coords of patch (0,0)
+    const bool inside = py0 >= 0 && px0 >= 0 && py0 + S <= H && px0 + S <= W;
 
-    // replicate-clamped patch (bad.py:474-478 pads the image, grid_sample clamps the centre).
-    // Thread t owns integral column t (patch column t-1): its clamped global column is fixed, rows
-    // are independent loads.  Row 0 / column 0 of the integral are zero.
-    static_assert(S + 1 <= TPG, "one thread per integral column");
-    if (t <= S) {
-        double* col = D + t;
-        col[0] = 0.0;
-        if (t == 0) {
-#pragma unroll 4
-            for (int dy = 1; dy <= S; ++dy) col[dy * PD] = 0.0;
-        } else {
-            const float* src = img + clampi(px0 + t - 1, 0, W - 1);
-#pragma unroll 8
-            for (int dy = 1; dy <= S; ++dy)
-                col[dy * PD] = (double)__ldg(src + (size_t)clampi(py0 + dy - 1, 0, H - 1) * W);
-        }
-    }
-    __syncthreads();
-
-    // orientation of this keypoint
     float ct = 1.0f, st = 0.0f;
-    if (a.theta_mode != OM_THETA_NONE) {
-        // nearest sample of the orientation map at the keypoint (bad.py:490-499)
+    if (!ORIENTED) {
+        // column prefix straight from global memory; row 0 / column 0 of the integral are zero
+        if (t < S) {
+            D[t + 1] = 0.0;
+            double acc = 0.0;
+            double* col = D + PD + t + 1;
+            if (inside) {
+                const float* src = img + (size_t)py0 * W + px0 + t;
+#pragma unroll
+                for (int dy = 0; dy < S; ++dy) { acc += (double)__ldg(src + (size_t)dy * W); col[dy * PD] = acc; }
+            } else {
+                // replicate-clamped patch (bad.py:474-478 pads the image, grid_sample clamps the centre)
+                const float* src = img + clampi(px0 + t, 0, W - 1);
+#pragma unroll 8
+                for (int dy = 0; dy < S; ++dy) {
+                    acc += (double)__ldg(src + (size_t)clampi(py0 + dy, 0, H - 1) * W);
+                    col[dy * PD] = acc;
+                }
+            }
+        } else if (t == S) {
+#pragma unroll 8
+            for (int dy = 0; dy <= S; ++dy) D[dy * PD] = 0.0;
+        }
+        group_bar(g);
+    } else {
+        static_assert(S + 1 <= TPG, "one thread per integral column");
+        if (t <= S) {
+            double* col = D + t;
+            col[0] = 0.0;
+            if (t == 0) {
+#pragma unroll 4
+                for (int dy = 1; dy <= S; ++dy) col[dy * PD] = 0.0;
+            } else {
+                const float* src = img + clampi(px0 + t - 1, 0, W - 1);
+#pragma unroll 8
+                for (int dy = 1; dy <= S; ++dy)
+                    col[dy * PD] = (double)__ldg(src + (size_t)clampi(py0 + dy - 1, 0, H - 1) * W);
+            }
+        }
+        group_bar(g);
+        // orientation of this keypoint: nearest sample of the orientation map (bad.py:490-499)
         const int ny = (int)nearbyintf(sample_coord(yc, a.sy, (float)(H - 1) * 0.5f, (float)(H - 1)));
         const int nx = (int)nearbyintf(sample_coord(xc, a.sx, (float)(W - 1) * 0.5f, (float)(W - 1)));
         float theta = 0.0f;
@@ -157,75 +227,92 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) 
             m10 = group_sum(m10, red, g, t);
             m01 = group_sum(m01, red, g, t);
             theta = atan2f(m01, m10);
+            if (t == 0) sTheta[g] = theta;      // one value for the whole group (sums are identical anyway)
+            group_bar(g);
+            theta = sTheta[g];
         }
-        if (t == 0) sTheta[g] = theta;
-        __syncthreads();
-        theta = sTheta[g];
         ct = cosf(theta);                                                   // bad.py:501-502
         st = sinf(theta);
+        group_bar(g);
+        if (t < S) {                                                        // column prefix
+            double acc = 0.0;
+            double* p = D + PD + (t + 1);
+#pragma unroll 8
+            for (int y = 0; y < S; ++y, p += PD) { acc += *p; *p = acc; }
+        }
+        group_bar(g);
     }
-    __syncthreads();
-
-    // exact integral image of the patch: column prefix, then row prefix
-    if (t < S) {
-        double acc = 0.0;
-        double* p = D + PD + (t + 1);
-        for (int y = 0; y < S; ++y, p += PD) { acc += *p; *p = acc; }
-    }
-    __syncthreads();
-    if (t < S) {
+    if (t < S) {                                                            // row prefix
         double acc = 0.0;
         double* p = D + (t + 1) * PD + 1;
+#pragma unroll
         for (int x = 0; x < S; ++x) { acc += p[x]; p[x] = acc; }
     }
-    __syncthreads();
-
-    const float hy = (float)(H - 1) * 0.5f, hx = (float)(W - 1) * 0.5f;
-    const float my = (float)(H - 1), mx = (float)(W - 1);
-
-    auto box_mean = [&](int cy, int cx, int r) -> float {
-        // cy,cx: integer sample centre in image coords; box of radius r on the replicate-padded image
-        const int pyc = clampi(cy - py0, r, S - 1 - r), pxc = clampi(cx - px0, r, S - 1 - r);
-        const int y0 = pyc - r, y1 = pyc + r + 1, x0 = pxc - r, x1 = pxc + r + 1;
-        const double s = D[y1 * PD + x1] - D[y0 * PD + x1] - D[y1 * PD + x0] + D[y0 * PD + x0];
-        const double side = (double)(2 * r + 1);
-        return (float)(s / (side * side));
-    };
-    auto sample = [&](float oy, float ox, int r) -> float {
-        float py, px;
-        if (a.theta_mode != OM_THETA_NONE) {                                // bad.py:504-517
-            const float dy = __fadd_rn(__fmul_rn(ox, st), __fmul_rn(oy, ct));
-            const float dx = __fsub_rn(__fmul_rn(ox, ct), __fmul_rn(oy, st));
-            py = __fadd_rn(yc, dy);
-            px = __fadd_rn(xc, dx);
-        } else {                                                            // bad.py:518-525
-            py = __fadd_rn(yc, oy);
-            px = __fadd_rn(xc, ox);
-        }
-        const float uy = sample_coord(py, a.sy, hy, my), ux = sample_coord(px, a.sx, hx, mx);
-        if (!a.bilinear) return box_mean((int)nearbyintf(uy), (int)nearbyintf(ux), r);   // half-to-even
-        const float fy = floorf(uy), fx = floorf(ux);
-        const float w = ux - fx, e = 1.0f - w, s = uy - fy, n = 1.0f - s;   // ATen bilinear weights
-        const int y_n = (int)fy, x_w = (int)fx;
-        const int y_s = min(y_n + 1, H - 1), x_e = min(x_w + 1, W - 1);     // weight is 0 where this clamps
-        const float nw = box_mean(y_n, x_w, r), ne = box_mean(y_n, x_e, r);
-        const float sw = box_mean(y_s, x_w, r), se = box_mean(y_s, x_e, r);
-        return nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
-    };
+    group_bar(g);
 
     constexpr int MAXPP = 8;   // pairs per thread: P <= 512
     float d[MAXPP];
     float ss = 0.0f;
+    const bool fast = FAST && inside && ky == (float)iy0 && kx == (float)ix0;
+    if (fast) {
 #pragma unroll
-    for (int q = 0; q < MAXPP; ++q) {
-        const int p = t + q * TPG;
-        d[q] = 0.0f;
-        if (p < a.P) {
-            const PairRow row = load_pair(a.table, p);
-            const int r = (int)row.r;
-            const float diff = __fsub_rn(sample(row.oy1, row.ox1, r), sample(row.oy2, row.ox2, r));   // bad.py:557
-            d[q] = __fmul_rn(finish_value(diff, row.thr, a.mode, a.temperature), valid);            // bad.py:570
-            ss = fmaf(d[q], d[q], ss);
+        for (int q = 0; q < MAXPP; ++q) {
+            const int p = t + q * TPG;
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const uint4 tp = sTap[p];
+                const float2 tb = sThr[p];
+                const double s1 = (D[tp.x & 0xFFFFu] - D[tp.x >> 16]) - (D[tp.y & 0xFFFFu] - D[tp.y >> 16]);
+                const double s2 = (D[tp.z & 0xFFFFu] - D[tp.z >> 16]) - (D[tp.w & 0xFFFFu] - D[tp.w >> 16]);
+                const float diff = __fsub_rn(__fmul_rn((float)s1, tb.y), __fmul_rn((float)s2, tb.y));   // bad.py:557
+                d[q] = finish_value(diff, tb.x, a.mode, a.temperature);
+                ss = fmaf(d[q], d[q], ss);
+            }
+        }
+    } else {
+        const float hy = (float)(H - 1) * 0.5f, hx = (float)(W - 1) * 0.5f;
+        const float my = (float)(H - 1), mx = (float)(W - 1);
+        auto box_mean = [&](int cy, int cx, int r, float inv_area) -> float {
+            // cy,cx: integer sample centre in image coords; box of radius r on the replicate-padded image
+            const int pyc = clampi(cy - py0, r, S - 1 - r), pxc = clampi(cx - px0, r, S - 1 - r);
+            const int y0 = pyc - r, y1 = pyc + r + 1, x0 = pxc - r, x1 = pxc + r + 1;
+            const double s = (D[y1 * PD + x1] - D[y0 * PD + x1]) - (D[y1 * PD + x0] - D[y0 * PD + x0]);
+            return __fmul_rn((float)s, inv_area);
+        };
+        auto sample = [&](float oy, float ox, int r, float inv_area) -> float {
+            float py, px;
+            if (ORIENTED) {                                                     // bad.py:504-517
+                const float dy = __fadd_rn(__fmul_rn(ox, st), __fmul_rn(oy, ct));
+                const float dx = __fsub_rn(__fmul_rn(ox, ct), __fmul_rn(oy, st));
+                py = __fadd_rn(yc, dy);
+                px = __fadd_rn(xc, dx);
+            } else {                                                            // bad.py:518-525
+                py = __fadd_rn(yc, oy);
+                px = __fadd_rn(xc, ox);
+            }
+            const float uy = sample_coord(py, a.sy, hy, my), ux = sample_coord(px, a.sx, hx, mx);
+            if (!BILINEAR) return box_mean((int)nearbyintf(uy), (int)nearbyintf(ux), r, inv_area);   // half-to-even
+            const float fy = floorf(uy), fx = floorf(ux);
+            const float w = ux - fx, e = 1.0f - w, s = uy - fy, n = 1.0f - s;   // ATen bilinear weights
+            const int y_n = (int)fy, x_w = (int)fx;
+            const int y_s = min(y_n + 1, H - 1), x_e = min(x_w + 1, W - 1);     // weight is 0 where this clamps
+            const float nw = box_mean(y_n, x_w, r, inv_area), ne = box_mean(y_n, x_e, r, inv_area);
+            const float sw = box_mean(y_s, x_w, r, inv_area), se = box_mean(y_s, x_e, r, inv_area);
+            return nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
+        };
+#pragma unroll
+        for (int q = 0; q < MAXPP; ++q) {
+            const int p = t + q * TPG;
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const PairRow row = load_pair(a.table, p);
+                const int r = (int)row.r;
+                const float side = (float)(2 * r + 1);
+                const float inv_area = __fdiv_rn(1.0f, side * side);
+                const float diff = __fsub_rn(sample(row.oy1, row.ox1, r, inv_area), sample(row.oy2, row.ox2, r, inv_area));
+                d[q] = finish_value(diff, row.thr, a.mode, a.temperature);
+                ss = fmaf(d[q], d[q], ss);
+            }
         }
     }
     float inv = 1.0f;
@@ -233,24 +320,231 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) 
         const float nrm = sqrtf(group_sum(ss, red, g, t));
         inv = 1.0f / fmaxf(nrm, 1e-12f);
     }
-    if (live) {
-        float* out = a.desc + (size_t)kidx * a.P;
 #pragma unroll
-        for (int q = 0; q < MAXPP; ++q) {
-            const int p = t + q * TPG;
-            if (p < a.P) out[p] = a.normalize ? d[q] * inv : d[q];
-        }
+    for (int q = 0; q < MAXPP; ++q) {
+        const int p = t + q * TPG;
+        if (p < a.P) out[p] = d[q] * inv;
     }
 }
 
-template <int HS, int GROUPS>
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
 int launch_sparse(const SparseArgs& a, cudaStream_t st) {
     constexpr int S = 2 * HS + 1;
-    constexpr size_t smem = (size_t)GROUPS * (S + 1) * (S + 2) * sizeof(double);
-    OM_TRY(set_smem(sparse_bad_kernel<HS, GROUPS>, smem));
+    constexpr int PD = (S + 1) | 1;
+    const size_t smem = (size_t)GROUPS * (S + 1) * PD * sizeof(double) +
+                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2)) : 0);
+    auto kernel = sparse_bad_kernel<HS, GROUPS, ORIENTED, BILINEAR>;
+    OM_TRY(set_smem(kernel, smem));
     const long long total = (long long)a.B * a.K;
     const unsigned grid = (unsigned)((total + GROUPS - 1) / GROUPS);
-    sparse_bad_kernel<HS, GROUPS><<<grid, GROUPS * TPG, smem, st>>>(a);
+    kernel<<<grid, GROUPS * TPG, smem, st>>>(a);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+// ---- sparse BAD, window kernel (the fast path) ------------------------------------------------------
+// The exact uint32 integral of the replicate-padded image exists in global memory (build_prefix<true>),
+// so a keypoint needs no arithmetic to get its patch: one TMA box load brings the (S+1)x(S+1) window of
+// the integral around the keypoint into shared memory (padding is baked into the integral: the window
+// is always in bounds), and every box sum is 4 taps in wrap-around uint32 arithmetic.
+//   * interior fast path (non-oriented, nearest, integer keypoint at least 15 px from the border, i.e.
+//     no sample centre clamps): the 8 taps of every pair sit at keypoint-independent window offsets,
+//     precomputed once per CTA.
+//   * general path: the fp32 normalise -> unnormalise -> clip -> round pipeline of grid_sample.
+// box mean = float(exact sum) * float(1/area): the reference's bank weights are exactly float(1/area)
+// (bad.py:426-434), so this is its arithmetic with an exact accumulator.
+// Images whose flag is set (a pixel that is not an integer in [0,65535]) are skipped here and handled by
+// sparse_bad_kernel (fp64 integral built per keypoint).
+// Window geometry: nearest / bilinear sample centres are at most 16 px from the rounded keypoint (15
+// offset + two roundings), + radius 7 -> HS = 23, window 48x48; rotated offsets reach 22 + 7 -> HS = 30,
+// window 62 rows x 64 columns (box width must be a multiple of 16 bytes).
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
+__global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_constant__ CUtensorMap tmap, SparseArgs a) {
+    constexpr int S = 2 * HS + 1;
+    constexpr int WR = S + 1;                    // window rows
+    constexpr int WP = (S + 1 + 3 + 3) / 4 * 4;  // TMA box width == shared-memory pitch: the box must start on a 16-byte
+                                                 // boundary in global memory, so it starts up to 3 columns early
+    constexpr int GSTRIDE = (WR * WP + 31) / 32 * 32;   // words per group, keeps every window 128-byte aligned
+    constexpr bool FAST = !ORIENTED && !BILINEAR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ float red[GROUPS * 2];
+    __shared__ float sTheta[GROUPS];
+    __shared__ __align__(8) unsigned long long bars[GROUPS];
+    unsigned int* sWin = reinterpret_cast<unsigned int*>(smem_raw);             // GROUPS x WR x WP
+    uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * GSTRIDE);            // fast path: 8 window offsets per pair
+    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));          //            {threshold, 1/area}
+
+    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < GROUPS; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_fence_init();
+    }
+    if (FAST) {
+        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+            const PairRow row = load_pair(a.table, p);
+            const int r = (int)row.r;
+            const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
+            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * WP + x); };
+            uint4 tp;
+            tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
+            tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
+            tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
+            tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
+            sTap[p] = tp;
+            const float side = (float)(2 * r + 1);
+            sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
+        }
+    }
+    __syncthreads();                             // barriers initialised, tables built
+
+    const long long total = (long long)a.B * a.K;
+    const long long kidx = (long long)blockIdx.x * GROUPS + g;
+    if (kidx >= total) return;                   // whole group leaves: later barriers are per group
+    const int z = (int)(kidx / a.K);
+    if (a.flags[z] != 0u) return;                // non-integer image: sparse_bad_kernel does this keypoint
+    const int H = a.H, W = a.W;
+    float* out = a.desc + (size_t)kidx * a.P;
+
+    const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
+    if (!(ky >= 0.0f)) {                                                    // bad.py:461, :570 -> the row is all zeros
+        for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
+        return;
+    }
+    const float yc = fminf(fmaxf(ky, 0.0f), (float)(H - 1));               // bad.py:464-465
+    const float xc = fminf(fmaxf(kx, 0.0f), (float)(W - 1));
+    const int iy0 = (int)nearbyintf(yc), ix0 = (int)nearbyintf(xc);
+    const int wx0 = ix0 - HS + a.pad;            // integral column of window column 0 (>= 0)
+    const unsigned int* Wn = sWin + g * GSTRIDE + (wx0 & 3);
+    if (t == 0) {
+        mbar_arrive_expect_tx(smem_u32(&bars[g]), WR * WP * 4);
+        tma_load_3d(smem_u32(sWin + g * GSTRIDE), &tmap, smem_u32(&bars[g]), wx0 & ~3, iy0 - HS + a.pad, z);
+    }
+
+    float ct = 1.0f, st = 0.0f;
+    if (ORIENTED) {
+        // orientation of this keypoint: nearest sample of the orientation map (bad.py:490-499)
+        const int ny = (int)nearbyintf(sample_coord(yc, a.sy, (float)(H - 1) * 0.5f, (float)(H - 1)));
+        const int nx = (int)nearbyintf(sample_coord(xc, a.sx, (float)(W - 1) * 0.5f, (float)(W - 1)));
+        float theta;
+        if (a.theta_mode == OM_THETA_MAP) {
+            theta = __ldg(a.orientation + (size_t)z * H * W + (size_t)ny * W + nx);
+        } else {
+            // angle_estimation.py:161-170 at (ny,nx) only: zero-padded cross-correlation, then atan2
+            const float* img = a.image + (size_t)z * H * W;
+            const int ps = a.patch_size, half = ps / 2;
+            float m10 = 0.0f, m01 = 0.0f;
+            for (int tap = t; tap < ps * ps; tap += TPG) {
+                const int j = tap / ps, i = tap - j * ps;
+                const int gy = ny + j - half, gx = nx + i - half;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    const float v = __ldg(img + (size_t)gy * W + gx);
+                    m10 = fmaf(__ldg(a.moments + tap), v, m10);
+                    m01 = fmaf(__ldg(a.moments + ps * ps + tap), v, m01);
+                }
+            }
+            m10 = group_sum(m10, red, g, t);
+            m01 = group_sum(m01, red, g, t);
+            theta = atan2f(m01, m10);
+            if (t == 0) sTheta[g] = theta;
+            group_bar(g);
+            theta = sTheta[g];
+        }
+        ct = cosf(theta);                                                   // bad.py:501-502
+        st = sinf(theta);
+    }
+    mbar_wait(smem_u32(&bars[g]), 0u);           // window has landed
+
+    constexpr int MAXPP = 8;   // pairs per thread: P <= 512
+    float d[MAXPP];
+    float ss = 0.0f;
+    const bool fast = FAST && ky == (float)iy0 && kx == (float)ix0 && iy0 >= 15 && iy0 + 14 <= H - 1 && ix0 >= 15 &&
+                      ix0 + 14 <= W - 1;
+    if (fast) {
+#pragma unroll
+        for (int q = 0; q < MAXPP; ++q) {
+            const int p = t + q * TPG;
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const uint4 tp = sTap[p];
+                const float2 tb = sThr[p];
+                const unsigned int s1 = (Wn[tp.x & 0xFFFFu] - Wn[tp.x >> 16]) - (Wn[tp.y & 0xFFFFu] - Wn[tp.y >> 16]);
+                const unsigned int s2 = (Wn[tp.z & 0xFFFFu] - Wn[tp.z >> 16]) - (Wn[tp.w & 0xFFFFu] - Wn[tp.w >> 16]);
+                const float diff = __fsub_rn(__fmul_rn((float)s1, tb.y), __fmul_rn((float)s2, tb.y));   // bad.py:557
+                d[q] = finish_value(diff, tb.x, a.mode, a.temperature);
+                ss = fmaf(d[q], d[q], ss);
+            }
+        }
+    } else {
+        const float hy = (float)(H - 1) * 0.5f, hx = (float)(W - 1) * 0.5f;
+        const float my = (float)(H - 1), mx = (float)(W - 1);
+        auto box_mean = [&](int cy, int cx, int r, float inv_area) -> float {
+            // cy,cx: integer sample centre in image coords (already clipped to the image by grid_sample's
+            // border mode); the box may reach into the replicate padding, which the integral contains
+            const int wy = clampi(cy - iy0 + HS, r, S - 1 - r), wx = clampi(cx - ix0 + HS, r, S - 1 - r);
+            const int y0 = wy - r, y1 = wy + r + 1, x0 = wx - r, x1 = wx + r + 1;
+            const unsigned int s = (Wn[y1 * WP + x1] - Wn[y0 * WP + x1]) - (Wn[y1 * WP + x0] - Wn[y0 * WP + x0]);
+            return __fmul_rn((float)s, inv_area);
+        };
+        auto sample = [&](float oy, float ox, int r, float inv_area) -> float {
+            float py, px;
+            if (ORIENTED) {                                                     // bad.py:504-517
+                const float dy = __fadd_rn(__fmul_rn(ox, st), __fmul_rn(oy, ct));
+                const float dx = __fsub_rn(__fmul_rn(ox, ct), __fmul_rn(oy, st));
+                py = __fadd_rn(yc, dy);
+                px = __fadd_rn(xc, dx);
+            } else {                                                            // bad.py:518-525
+                py = __fadd_rn(yc, oy);
+                px = __fadd_rn(xc, ox);
+            }
+            const float uy = sample_coord(py, a.sy, hy, my), ux = sample_coord(px, a.sx, hx, mx);
+            if (!BILINEAR) return box_mean((int)nearbyintf(uy), (int)nearbyintf(ux), r, inv_area);   // half-to-even
+            const float fy = floorf(uy), fx = floorf(ux);
+            const float w = ux - fx, e = 1.0f - w, s = uy - fy, n = 1.0f - s;   // ATen bilinear weights
+            const int y_n = (int)fy, x_w = (int)fx;
+            const int y_s = min(y_n + 1, H - 1), x_e = min(x_w + 1, W - 1);     // weight is 0 where this clamps
+            const float nw = box_mean(y_n, x_w, r, inv_area), ne = box_mean(y_n, x_e, r, inv_area);
+            const float sw = box_mean(y_s, x_w, r, inv_area), se = box_mean(y_s, x_e, r, inv_area);
+            return nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
+        };
+#pragma unroll
+        for (int q = 0; q < MAXPP; ++q) {
+            const int p = t + q * TPG;
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const PairRow row = load_pair(a.table, p);
+                const int r = (int)row.r;
+                const float side = (float)(2 * r + 1);
+                const float inv_area = __fdiv_rn(1.0f, side * side);
+                const float diff = __fsub_rn(sample(row.oy1, row.ox1, r, inv_area), sample(row.oy2, row.ox2, r, inv_area));
+                d[q] = finish_value(diff, row.thr, a.mode, a.temperature);
+                ss = fmaf(d[q], d[q], ss);
+            }
+        }
+    }
+    float inv = 1.0f;
+    if (a.normalize) {                                                      // F.normalize, bad.py:573-574
+        const float nrm = sqrtf(group_sum(ss, red, g, t));
+        inv = 1.0f / fmaxf(nrm, 1e-12f);
+    }
+#pragma unroll
+    for (int q = 0; q < MAXPP; ++q) {
+        const int p = t + q * TPG;
+        if (p < a.P) out[p] = d[q] * inv;
+    }
+}
+
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
+int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t st) {
+    constexpr int S = 2 * HS + 1, WR = S + 1, WP = (S + 1 + 3 + 3) / 4 * 4, GSTRIDE = (WR * WP + 31) / 32 * 32;
+    const int Hi = a.H + 2 * a.pad + 1, IP = ipitch(a.W, a.pad);
+    CUtensorMap tmap;
+    OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, WP, WR));
+    const size_t smem = (size_t)GROUPS * GSTRIDE * 4 + ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2)) : 0);
+    auto kernel = sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR>;
+    OM_TRY(set_smem(kernel, smem));
+    const long long total = (long long)a.B * a.K;
+    kernel<<<(unsigned)((total + GROUPS - 1) / GROUPS), GROUPS * TPG, smem, st>>>(tmap, a);
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -299,49 +593,121 @@ __global__ void __launch_bounds__(256) angle_map_kernel(const float* image, int 
 // ------------------------------------------------------------------------------------------
 // dense BAD: float32 integral image exactly as the reference builds it
 // ------------------------------------------------------------------------------------------
-// pass 1: cumsum along H of the replicate-padded image, double accumulator, rounded to f32 (bad.py:70-71)
-__global__ void __launch_bounds__(128) integral_cols_kernel(const float* image, int H, int W, float* T) {
-    const int Wp = W + 2 * MAXR, Hp = H + 2 * MAXR;
-    const int xx = blockIdx.x * 128 + threadIdx.x;
-    if (xx >= Wp) return;
+// Integral images of the replicate-padded image, two flavours of the same two passes:
+//   EXACT = false (dense path): the reference's float32 integral -- cumsum along H with a double
+//           accumulator rounded to f32 per element, then cumsum along W of THAT (bad.py:70-72).
+//   EXACT = true (sparse path): exact uint32 integral (wrap-around is harmless: box sums are
+//           differences).  Exact only for integer-valued pixels in [0, 65535]; any other pixel raises
+//           flags[image] and that image's keypoints are handled by the fp64 per-keypoint kernel.
+// I is (H+2*pad+1) x ipitch with the zero row / column of bad.py:72; ipitch % 4 == 0 so that a
+// keypoint's window is one TMA box.
+
+// pass 1 (columns).  A column is cut into PC_SEG segments: every thread first sums its segment, the
+// segment totals are combined in order through shared memory, then the thread re-walks its segment
+// (an L1/L2 hit) from that base.  Double sums of <= 2^12 float32 values are exact for integer-valued
+// images and within 1e-13 relative otherwise, i.e. identical after the single rounding.
+constexpr int PC_COLS = 32, PC_SEG = 32;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(PC_COLS * PC_SEG) prefix_cols_kernel(const float* image, int H, int W, int pad, void* Tout,
+                                                                       unsigned int* flags) {
+    using Acc = typename std::conditional<EXACT, unsigned int, double>::type;
+    using Out = typename std::conditional<EXACT, unsigned int, float>::type;
+    __shared__ Acc seg_total[PC_SEG][PC_COLS];
+    const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+    const int cx = threadIdx.x % PC_COLS, sg = threadIdx.x / PC_COLS;
+    const int xx = blockIdx.x * PC_COLS + cx;
     const int z = blockIdx.y;
-    const float* col = image + (size_t)z * H * W + clampi(xx - MAXR, 0, W - 1);
-    float* dst = T + (size_t)z * Hp * Wp + xx;
-    double acc = 0.0;
-    for (int yy = 0; yy < Hp; ++yy) {
-        acc += (double)__ldg(col + (size_t)clampi(yy - MAXR, 0, H - 1) * W);
-        dst[(size_t)yy * Wp] = (float)acc;
+    const int L = (Hp + PC_SEG - 1) / PC_SEG;
+    const int y0 = sg * L, y1 = min(y0 + L, Hp);
+    const bool live = xx < Wp;
+    const float* col = image + (size_t)z * H * W + clampi(xx - pad, 0, W - 1);
+    Acc acc = 0;
+    bool odd = false;
+    if (live) {
+#pragma unroll 4
+        for (int yy = y0; yy < y1; ++yy) {
+            const float v = __ldg(col + (size_t)clampi(yy - pad, 0, H - 1) * W);
+            if (EXACT) {
+                odd |= !(v == rintf(v) && v >= 0.0f && v <= 65535.0f);
+                acc += (Acc)__float2uint_rz(v);
+            } else {
+                acc += (Acc)v;
+            }
+        }
+    }
+    seg_total[sg][cx] = acc;
+    const int any_odd = __syncthreads_or(odd ? 1 : 0);
+    if (EXACT && any_odd && threadIdx.x == 0) atomicOr(&flags[z], 1u);
+    if (!live) return;
+    acc = 0;
+    for (int q = 0; q < sg; ++q) acc += seg_total[q][cx];
+    Out* dst = reinterpret_cast<Out*>(Tout) + (size_t)z * Hp * Wp + xx;
+#pragma unroll 4
+    for (int yy = y0; yy < y1; ++yy) {
+        const float v = __ldg(col + (size_t)clampi(yy - pad, 0, H - 1) * W);
+        acc += EXACT ? (Acc)__float2uint_rz(v) : (Acc)v;
+        dst[(size_t)yy * Wp] = (Out)acc;
     }
 }
 
-// pass 2: cumsum along W of pass 1 (double accumulator, rounded to f32), stored with the zero
-// row/column of bad.py:72 -> I is (H+15) x (W+15)
-__global__ void __launch_bounds__(256) integral_rows_kernel(const float* T, int H, int W, float* I) {
-    const int Wp = W + 2 * MAXR, Hp = H + 2 * MAXR;
+// pass 2 (rows).  One warp per row: the row is staged in shared memory, lane l sums the l-th segment,
+// the 32 segment totals are scanned with shuffles, then every lane re-walks its segment and the row is
+// written back coalesced, shifted by the zero column.
+constexpr int IR_ROWS = 8;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(IR_ROWS * 32) prefix_rows_kernel(const void* Tin, int H, int W, int pad, int SL, void* Iout) {
+    using Acc = typename std::conditional<EXACT, unsigned int, double>::type;
+    using Val = typename std::conditional<EXACT, unsigned int, float>::type;
+    extern __shared__ __align__(16) unsigned char sRowRaw[];
+    Val* sRow = reinterpret_cast<Val*>(sRowRaw);             // IR_ROWS x (32*SL)
+    const int Wp = W + 2 * pad, Hp = H + 2 * pad, IP = ipitch(W, pad);
     const int z = blockIdx.y;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);      // row of I, 0 .. Hp
-    const int lane = threadIdx.x & 31;
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * IR_ROWS + wrp;              // row of I, 0 .. Hp
     if (row > Hp) return;
-    float* dst = I + (size_t)z * (Hp + 1) * (Wp + 1) + (size_t)row * (Wp + 1);
+    Val* dst = reinterpret_cast<Val*>(Iout) + (size_t)z * (Hp + 1) * IP + (size_t)row * IP;
     if (row == 0) {
-        for (int x = lane; x <= Wp; x += 32) dst[x] = 0.0f;
+        for (int x = lane; x < IP; x += 32) dst[x] = 0;
         return;
     }
-    const float* src = T + (size_t)z * Hp * Wp + (size_t)(row - 1) * Wp;
-    if (lane == 0) dst[0] = 0.0f;
-    double carry = 0.0;
-    for (int x0 = 0; x0 < Wp; x0 += 32) {
-        const int x = x0 + lane;
-        double v = x < Wp ? (double)src[x] : 0.0;
+    const Val* src = reinterpret_cast<const Val*>(Tin) + (size_t)z * Hp * Wp + (size_t)(row - 1) * Wp;
+    Val* buf = sRow + (size_t)wrp * 32 * SL;
+    for (int x = lane; x < 32 * SL; x += 32) buf[x] = x < Wp ? __ldg(src + x) : (Val)0;
+    __syncwarp();
+    Val* seg = buf + lane * SL;                              // SL is odd: conflict-free
+    Acc tot = 0;
+    for (int k = 0; k < SL; ++k) tot += (Acc)seg[k];
+    Acc incl = tot;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double n = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += n;
-        }
-        v += carry;
-        if (x < Wp) dst[x + 1] = (float)v;
-        carry = __shfl_sync(0xffffffffu, v, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+        const Acc nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
     }
+    Acc acc = incl - tot;                                    // exclusive base of this segment
+    for (int k = 0; k < SL; ++k) {
+        acc += (Acc)seg[k];
+        seg[k] = (Val)acc;
+    }
+    __syncwarp();
+    if (lane == 0) dst[0] = 0;
+    for (int x = lane; x < Wp; x += 32) dst[x + 1] = buf[x];
+    for (int x = Wp + 1 + lane; x < IP; x += 32) dst[x] = 0;
+}
+
+template <bool EXACT>
+int build_prefix(const float* image, int B, int H, int W, int pad, void* T, void* I, unsigned int* flags, cudaStream_t st) {
+    const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+    prefix_cols_kernel<EXACT><<<dim3((Wp + PC_COLS - 1) / PC_COLS, B), PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags);
+    OM_AFTER_LAUNCH();
+    const int SL = ((Wp + 31) / 32) | 1;
+    const size_t smem = (size_t)IR_ROWS * 32 * SL * 4;
+    if (smem > 200 * 1024) return OM_ERR_LIMIT;              // W <= ~6300
+    OM_TRY(set_smem(prefix_rows_kernel<EXACT>, smem));
+    prefix_rows_kernel<EXACT><<<dim3((Hp + 1 + IR_ROWS - 1) / IR_ROWS, B), IR_ROWS * 32, smem, st>>>(T, H, W, pad, SL, I);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
 }
 
 // box mean of the reference's dense path at padded-integral centre (cy,cx) (already +MAXR):
@@ -360,7 +726,7 @@ __global__ void __launch_bounds__(128) box_planes_kernel(const float* I, int H, 
     const int y = blockIdx.y;
     const int z = blockIdx.z;
     if (x >= W) return;
-    const int pitch = W + 2 * MAXR + 1;
+    const int pitch = ipitch(W, MAXR);
     const float* Iz = I + (size_t)z * (H + 2 * MAXR + 1) * pitch;
     float* pz = planes + (size_t)z * (MAXR + 1) * H * W + (size_t)y * W + x;
 #pragma unroll
@@ -400,25 +766,64 @@ struct DenseKpArgs {
 };
 
 // Dense-path descriptors at the K keypoints only: bilinear blend of the dense map's values at the
-// four neighbouring pixels (bad.py:277-333), mask, L2 normalise (shi_tomasi_bad_sinkhorn.py:143-158, :213-214)
+// four neighbouring pixels (bad.py:277-333), mask, L2 normalise (shi_tomasi_bad_sinkhorn.py:143-158, :213-214).
+// One 64-thread group per keypoint stages the 47x47 window of the float32 integral that covers every
+// tap of the four neighbours.  The bilinear weights are the same for all pairs of a keypoint and are
+// exactly 0 for the neighbours an exact coordinate round trip does not touch (0 * value adds
+// nothing), so those neighbours are skipped.  Interior keypoints (no centre clamps, bad.py:81-82)
+// read their 8 taps per pair at window offsets precomputed once per CTA.
+// 47 rows x 47 columns are needed; the TMA box must start on a 16-byte boundary in global memory, so it starts up
+// to 3 columns early: 48 rows x 52 columns
+constexpr int DK_LO = 15, DK_ROWS = 48, DK_SPAN = 52;
+
 template <int GROUPS>
-__global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(DenseKpArgs a) {
-    constexpr int LO = 15, SPAN = 47;       // integral rows [iy0-15, iy0+31] cover every tap of the 4 neighbours
-    extern __shared__ float sI[];
+__global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __grid_constant__ CUtensorMap tmap, DenseKpArgs a) {
+    constexpr int LO = DK_LO, SPAN = DK_SPAN;   // integral rows [iy0-15, iy0+31] cover every tap of the 4 neighbours
+    constexpr int WIN = GROUPS * DK_ROWS * SPAN;             // 48*52*4 bytes per group: a multiple of 128
+    extern __shared__ __align__(128) float sI[];
     __shared__ float red[GROUPS * 2];
+    __shared__ __align__(8) unsigned long long bars[GROUPS];
+    uint4* sTap = reinterpret_cast<uint4*>(sI + WIN);
+    float2* sThr = reinterpret_cast<float2*>(sTap + a.P);
     const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < GROUPS; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_fence_init();
+    }
+
+    for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+        // window coordinates of the taps of neighbour (0,0): pixel q of the image is integral index q + MAXR,
+        // the window starts at integral index iy0 - LO
+        const PairRow row = load_pair(a.table, p);
+        const int r = (int)row.r;
+        const int cy1 = LO + MAXR + (int)row.oy1, cx1 = LO + MAXR + (int)row.ox1;
+        const int cy2 = LO + MAXR + (int)row.oy2, cx2 = LO + MAXR + (int)row.ox2;
+        auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * SPAN + x); };
+        uint4 tp;   // order of bad.py:98: (y1,x1) - (y0,x1) - (y1,x0) + (y0,x0)
+        tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
+        tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
+        tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
+        tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
+        sTap[p] = tp;
+        const float side = (float)(2 * r + 1);
+        sThr[p] = make_float2(row.thr, side * side);
+    }
+    __syncthreads();
+
     const long long total = (long long)a.B * a.K;
-    long long kidx = (long long)blockIdx.x * GROUPS + g;
-    const bool live = kidx < total;
-    if (!live) kidx = total - 1;
+    const long long kidx = (long long)blockIdx.x * GROUPS + g;
+    if (kidx >= total) return;                  // whole group leaves: later barriers are per group
     const int z = (int)(kidx / a.K);
     const int H = a.H, W = a.W;
-    const int Hi = H + 2 * MAXR + 1, Wi = W + 2 * MAXR + 1;
-    const float* Iz = a.I + (size_t)z * Hi * Wi;
-    float* L = sI + (size_t)g * SPAN * SPAN;
+    float* Lbox = sI + (size_t)g * DK_ROWS * SPAN;
+    float* out = a.desc + (size_t)kidx * a.P;
 
     const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
-    const float valid = ky >= 0.0f ? 1.0f : 0.0f;
+    if (!(ky >= 0.0f)) {                        // shi_tomasi_bad_sinkhorn.py:143,158: masked rows are zero
+        for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
+        return;
+    }
     const float yc = fminf(fmaxf(ky, 0.0f), (float)(H - 1));
     const float xc = fminf(fmaxf(kx, 0.0f), (float)(W - 1));
     // bad.py:311-312: kp / (dim-1+1e-8) * 2 - 1, then ATen unnormalise + clip
@@ -431,55 +836,91 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(DenseKpArgs
     const int iy0 = (int)fy, ix0 = (int)fx;
     const int ys = min(iy0 + 1, H - 1), xe = min(ix0 + 1, W - 1);
     const int oy = iy0 - LO, ox = ix0 - LO;     // integral coords of L(0,0)
+    const float wgt[4] = {n * e, n * w, s * e, s * w};                  // nw, ne, sw, se
 
-    static_assert(SPAN <= TPG, "one thread per window column");
-    if (t < SPAN) {
-        const float* src = Iz + clampi(ox + t, 0, Wi - 1);
-#pragma unroll 8
-        for (int dy = 0; dy < SPAN; ++dy) L[dy * SPAN + t] = __ldg(src + (size_t)clampi(oy + dy, 0, Hi - 1) * Wi);
+    // one TMA box: rows/columns outside the integral read as zero and are never used as taps
+    const float* L = Lbox + (ox & 3);           // window column 0 inside the 16-byte aligned box
+    if (t == 0) {
+        mbar_arrive_expect_tx(smem_u32(&bars[g]), DK_ROWS * SPAN * 4);
+        tma_load_3d(smem_u32(Lbox), &tmap, smem_u32(&bars[g]), ox & ~3, oy, z);
     }
-    __syncthreads();
-
-    auto value_at = [&](int py, int px, const PairRow& row, int r) -> float {
-        const int c1y = clampi(py + (int)row.oy1, 0, H - 1) + MAXR - oy, c1x = clampi(px + (int)row.ox1, 0, W - 1) + MAXR - ox;
-        const int c2y = clampi(py + (int)row.oy2, 0, H - 1) + MAXR - oy, c2x = clampi(px + (int)row.ox2, 0, W - 1) + MAXR - ox;
-        const float diff = __fsub_rn(dense_box_mean(L, SPAN, c1y, c1x, r), dense_box_mean(L, SPAN, c2y, c2x, r));
-        return finish_value(diff, row.thr, a.mode, a.temperature);
-    };
+    mbar_wait(smem_u32(&bars[g]), 0u);
 
     constexpr int MAXPP = 8;
     float d[MAXPP];
     float ss = 0.0f;
-#pragma unroll
-    for (int q = 0; q < MAXPP; ++q) {
-        const int p = t + q * TPG;
-        d[q] = 0.0f;
-        if (p < a.P) {
-            const PairRow row = load_pair(a.table, p);
-            const int r = (int)row.r;
-            const float nw = value_at(iy0, ix0, row, r), ne = value_at(iy0, xe, row, r);
-            const float sw = value_at(ys, ix0, row, r), se = value_at(ys, xe, row, r);
-            const float v = nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
-            d[q] = __fmul_rn(v, valid);
-            ss = fmaf(d[q], d[q], ss);
-        }
-    }
-    float inv = 1.0f;
-    if (a.normalize) {
-        float v = warp_sum(ss);
-        __syncthreads();
-        if ((t & 31) == 0) red[g * 2 + (t >> 5)] = v;
-        __syncthreads();
-        inv = 1.0f / fmaxf(sqrtf(red[g * 2] + red[g * 2 + 1]), 1e-12f);
-    }
-    if (live) {
-        float* out = a.desc + (size_t)kidx * a.P;
+    // no centre clamp for any of the four neighbours <=> their offsets in [-15,14] stay inside the image
+    const bool interior = iy0 >= 15 && iy0 + 1 + 14 <= H - 1 && ix0 >= 15 && ix0 + 1 + 14 <= W - 1;
+    if (interior) {
 #pragma unroll
         for (int q = 0; q < MAXPP; ++q) {
             const int p = t + q * TPG;
-            if (p < a.P) out[p] = a.normalize ? d[q] * inv : d[q];
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const uint4 tp = sTap[p];
+                const float2 tb = sThr[p];
+                float v = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (wgt[k] != 0.0f) {                                   // group-uniform
+                        const float* Lk = L + (k >> 1) * SPAN + (k & 1);
+                        const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(Lk[tp.x & 0xFFFFu], Lk[tp.x >> 16]), Lk[tp.y & 0xFFFFu]),
+                                                   Lk[tp.y >> 16]);
+                        const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(Lk[tp.z & 0xFFFFu], Lk[tp.z >> 16]), Lk[tp.w & 0xFFFFu]),
+                                                   Lk[tp.w >> 16]);
+                        const float diff = __fsub_rn(__fdiv_rn(s1, tb.y), __fdiv_rn(s2, tb.y));
+                        v += finish_value(diff, tb.x, a.mode, a.temperature) * wgt[k];
+                    }
+                }
+                d[q] = v;
+                ss = fmaf(v, v, ss);
+            }
+        }
+    } else {
+        const int py[4] = {iy0, iy0, ys, ys}, px[4] = {ix0, xe, ix0, xe};
+        auto value_at = [&](int qy, int qx, const PairRow& row, int r) -> float {
+            const int c1y = clampi(qy + (int)row.oy1, 0, H - 1) + MAXR - oy, c1x = clampi(qx + (int)row.ox1, 0, W - 1) + MAXR - ox;
+            const int c2y = clampi(qy + (int)row.oy2, 0, H - 1) + MAXR - oy, c2x = clampi(qx + (int)row.ox2, 0, W - 1) + MAXR - ox;
+            const float diff = __fsub_rn(dense_box_mean(L, SPAN, c1y, c1x, r), dense_box_mean(L, SPAN, c2y, c2x, r));
+            return finish_value(diff, row.thr, a.mode, a.temperature);
+        };
+#pragma unroll
+        for (int q = 0; q < MAXPP; ++q) {
+            const int p = t + q * TPG;
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const PairRow row = load_pair(a.table, p);
+                const int r = (int)row.r;
+                float v = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (wgt[k] != 0.0f) v += value_at(py[k], px[k], row, r) * wgt[k];
+                d[q] = v;
+                ss = fmaf(v, v, ss);
+            }
         }
     }
+    float inv = 1.0f;
+    if (a.normalize) inv = 1.0f / fmaxf(sqrtf(group_sum(ss, red, g, t)), 1e-12f);
+#pragma unroll
+    for (int q = 0; q < MAXPP; ++q) {
+        const int p = t + q * TPG;
+        if (p < a.P) out[p] = d[q] * inv;
+    }
+}
+
+template <int GROUPS>
+int launch_dense_kp(const DenseKpArgs& a, cudaStream_t st) {
+    CUtensorMap tmap;
+    const int IP = ipitch(a.W, MAXR);
+    OM_TRY(make_tmap_3d(&tmap, true, a.I, (uint64_t)IP, (uint64_t)(a.H + 2 * MAXR + 1), (uint64_t)a.B, (uint64_t)IP, DK_SPAN,
+                        DK_ROWS));
+    const size_t smem = (size_t)GROUPS * DK_ROWS * DK_SPAN * sizeof(float) + (size_t)a.P * (sizeof(uint4) + sizeof(float2));
+    OM_TRY(set_smem(dense_at_kpts_kernel<GROUPS>, smem));
+    const long long total = (long long)a.B * a.K;
+    dense_at_kpts_kernel<GROUPS><<<(unsigned)((total + GROUPS - 1) / GROUPS), GROUPS * TPG, smem, st>>>(tmap, a);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const float* map, int B, int D, int H, int W, const float* kpts,
@@ -509,7 +950,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* map, int B, in
 
 struct DenseWs {
     float* T;       // (B, H+14, W+14)
-    float* I;       // (B, H+15, W+15)
+    float* I;       // (B, H+15, ipitch)
     float* planes;  // (B, 8, H, W)   (dense map only)
 };
 
@@ -519,8 +960,28 @@ DenseWs carve_dense(void* ws, int B, int H, int W) {
     d.T = (float*)p;
     p += align_up((size_t)B * (H + 2 * MAXR) * (W + 2 * MAXR) * sizeof(float));
     d.I = (float*)p;
-    p += align_up((size_t)B * (H + 2 * MAXR + 1) * (W + 2 * MAXR + 1) * sizeof(float));
+    p += align_up((size_t)B * (H + 2 * MAXR + 1) * ipitch(W, MAXR) * sizeof(float));
     d.planes = (float*)p;
+    return d;
+}
+
+struct SparseWs {
+    unsigned int* flags;   // (B) non-integer-pixel flags
+    unsigned int* T;       // (B, H+2pad, W+2pad)
+    unsigned int* I;       // (B, H+2pad+1, ipitch)
+};
+
+// window half size / integral padding per mode (see sparse_win_kernel)
+constexpr int HS_PLAIN = 23, PAD_PLAIN = 23, HS_ORI = 30, PAD_ORI = 32;
+
+SparseWs carve_sparse(void* ws, int B, int H, int W, int pad) {
+    SparseWs d;
+    char* p = (char*)ws;
+    d.flags = (unsigned int*)p;
+    p += align_up((size_t)B * sizeof(unsigned int));
+    d.T = (unsigned int*)p;
+    p += align_up((size_t)B * (H + 2 * pad) * (W + 2 * pad) * sizeof(unsigned int));
+    d.I = (unsigned int*)p;
     return d;
 }
 
@@ -531,20 +992,23 @@ int check_table(const float* table, int P) {
 }
 
 int build_integral(const float* image, int B, int H, int W, const DenseWs& d, cudaStream_t st) {
-    const int Wp = W + 2 * MAXR, Hp = H + 2 * MAXR;
-    integral_cols_kernel<<<dim3((Wp + 127) / 128, B), 128, 0, st>>>(image, H, W, d.T);
-    OM_AFTER_LAUNCH();
-    integral_rows_kernel<<<dim3((Hp + 1 + 7) / 8, B), 256, 0, st>>>(d.T, H, W, d.I);
-    OM_AFTER_LAUNCH();
-    return OM_OK;
+    return build_prefix<false>(image, B, H, W, MAXR, d.T, d.I, nullptr, st);
 }
 
 }  // namespace
 
+size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const int pad = theta_mode == OM_THETA_NONE ? PAD_PLAIN : PAD_ORI;
+    return align_up((size_t)B * sizeof(unsigned int)) +
+           align_up((size_t)B * (H + 2 * pad) * (W + 2 * pad) * sizeof(unsigned int)) +
+           align_up((size_t)B * (H + 2 * pad + 1) * ipitch(W, pad) * sizeof(unsigned int));
+}
+
 int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
                       const float* orientation, const float* moment_kernels, int patch_size, float* desc,
-                      cudaStream_t st) {
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
     if (image == nullptr || kpts == nullptr || desc == nullptr) return OM_ERR_NULL;
     if (B <= 0 || H <= 1 || W <= 1 || K <= 0) return OM_ERR_SHAPE;
     OM_TRY(check_table(pair_table, P));
@@ -556,6 +1020,12 @@ int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts
         if (moment_kernels == nullptr) return OM_ERR_NULL;
         if (patch_size < 1 || patch_size % 2 == 0 || patch_size > 31) return OM_ERR_PARAM;
     }
+    if (ws == nullptr || ws_bytes < sparse_bad_workspace_bytes(B, H, W, theta_mode)) return OM_ERR_WORKSPACE;
+    const bool oriented = theta_mode != OM_THETA_NONE;
+    const int pad = oriented ? PAD_ORI : PAD_PLAIN;
+    const SparseWs w = carve_sparse(ws, B, H, W, pad);
+    OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)B * sizeof(unsigned int), st));
+    OM_TRY(build_prefix<true>(image, B, H, W, pad, w.T, w.I, w.flags, st));
     SparseArgs a{};
     a.image = image; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P;
     a.mode = desc_mode; a.temperature = temperature; a.normalize = normalize;
@@ -563,14 +1033,21 @@ int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts
     a.moments = moment_kernels; a.patch_size = patch_size; a.desc = desc;
     a.sy = (float)(2.0 / ((double)(H - 1) + 1e-8));
     a.sx = (float)(2.0 / ((double)(W - 1) + 1e-8));
-    if (theta_mode == OM_THETA_NONE) return launch_sparse<24, 4>(a, st);
-    return launch_sparse<30, 3>(a, st);
+    a.flags = w.flags; a.pad = pad;
+    const bool bil = a.bilinear != 0;
+    // integer-valued images: window kernel on the exact integral; every other image: the general kernel
+    if (!oriented) {
+        OM_TRY((bil ? launch_sparse_win<HS_PLAIN, 4, false, true>(a, w.I, st) : launch_sparse_win<HS_PLAIN, 4, false, false>(a, w.I, st)));
+        return bil ? launch_sparse<HS_PLAIN, 4, false, true>(a, st) : launch_sparse<HS_PLAIN, 4, false, false>(a, st);
+    }
+    OM_TRY((bil ? launch_sparse_win<HS_ORI, 4, true, true>(a, w.I, st) : launch_sparse_win<HS_ORI, 4, true, false>(a, w.I, st)));
+    return bil ? launch_sparse<HS_ORI, 3, true, true>(a, st) : launch_sparse<HS_ORI, 3, true, false>(a, st);
 }
 
 size_t dense_bad_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     return align_up((size_t)B * (H + 2 * MAXR) * (W + 2 * MAXR) * sizeof(float)) +
-           align_up((size_t)B * (H + 2 * MAXR + 1) * (W + 2 * MAXR + 1) * sizeof(float)) +
+           align_up((size_t)B * (H + 2 * MAXR + 1) * ipitch(W, MAXR) * sizeof(float)) +
            align_up((size_t)B * (MAXR + 1) * H * W * sizeof(float));
 }
 
@@ -587,12 +1064,7 @@ int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const floa
     DenseKpArgs a{};
     a.I = d.I; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P; a.mode = desc_mode;
     a.temperature = temperature; a.normalize = normalize; a.desc = desc;
-    constexpr int GROUPS = 4;
-    constexpr size_t smem = (size_t)GROUPS * 47 * 47 * sizeof(float);
-    const long long total = (long long)B * K;
-    dense_at_kpts_kernel<GROUPS><<<(unsigned)((total + GROUPS - 1) / GROUPS), GROUPS * TPG, smem, st>>>(a);
-    OM_AFTER_LAUNCH();
-    return OM_OK;
+    return launch_dense_kp<4>(a, st);
 }
 
 }  // namespace om
@@ -616,9 +1088,15 @@ extern "C" int om_angle_map_f32(const float* image, int B, int H, int W, const f
 extern "C" int om_sparse_bad_f32(const float* image, int B, int H, int W, const float* kpts, int K,
                                  const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                                  int sampling_mode, int theta_mode, const float* orientation,
-                                 const float* moment_kernels, int patch_size, float* desc, void* stream) {
+                                 const float* moment_kernels, int patch_size, float* desc, void* ws, size_t ws_bytes,
+                                 void* stream) {
     return sparse_bad_launch(image, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, sampling_mode,
-                             theta_mode, orientation, moment_kernels, patch_size, desc, (cudaStream_t)stream);
+                             theta_mode, orientation, moment_kernels, patch_size, desc, ws, ws_bytes,
+                             (cudaStream_t)stream);
+}
+
+extern "C" size_t om_sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode) {
+    return sparse_bad_workspace_bytes(B, H, W, theta_mode);
 }
 
 extern "C" size_t om_dense_bad_workspace_bytes(int B, int H, int W) { return dense_bad_workspace_bytes(B, H, W); }
@@ -673,10 +1151,5 @@ extern "C" int om_debug_dense_stage(const float* image, int B, int H, int W, con
     DenseKpArgs a{};
     a.I = d.I; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P; a.mode = desc_mode;
     a.temperature = temperature; a.normalize = normalize; a.desc = desc;
-    constexpr int GROUPS = 4;
-    const long long total = (long long)B * K;
-    dense_at_kpts_kernel<GROUPS><<<(unsigned)((total + GROUPS - 1) / GROUPS), GROUPS * TPG,
-                                   (size_t)GROUPS * 47 * 47 * sizeof(float), st>>>(a);
-    OM_AFTER_LAUNCH();
-    return OM_OK;
+    return launch_dense_kp<4>(a, st);
 }

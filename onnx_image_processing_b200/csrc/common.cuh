@@ -1,5 +1,6 @@
 // Shared host/device helpers for libom_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,6 +56,41 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- mbarrier / TMA (cp.async.bulk.tensor) primitives ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA tile load global -> shared of one box of a rank-3 tensor map; completes `bytes of the box` on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// Host: rank-3 tiled tensor map over a dense (d2, d1, d0) array of 4-byte elements whose rows are
+// `pitch_elems` apart (pitch_elems % 4 == 0, base 16-byte aligned); box = (1, box1, box0), no swizzle,
+// out-of-bounds elements read as zero.  Defined in api.cu (driver entry point resolved at run time).
+int make_tmap_3d(CUtensorMap* map, bool is_float, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t pitch_elems, uint32_t box0, uint32_t box1);
+
 // ---- internal stage launchers shared between the per-stage C ABI and the fused matcher -------
 struct DetectCfg {
     int B, H, W;
@@ -67,10 +103,11 @@ size_t topk_workspace_bytes(int B, int H, int W, int K);
 int detect_launch(const float* image, const DetectCfg& c, float* score_map, float* kpts, float* kpt_scores,
                   void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode);
 int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
                       const float* orientation, const float* moment_kernels, int patch_size, float* desc,
-                      cudaStream_t st);
+                      void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t dense_bad_workspace_bytes(int B, int H, int W);
 int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const float* kpts, int K,

@@ -121,6 +121,22 @@ def test_sparse_bad_matches_oracle(kw):
     assert float(got[1, -5:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(sampling_mode="bilinear")])
+def test_sparse_bad_float_valued_and_mixed_batch(kw):
+    """Image 0 is float-valued (general fp64 kernel), image 1 integer-valued (exact uint32 window kernel):
+    both halves of the batch must match the oracle, i.e. the per-image flag routes every keypoint once."""
+    img, _ = O.texture_images(2, 120, 160, seed=22)
+    img = img.clone()
+    img[0] = img[0] * 0.731 + 0.123                 # non-integer pixels
+    k, _ = O.detect(img.round(), 150, 3, 3, 0.0, 0)
+    k[0, -3:] = -1.0
+    ref = O.sparse_bad(img, k, None, **kw)
+    got = om.SparseBAD(**kw).to(DEV)(img.to(DEV), k.to(DEV))
+    m = PR.desc_metrics(got, ref)
+    assert m["rows_within"] == 1.0, m
+    assert float(got[0, -3:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("sampling_mode", ["nearest", "bilinear"])
 def test_oriented_sparse_bad(sampling_mode):
     """theta taken from a map (module API) and from the in-kernel moments must both match the
