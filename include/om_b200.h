@@ -195,7 +195,8 @@ void om_debug_force_generic_stencil(int on);
 /* Route om_sinkhorn_f32 / the fused matcher through the generic global-memory Sinkhorn kernels
  * instead of the cluster kernel. */
 void om_debug_force_generic_sinkhorn(int on);
-/* 0: tcgen05/TMEM cluster kernel (default), 1: FP32-FFMA cluster kernel, 2: generic kernels. */
+/* 0: tcgen05/TMEM cluster kernel (default; scaling-form loop when exp(-unused/eps) is safe),
+ * 1: FP32-FFMA cluster kernel, 2: generic kernels, 3: tcgen05 kernel with the log-domain loop forced. */
 void om_debug_sinkhorn_variant(int variant);
 /* Device buffer of (B*8 CTAs) x 12 int64: the tcgen05 kernel stores clock64 stamps of its phases there
  * (NULL switches tracing off).  Used by tools/sinkhorn_trace.py only. */

@@ -81,7 +81,7 @@ struct SparseArgs {
     int patch_size;
     float* desc;
     float sy, sx;              // float32(2/(dim-1+1e-8)), bad.py:469-470
-    const unsigned int* flags; // per image: 1 = has a pixel that is not an integer in [0,65535]
+    const unsigned int* flags; // per image: 1 = has a pixel that is not an integer in [0,65535]; [B] = any image
     int pad;                   // replicate padding baked into the uint32 integral (window kernel)
 };
 
@@ -100,6 +100,14 @@ struct SparseArgs {
 //      float(1/area) (bad.py:426-434), so this is its arithmetic with an exact accumulator.
 // HS: patch half size.  Nearest / bilinear sample centres are at most 16 px from the rounded
 // keypoint (15 offset + two roundings), + radius 7 -> HS = 23; rotated offsets reach 22 + 7 -> 30.
+// correctly rounded s / area given y = float(1/area) (Markstein: one residual correction of the product; checked
+// against exact rational arithmetic for every box area) -- replaces the ~15-instruction branchy IEEE division
+__device__ __forceinline__ float div_area(float s, float area, float y) {
+    const float q0 = __fmul_rn(s, y);
+    const float r = __fmaf_rn(-area, q0, s);
+    return __fmaf_rn(r, y, q0);
+}
+
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TPG) : "memory"); }
 
 // sum of `v` over the TPG threads of one keypoint group; red is per-CTA scratch [groups][2]
@@ -111,45 +119,17 @@ __device__ __forceinline__ float group_sum(float v, float* red, int g, int t) {
     return red[g * 2] + red[g * 2 + 1];
 }
 
-template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
-__global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) {
+// one keypoint, one 64-thread group (see sparse_bad_kernel below)
+template <int HS, bool ORIENTED, bool BILINEAR>
+__device__ __forceinline__ void sparse_bad_group(const SparseArgs& a, long long kidx, double* D, float* red, float* sTheta,
+                                                 const uint4* sTap, const float2* sThr, int g, int t) {
     constexpr int S = 2 * HS + 1;       // patch side
     constexpr int PD = (S + 1) | 1;     // odd pitch (in doubles) of the (S+1)x(S+1) integral
     constexpr bool FAST = !ORIENTED && !BILINEAR;
-    extern __shared__ __align__(16) double sD[];
-    __shared__ float red[GROUPS * 2];
-    __shared__ float sTheta[GROUPS];
-    // fast-path tables, one entry per pair: 8 integral offsets (uint16) and {threshold, 1/area}
-    uint4* sTap = reinterpret_cast<uint4*>(sD + (size_t)GROUPS * (S + 1) * PD);
-    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));
-
-    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
-    if (FAST) {
-        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
-            const PairRow row = load_pair(a.table, p);
-            const int r = (int)row.r;
-            const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
-            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * PD + x); };
-            uint4 tp;
-            tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
-            tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
-            tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
-            tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
-            sTap[p] = tp;
-            const float side = (float)(2 * r + 1);
-            sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
-        }
-        __syncthreads();
-    }
-
-    const long long total = (long long)a.B * a.K;
-    const long long kidx = (long long)blockIdx.x * GROUPS + g;
-    if (kidx >= total) return;          // whole group leaves: later barriers are per group
     const int z = (int)(kidx / a.K);
     if (a.flags != nullptr && a.flags[z] == 0u) return;   // integer-valued image: sparse_win_kernel did this keypoint
     const int H = a.H, W = a.W;
     const float* img = a.image + (size_t)z * H * W;
-    double* D = sD + (size_t)g * (S + 1) * PD;
     float* out = a.desc + (size_t)kidx * a.P;
 
     const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
@@ -328,6 +308,49 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) 
 }
 
 template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
+__global__ void __launch_bounds__(GROUPS * TPG) sparse_bad_kernel(SparseArgs a) {
+    if (a.flags != nullptr && a.flags[a.B] == 0u) return;   // whole batch integer-valued: nothing to do here
+    constexpr int S = 2 * HS + 1;       // patch side
+    constexpr int PD = (S + 1) | 1;     // odd pitch (in doubles) of the (S+1)x(S+1) integral
+    constexpr bool FAST = !ORIENTED && !BILINEAR;
+    extern __shared__ __align__(16) double sD[];
+    __shared__ float red[GROUPS * 2];
+    __shared__ float sTheta[GROUPS];
+    // fast-path tables, one entry per pair: 8 integral offsets (uint16) and {threshold, 1/area}
+    uint4* sTap = reinterpret_cast<uint4*>(sD + (size_t)GROUPS * (S + 1) * PD);
+    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));
+
+    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    if (FAST) {
+        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+            const PairRow row = load_pair(a.table, p);
+            const int r = (int)row.r;
+            const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
+            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * PD + x); };
+            uint4 tp;
+            tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
+            tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
+            tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
+            tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
+            sTap[p] = tp;
+            const float side = (float)(2 * r + 1);
+            sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
+        }
+        __syncthreads();
+    }
+
+    // persistent loop: the grid is small, so an all-integer batch (nothing to do here) costs ~1 us
+    const long long total = (long long)a.B * a.K;
+    const long long nblk = (total + GROUPS - 1) / GROUPS;
+    double* D = sD + (size_t)g * (S + 1) * PD;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long kidx = blk * GROUPS + g;
+        if (kidx < total) sparse_bad_group<HS, ORIENTED, BILINEAR>(a, kidx, D, red, sTheta, sTap, sThr, g, t);
+        group_bar(g);                   // the group's shared memory is reused by its next keypoint
+    }
+}
+
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
 int launch_sparse(const SparseArgs& a, cudaStream_t st) {
     constexpr int S = 2 * HS + 1;
     constexpr int PD = (S + 1) | 1;
@@ -336,7 +359,8 @@ int launch_sparse(const SparseArgs& a, cudaStream_t st) {
     auto kernel = sparse_bad_kernel<HS, GROUPS, ORIENTED, BILINEAR>;
     OM_TRY(set_smem(kernel, smem));
     const long long total = (long long)a.B * a.K;
-    const unsigned grid = (unsigned)((total + GROUPS - 1) / GROUPS);
+    const long long nblk = (total + GROUPS - 1) / GROUPS;
+    const unsigned grid = (unsigned)(nblk < 148 * 2 ? nblk : 148 * 2);
     kernel<<<grid, GROUPS * TPG, smem, st>>>(a);
     OM_AFTER_LAUNCH();
     return OM_OK;
@@ -358,68 +382,39 @@ int launch_sparse(const SparseArgs& a, cudaStream_t st) {
 // Window geometry: nearest / bilinear sample centres are at most 16 px from the rounded keypoint (15
 // offset + two roundings), + radius 7 -> HS = 23, window 48x48; rotated offsets reach 22 + 7 -> HS = 30,
 // window 62 rows x 64 columns (box width must be a multiple of 16 bytes).
-template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
-__global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_constant__ CUtensorMap tmap, SparseArgs a) {
-    constexpr int S = 2 * HS + 1;
-    constexpr int WR = S + 1;                    // window rows
-    constexpr int WP = (S + 1 + 3 + 3) / 4 * 4;  // TMA box width == shared-memory pitch: the box must start on a 16-byte
-                                                 // boundary in global memory, so it starts up to 3 columns early
-    constexpr int GSTRIDE = (WR * WP + 31) / 32 * 32;   // words per group, keeps every window 128-byte aligned
+// geometry shared by the kernel and its launcher
+template <int HS>
+struct WinGeom {
+    static constexpr int S = 2 * HS + 1;
+    static constexpr int WR = S + 1;                    // window rows
+    static constexpr int WP = (S + 1 + 3 + 3) / 4 * 4;  // TMA box width == shared-memory pitch: the box must start on a
+                                                        // 16-byte boundary in global memory, so up to 3 columns early
+    static constexpr int GSTRIDE = (WR * WP + 31) / 32 * 32;   // words per window buffer (128-byte aligned)
+};
+
+// keypoint -> does it need a window here?  (valid, and its image is integer-valued)
+__device__ __forceinline__ bool win_needed(const SparseArgs& a, long long kidx, float& ky, float& kx, int& z) {
+    z = (int)(kidx / a.K);
+    ky = a.kpts[kidx * 2 + 0];
+    kx = a.kpts[kidx * 2 + 1];
+    return ky >= 0.0f && a.flags[z] == 0u;
+}
+
+// one keypoint whose window `win` is in flight / has landed on mbarrier `bar` (phase `parity`)
+template <int HS, bool ORIENTED, bool BILINEAR>
+__device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long kidx, int z, float ky, float kx,
+                                                 const unsigned int* win, uint32_t bar, uint32_t parity, float* red,
+                                                 float* sTheta, const uint4* sTap, const float2* sThr, int g, int t) {
+    using G = WinGeom<HS>;
+    constexpr int S = G::S, WP = G::WP;
     constexpr bool FAST = !ORIENTED && !BILINEAR;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ float red[GROUPS * 2];
-    __shared__ float sTheta[GROUPS];
-    __shared__ __align__(8) unsigned long long bars[GROUPS];
-    unsigned int* sWin = reinterpret_cast<unsigned int*>(smem_raw);             // GROUPS x WR x WP
-    uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * GSTRIDE);            // fast path: 8 window offsets per pair
-    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));          //            {threshold, 1/area}
-
-    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < GROUPS; ++i) mbar_init(smem_u32(&bars[i]), 1);
-        mbar_fence_init();
-    }
-    if (FAST) {
-        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
-            const PairRow row = load_pair(a.table, p);
-            const int r = (int)row.r;
-            const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
-            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * WP + x); };
-            uint4 tp;
-            tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
-            tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
-            tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
-            tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
-            sTap[p] = tp;
-            const float side = (float)(2 * r + 1);
-            sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
-        }
-    }
-    __syncthreads();                             // barriers initialised, tables built
-
-    const long long total = (long long)a.B * a.K;
-    const long long kidx = (long long)blockIdx.x * GROUPS + g;
-    if (kidx >= total) return;                   // whole group leaves: later barriers are per group
-    const int z = (int)(kidx / a.K);
-    if (a.flags[z] != 0u) return;                // non-integer image: sparse_bad_kernel does this keypoint
     const int H = a.H, W = a.W;
     float* out = a.desc + (size_t)kidx * a.P;
-
-    const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
-    if (!(ky >= 0.0f)) {                                                    // bad.py:461, :570 -> the row is all zeros
-        for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
-        return;
-    }
     const float yc = fminf(fmaxf(ky, 0.0f), (float)(H - 1));               // bad.py:464-465
     const float xc = fminf(fmaxf(kx, 0.0f), (float)(W - 1));
     const int iy0 = (int)nearbyintf(yc), ix0 = (int)nearbyintf(xc);
     const int wx0 = ix0 - HS + a.pad;            // integral column of window column 0 (>= 0)
-    const unsigned int* Wn = sWin + g * GSTRIDE + (wx0 & 3);
-    if (t == 0) {
-        mbar_arrive_expect_tx(smem_u32(&bars[g]), WR * WP * 4);
-        tma_load_3d(smem_u32(sWin + g * GSTRIDE), &tmap, smem_u32(&bars[g]), wx0 & ~3, iy0 - HS + a.pad, z);
-    }
+    const unsigned int* Wn = win + (wx0 & 3);    // the box starts on a 16-byte boundary, up to 3 columns early
 
     float ct = 1.0f, st = 0.0f;
     if (ORIENTED) {
@@ -453,23 +448,25 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_c
         ct = cosf(theta);                                                   // bad.py:501-502
         st = sinf(theta);
     }
-    mbar_wait(smem_u32(&bars[g]), 0u);           // window has landed
+    mbar_wait(bar, parity);                      // window has landed
 
     constexpr int MAXPP = 8;   // pairs per thread: P <= 512
     float d[MAXPP];
     float ss = 0.0f;
     const bool fast = FAST && ky == (float)iy0 && kx == (float)ix0 && iy0 >= 15 && iy0 + 14 <= H - 1 && ix0 >= 15 &&
                       ix0 + 14 <= W - 1;
+    const char* wbytes = reinterpret_cast<const char*>(Wn);
+    auto ldw = [&](unsigned int byte_off) -> unsigned int { return *reinterpret_cast<const unsigned int*>(wbytes + byte_off); };
     if (fast) {
 #pragma unroll
         for (int q = 0; q < MAXPP; ++q) {
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                const uint4 tp = sTap[p];
+                const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
                 const float2 tb = sThr[p];
-                const unsigned int s1 = (Wn[tp.x & 0xFFFFu] - Wn[tp.x >> 16]) - (Wn[tp.y & 0xFFFFu] - Wn[tp.y >> 16]);
-                const unsigned int s2 = (Wn[tp.z & 0xFFFFu] - Wn[tp.z >> 16]) - (Wn[tp.w & 0xFFFFu] - Wn[tp.w >> 16]);
+                const unsigned int s1 = (ldw(ta.x) - ldw(ta.y)) - (ldw(ta.z) - ldw(ta.w));
+                const unsigned int s2 = (ldw(tc.x) - ldw(tc.y)) - (ldw(tc.z) - ldw(tc.w));
                 const float diff = __fsub_rn(__fmul_rn((float)s1, tb.y), __fmul_rn((float)s2, tb.y));   // bad.py:557
                 d[q] = finish_value(diff, tb.x, a.mode, a.temperature);
                 ss = fmaf(d[q], d[q], ss);
@@ -534,17 +531,96 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_c
     }
 }
 
+// GROUPS keypoint groups per CTA; every group walks its keypoints (grid-stride).  NBUF = 2: two-deep window
+// pipeline, the TMA box of keypoint n+1 is in flight while keypoint n is evaluated; NBUF = 1: one window per group
+// and twice the resident groups instead (measured faster on B200: the kernel is bound by shared-memory wavefronts
+// of the random taps, not by the TMA latency, so more warps beat prefetching).
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR, int NBUF>
+__global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_constant__ CUtensorMap tmap, SparseArgs a) {
+    using G = WinGeom<HS>;
+    constexpr bool FAST = !ORIENTED && !BILINEAR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ float red[GROUPS * 2];
+    __shared__ float sTheta[GROUPS];
+    __shared__ __align__(8) unsigned long long bars[GROUPS * 2];
+    unsigned int* sWin = reinterpret_cast<unsigned int*>(smem_raw);             // GROUPS x NBUF x GSTRIDE
+    uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * NBUF * G::GSTRIDE);  // fast path: 2 x 4 window byte offsets per pair
+    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? 2 * a.P : 0));      //            {threshold, 1/area}
+
+    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < GROUPS * 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_fence_init();
+    }
+    if (FAST) {
+        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+            const PairRow row = load_pair(a.table, p);
+            const int r = (int)row.r;
+            const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
+            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * G::WP + x) * 4u; };
+            sTap[2 * p] = make_uint4(off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r),
+                                     off(cy1 - r, cx1 - r));
+            sTap[2 * p + 1] = make_uint4(off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r),
+                                         off(cy2 - r, cx2 - r));
+            const float side = (float)(2 * r + 1);
+            sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
+        }
+    }
+    __syncthreads();                             // barriers initialised, tables built
+
+    const long long total = (long long)a.B * a.K;
+    const long long stride = (long long)gridDim.x * GROUPS;
+    unsigned int* wbuf = sWin + g * NBUF * G::GSTRIDE;
+    const uint32_t bar0 = smem_u32(&bars[2 * g]);
+    // thread 0 of the group launches the window load of keypoint k into buffer `buf`
+    auto issue = [&](long long k, int buf) {
+        float ky, kx;
+        int z;
+        if (t == 0 && win_needed(a, k, ky, kx, z)) {
+            const int iy0 = (int)nearbyintf(fminf(ky, (float)(a.H - 1))), ix0 = (int)nearbyintf(fminf(fmaxf(kx, 0.0f), (float)(a.W - 1)));
+            const uint32_t bar = bar0 + 8u * buf;
+            mbar_arrive_expect_tx(bar, G::WR * G::WP * 4);
+            tma_load_3d(smem_u32(wbuf + buf * G::GSTRIDE), &tmap, bar, (ix0 - HS + a.pad) & ~3, iy0 - HS + a.pad, z);
+        }
+    };
+    long long kidx = (long long)blockIdx.x * GROUPS + g;
+    if (kidx < total) issue(kidx, 0);
+    uint32_t phase[2] = {0u, 0u};
+    for (int n = 0; kidx < total; kidx += stride, ++n) {
+        const int buf = NBUF == 2 ? (n & 1) : 0;
+        if (NBUF == 2 && kidx + stride < total) issue(kidx + stride, buf ^ 1);   // that buffer was released by the barrier below
+        float ky, kx;
+        int z;
+        if (win_needed(a, kidx, ky, kx, z)) {
+            sparse_win_group<HS, ORIENTED, BILINEAR>(a, kidx, z, ky, kx, wbuf + buf * G::GSTRIDE, bar0 + 8u * buf, phase[buf],
+                                                     red, sTheta, sTap, sThr, g, t);
+            phase[buf] ^= 1u;
+        } else if (!(ky >= 0.0f)) {                                 // bad.py:461, :570 -> the row is all zeros
+            float* out = a.desc + (size_t)kidx * a.P;
+            for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
+        }                                                           // else: non-integer image, sparse_bad_kernel does it
+        group_bar(g);                                               // everyone is done with this buffer
+        if (NBUF == 1 && kidx + stride < total) issue(kidx + stride, 0);
+    }
+}
+
 template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
 int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t st) {
-    constexpr int S = 2 * HS + 1, WR = S + 1, WP = (S + 1 + 3 + 3) / 4 * 4, GSTRIDE = (WR * WP + 31) / 32 * 32;
+    using G = WinGeom<HS>;
     const int Hi = a.H + 2 * a.pad + 1, IP = ipitch(a.W, a.pad);
     CUtensorMap tmap;
-    OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, WP, WR));
-    const size_t smem = (size_t)GROUPS * GSTRIDE * 4 + ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2)) : 0);
-    auto kernel = sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR>;
+    OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, G::WP, G::WR));
+    constexpr int NBUF = 1;
+    const size_t smem = (size_t)GROUPS * NBUF * G::GSTRIDE * 4 +
+                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (2 * sizeof(uint4) + sizeof(float2)) : 0);
+    auto kernel = sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF>;
     OM_TRY(set_smem(kernel, smem));
     const long long total = (long long)a.B * a.K;
-    kernel<<<(unsigned)((total + GROUPS - 1) / GROUPS), GROUPS * TPG, smem, st>>>(tmap, a);
+    const long long nblk = (total + GROUPS - 1) / GROUPS;
+    const int per_sm = (int)(220 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory
+    const long long resident = 148ll * (per_sm < 1 ? 1 : per_sm);
+    kernel<<<(unsigned)(nblk < resident ? nblk : resident), GROUPS * TPG, smem, st>>>(tmap, a);
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -608,7 +684,7 @@ __global__ void __launch_bounds__(256) angle_map_kernel(const float* image, int 
 // images and within 1e-13 relative otherwise, i.e. identical after the single rounding.
 constexpr int PC_COLS = 32, PC_SEG = 32;
 
-template <bool EXACT>
+template <bool EXACT, int LMAX>   // LMAX > 0: a segment (<= LMAX rows) is kept in registers between the two walks
 __global__ void __launch_bounds__(PC_COLS * PC_SEG) prefix_cols_kernel(const float* image, int H, int W, int pad, void* Tout,
                                                                        unsigned int* flags) {
     using Acc = typename std::conditional<EXACT, unsigned int, double>::type;
@@ -622,32 +698,61 @@ __global__ void __launch_bounds__(PC_COLS * PC_SEG) prefix_cols_kernel(const flo
     const int y0 = sg * L, y1 = min(y0 + L, Hp);
     const bool live = xx < Wp;
     const float* col = image + (size_t)z * H * W + clampi(xx - pad, 0, W - 1);
+    float vals[LMAX > 0 ? LMAX : 1];
     Acc acc = 0;
     bool odd = false;
     if (live) {
+        if (LMAX > 0) {
+#pragma unroll
+            for (int k = 0; k < LMAX; ++k)
+                vals[k] = (y0 + k < y1) ? __ldg(col + (size_t)clampi(y0 + k - pad, 0, H - 1) * W) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < LMAX; ++k) {
+                if (EXACT) {
+                    odd |= !(vals[k] == rintf(vals[k]) && vals[k] >= 0.0f && vals[k] <= 65535.0f);
+                    acc += (Acc)__float2uint_rz(vals[k]);
+                } else {
+                    acc += (Acc)vals[k];
+                }
+            }
+        } else {
 #pragma unroll 4
-        for (int yy = y0; yy < y1; ++yy) {
-            const float v = __ldg(col + (size_t)clampi(yy - pad, 0, H - 1) * W);
-            if (EXACT) {
-                odd |= !(v == rintf(v) && v >= 0.0f && v <= 65535.0f);
-                acc += (Acc)__float2uint_rz(v);
-            } else {
-                acc += (Acc)v;
+            for (int yy = y0; yy < y1; ++yy) {
+                const float v = __ldg(col + (size_t)clampi(yy - pad, 0, H - 1) * W);
+                if (EXACT) {
+                    odd |= !(v == rintf(v) && v >= 0.0f && v <= 65535.0f);
+                    acc += (Acc)__float2uint_rz(v);
+                } else {
+                    acc += (Acc)v;
+                }
             }
         }
     }
     seg_total[sg][cx] = acc;
     const int any_odd = __syncthreads_or(odd ? 1 : 0);
-    if (EXACT && any_odd && threadIdx.x == 0) atomicOr(&flags[z], 1u);
+    if (EXACT && any_odd && threadIdx.x == 0) {
+        atomicOr(&flags[z], 1u);
+        atomicOr(&flags[gridDim.y], 1u);                     // "some image of the batch is flagged"
+    }
     if (!live) return;
     acc = 0;
     for (int q = 0; q < sg; ++q) acc += seg_total[q][cx];
     Out* dst = reinterpret_cast<Out*>(Tout) + (size_t)z * Hp * Wp + xx;
+    if (LMAX > 0) {
+#pragma unroll
+        for (int k = 0; k < LMAX; ++k) {
+            if (y0 + k < y1) {
+                acc += EXACT ? (Acc)__float2uint_rz(vals[k]) : (Acc)vals[k];
+                dst[(size_t)(y0 + k) * Wp] = (Out)acc;
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (int yy = y0; yy < y1; ++yy) {
-        const float v = __ldg(col + (size_t)clampi(yy - pad, 0, H - 1) * W);
-        acc += EXACT ? (Acc)__float2uint_rz(v) : (Acc)v;
-        dst[(size_t)yy * Wp] = (Out)acc;
+        for (int yy = y0; yy < y1; ++yy) {
+            const float v = __ldg(col + (size_t)clampi(yy - pad, 0, H - 1) * W);
+            acc += EXACT ? (Acc)__float2uint_rz(v) : (Acc)v;
+            dst[(size_t)yy * Wp] = (Out)acc;
+        }
     }
 }
 
@@ -699,7 +804,10 @@ __global__ void __launch_bounds__(IR_ROWS * 32) prefix_rows_kernel(const void* T
 template <bool EXACT>
 int build_prefix(const float* image, int B, int H, int W, int pad, void* T, void* I, unsigned int* flags, cudaStream_t st) {
     const int Wp = W + 2 * pad, Hp = H + 2 * pad;
-    prefix_cols_kernel<EXACT><<<dim3((Wp + PC_COLS - 1) / PC_COLS, B), PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags);
+    const dim3 cgrid((Wp + PC_COLS - 1) / PC_COLS, B);
+    const int L = (Hp + PC_SEG - 1) / PC_SEG;
+    if (EXACT && L <= 20) prefix_cols_kernel<EXACT, 20><<<cgrid, PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags);
+    else prefix_cols_kernel<EXACT, 0><<<cgrid, PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags);
     OM_AFTER_LAUNCH();
     const int SL = ((Wp + 31) / 32) | 1;
     const size_t smem = (size_t)IR_ROWS * 32 * SL * 4;
@@ -717,7 +825,7 @@ __device__ __forceinline__ float dense_box_mean(const float* I, int pitch, int c
     const float s = __fadd_rn(__fsub_rn(__fsub_rn(I[y1 * pitch + x1], I[y0 * pitch + x1]), I[y1 * pitch + x0]),
                               I[y0 * pitch + x0]);
     const float side = (float)(2 * r + 1);
-    return __fdiv_rn(s, side * side);
+    return __fdiv_rn(s, side * side);                        // bad.py:99
 }
 
 // planes[r][y][x] = box mean of radius r centred on image pixel (y,x), r = 0..7
@@ -776,99 +884,65 @@ struct DenseKpArgs {
 // to 3 columns early: 48 rows x 52 columns
 constexpr int DK_LO = 15, DK_ROWS = 48, DK_SPAN = 52;
 
-template <int GROUPS>
-__global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __grid_constant__ CUtensorMap tmap, DenseKpArgs a) {
-    constexpr int LO = DK_LO, SPAN = DK_SPAN;   // integral rows [iy0-15, iy0+31] cover every tap of the 4 neighbours
-    constexpr int WIN = GROUPS * DK_ROWS * SPAN;             // 48*52*4 bytes per group: a multiple of 128
-    extern __shared__ __align__(128) float sI[];
-    __shared__ float red[GROUPS * 2];
-    __shared__ __align__(8) unsigned long long bars[GROUPS];
-    uint4* sTap = reinterpret_cast<uint4*>(sI + WIN);
-    float2* sThr = reinterpret_cast<float2*>(sTap + a.P);
-    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < GROUPS; ++i) mbar_init(smem_u32(&bars[i]), 1);
-        mbar_fence_init();
-    }
-
-    for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
-        // window coordinates of the taps of neighbour (0,0): pixel q of the image is integral index q + MAXR,
-        // the window starts at integral index iy0 - LO
-        const PairRow row = load_pair(a.table, p);
-        const int r = (int)row.r;
-        const int cy1 = LO + MAXR + (int)row.oy1, cx1 = LO + MAXR + (int)row.ox1;
-        const int cy2 = LO + MAXR + (int)row.oy2, cx2 = LO + MAXR + (int)row.ox2;
-        auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * SPAN + x); };
-        uint4 tp;   // order of bad.py:98: (y1,x1) - (y0,x1) - (y1,x0) + (y0,x0)
-        tp.x = off(cy1 + r + 1, cx1 + r + 1) | (off(cy1 - r, cx1 + r + 1) << 16);
-        tp.y = off(cy1 + r + 1, cx1 - r) | (off(cy1 - r, cx1 - r) << 16);
-        tp.z = off(cy2 + r + 1, cx2 + r + 1) | (off(cy2 - r, cx2 + r + 1) << 16);
-        tp.w = off(cy2 + r + 1, cx2 - r) | (off(cy2 - r, cx2 - r) << 16);
-        sTap[p] = tp;
-        const float side = (float)(2 * r + 1);
-        sThr[p] = make_float2(row.thr, side * side);
-    }
-    __syncthreads();
-
-    const long long total = (long long)a.B * a.K;
-    const long long kidx = (long long)blockIdx.x * GROUPS + g;
-    if (kidx >= total) return;                  // whole group leaves: later barriers are per group
-    const int z = (int)(kidx / a.K);
-    const int H = a.H, W = a.W;
-    float* Lbox = sI + (size_t)g * DK_ROWS * SPAN;
-    float* out = a.desc + (size_t)kidx * a.P;
-
-    const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
-    if (!(ky >= 0.0f)) {                        // shi_tomasi_bad_sinkhorn.py:143,158: masked rows are zero
-        for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
-        return;
-    }
+// bilinear sampling position of a keypoint (bad.py:311-312: kp / (dim-1+1e-8) * 2 - 1, then ATen unnormalise + clip)
+struct DenseKp {
+    int iy0, ix0;          // top-left neighbour
+    float w, s;            // fractional parts along x and y
+};
+__device__ __forceinline__ DenseKp dense_kp_pos(float ky, float kx, int H, int W) {
     const float yc = fminf(fmaxf(ky, 0.0f), (float)(H - 1));
     const float xc = fminf(fmaxf(kx, 0.0f), (float)(W - 1));
-    // bad.py:311-312: kp / (dim-1+1e-8) * 2 - 1, then ATen unnormalise + clip
     const float gyn = __fsub_rn(__fmul_rn(__fdiv_rn(yc, (float)(H - 1 + 1e-8)), 2.0f), 1.0f);
     const float gxn = __fsub_rn(__fmul_rn(__fdiv_rn(xc, (float)(W - 1 + 1e-8)), 2.0f), 1.0f);
     const float uy = fminf(fmaxf(__fmul_rn(__fadd_rn(gyn, 1.0f), (float)(H - 1) * 0.5f), 0.0f), (float)(H - 1));
     const float ux = fminf(fmaxf(__fmul_rn(__fadd_rn(gxn, 1.0f), (float)(W - 1) * 0.5f), 0.0f), (float)(W - 1));
     const float fy = floorf(uy), fx = floorf(ux);
-    const float w = ux - fx, e = 1.0f - w, s = uy - fy, n = 1.0f - s;
-    const int iy0 = (int)fy, ix0 = (int)fx;
+    DenseKp k;
+    k.iy0 = (int)fy; k.ix0 = (int)fx; k.w = ux - fx; k.s = uy - fy;
+    return k;
+}
+
+// one keypoint whose window `Lbox` is in flight / has landed on mbarrier `bar` (phase `parity`)
+__device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long kidx, float ky, float kx, const float* Lbox,
+                                               uint32_t bar, uint32_t parity, float* red, const uint4* sTap,
+                                               const float4* sThr, int g, int t) {
+    constexpr int LO = DK_LO, SPAN = DK_SPAN;
+    const int H = a.H, W = a.W;
+    float* out = a.desc + (size_t)kidx * a.P;
+    const DenseKp kp = dense_kp_pos(ky, kx, H, W);
+    const int iy0 = kp.iy0, ix0 = kp.ix0;
+    const float w = kp.w, e = 1.0f - w, s = kp.s, n = 1.0f - s;
     const int ys = min(iy0 + 1, H - 1), xe = min(ix0 + 1, W - 1);
     const int oy = iy0 - LO, ox = ix0 - LO;     // integral coords of L(0,0)
     const float wgt[4] = {n * e, n * w, s * e, s * w};                  // nw, ne, sw, se
-
-    // one TMA box: rows/columns outside the integral read as zero and are never used as taps
     const float* L = Lbox + (ox & 3);           // window column 0 inside the 16-byte aligned box
-    if (t == 0) {
-        mbar_arrive_expect_tx(smem_u32(&bars[g]), DK_ROWS * SPAN * 4);
-        tma_load_3d(smem_u32(Lbox), &tmap, smem_u32(&bars[g]), ox & ~3, oy, z);
-    }
-    mbar_wait(smem_u32(&bars[g]), 0u);
+    mbar_wait(bar, parity);
 
     constexpr int MAXPP = 8;
     float d[MAXPP];
     float ss = 0.0f;
     // no centre clamp for any of the four neighbours <=> their offsets in [-15,14] stay inside the image
     const bool interior = iy0 >= 15 && iy0 + 1 + 14 <= H - 1 && ix0 >= 15 && ix0 + 1 + 14 <= W - 1;
+    const char* lbytes = reinterpret_cast<const char*>(L);
+    auto ldl = [&](unsigned int byte_off) -> float { return *reinterpret_cast<const float*>(lbytes + byte_off); };
     if (interior) {
 #pragma unroll
         for (int q = 0; q < MAXPP; ++q) {
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                const uint4 tp = sTap[p];
-                const float2 tb = sThr[p];
+                const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+                const float4 tb = sThr[p];
                 float v = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (wgt[k] != 0.0f) {                                   // group-uniform
-                        const float* Lk = L + (k >> 1) * SPAN + (k & 1);
-                        const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(Lk[tp.x & 0xFFFFu], Lk[tp.x >> 16]), Lk[tp.y & 0xFFFFu]),
-                                                   Lk[tp.y >> 16]);
-                        const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(Lk[tp.z & 0xFFFFu], Lk[tp.z >> 16]), Lk[tp.w & 0xFFFFu]),
-                                                   Lk[tp.w >> 16]);
-                        const float diff = __fsub_rn(__fdiv_rn(s1, tb.y), __fdiv_rn(s2, tb.y));
+                        const unsigned int lk = ((k >> 1) * SPAN + (k & 1)) * 4;
+                        const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + ta.x), ldl(lk + ta.y)), ldl(lk + ta.z)),
+                                                   ldl(lk + ta.w));
+                        const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + tc.x), ldl(lk + tc.y)), ldl(lk + tc.z)),
+                                                   ldl(lk + tc.w));
+                        const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));   // bad.py:99, :110
                         v += finish_value(diff, tb.x, a.mode, a.temperature) * wgt[k];
                     }
                 }
@@ -909,16 +983,91 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __gri
     }
 }
 
+// Every 64-thread group walks its keypoints (grid-stride); NBUF as in sparse_win_kernel.
+template <int GROUPS, int NBUF>
+__global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __grid_constant__ CUtensorMap tmap, DenseKpArgs a) {
+    constexpr int LO = DK_LO, SPAN = DK_SPAN;   // integral rows [iy0-15, iy0+31] cover every tap of the 4 neighbours
+    constexpr int WBUF = DK_ROWS * SPAN;                     // 48*52*4 bytes per window: a multiple of 128
+    extern __shared__ __align__(128) float sI[];
+    __shared__ float red[GROUPS * 2];
+    __shared__ __align__(8) unsigned long long bars[GROUPS * 2];
+    uint4* sTap = reinterpret_cast<uint4*>(sI + GROUPS * NBUF * WBUF);   // 2 x 4 window byte offsets per pair
+    float4* sThr = reinterpret_cast<float4*>(sTap + 2 * a.P);         // {threshold, area, float(1/area), -}
+    const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < GROUPS * 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_fence_init();
+    }
+
+    for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+        // window coordinates of the taps of neighbour (0,0): pixel q of the image is integral index q + MAXR,
+        // the window starts at integral index iy0 - LO
+        const PairRow row = load_pair(a.table, p);
+        const int r = (int)row.r;
+        const int cy1 = LO + MAXR + (int)row.oy1, cx1 = LO + MAXR + (int)row.ox1;
+        const int cy2 = LO + MAXR + (int)row.oy2, cx2 = LO + MAXR + (int)row.ox2;
+        auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * SPAN + x) * 4u; };
+        // order of bad.py:98: (y1,x1) - (y0,x1) - (y1,x0) + (y0,x0)
+        sTap[2 * p] = make_uint4(off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r),
+                                 off(cy1 - r, cx1 - r));
+        sTap[2 * p + 1] = make_uint4(off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r),
+                                     off(cy2 - r, cx2 - r));
+        const float side = (float)(2 * r + 1);
+        sThr[p] = make_float4(row.thr, side * side, __fdiv_rn(1.0f, side * side), 0.0f);
+    }
+    __syncthreads();
+
+    const long long total = (long long)a.B * a.K;
+    const long long stride = (long long)gridDim.x * GROUPS;
+    float* wbuf = sI + (size_t)g * NBUF * WBUF;
+    const uint32_t bar0 = smem_u32(&bars[2 * g]);
+    // thread 0 of the group launches the window load of keypoint k into buffer `buf`: one TMA box, rows/columns
+    // outside the integral read as zero and are never used as taps
+    auto issue = [&](long long k, int buf) {
+        if (t == 0) {
+            const float ky = a.kpts[k * 2 + 0], kx = a.kpts[k * 2 + 1];
+            if (ky >= 0.0f) {
+                const DenseKp kp = dense_kp_pos(ky, kx, a.H, a.W);
+                const uint32_t bar = bar0 + 8u * buf;
+                mbar_arrive_expect_tx(bar, WBUF * 4);
+                tma_load_3d(smem_u32(wbuf + buf * WBUF), &tmap, bar, (kp.ix0 - LO) & ~3, kp.iy0 - LO, (int)(k / a.K));
+            }
+        }
+    };
+    long long kidx = (long long)blockIdx.x * GROUPS + g;
+    if (kidx < total) issue(kidx, 0);
+    uint32_t phase[2] = {0u, 0u};
+    for (int n = 0; kidx < total; kidx += stride, ++n) {
+        const int buf = NBUF == 2 ? (n & 1) : 0;
+        if (NBUF == 2 && kidx + stride < total) issue(kidx + stride, buf ^ 1);   // that buffer was released by the barrier below
+        const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
+        if (ky >= 0.0f) {
+            dense_kp_group(a, kidx, ky, kx, wbuf + buf * WBUF, bar0 + 8u * buf, phase[buf], red, sTap, sThr, g, t);
+            phase[buf] ^= 1u;
+        } else {                                                    // shi_tomasi_bad_sinkhorn.py:143,158: masked rows are zero
+            float* out = a.desc + (size_t)kidx * a.P;
+            for (int p = t; p < a.P; p += TPG) out[p] = 0.0f;
+        }
+        group_bar(g);                                               // everyone is done with this buffer
+        if (NBUF == 1 && kidx + stride < total) issue(kidx + stride, 0);
+    }
+}
+
 template <int GROUPS>
 int launch_dense_kp(const DenseKpArgs& a, cudaStream_t st) {
     CUtensorMap tmap;
     const int IP = ipitch(a.W, MAXR);
     OM_TRY(make_tmap_3d(&tmap, true, a.I, (uint64_t)IP, (uint64_t)(a.H + 2 * MAXR + 1), (uint64_t)a.B, (uint64_t)IP, DK_SPAN,
                         DK_ROWS));
-    const size_t smem = (size_t)GROUPS * DK_ROWS * DK_SPAN * sizeof(float) + (size_t)a.P * (sizeof(uint4) + sizeof(float2));
-    OM_TRY(set_smem(dense_at_kpts_kernel<GROUPS>, smem));
+    constexpr int NBUF = 1;
+    const size_t smem = (size_t)GROUPS * NBUF * DK_ROWS * DK_SPAN * sizeof(float) + (size_t)a.P * (2 * sizeof(uint4) + sizeof(float4));
+    OM_TRY(set_smem((dense_at_kpts_kernel<GROUPS, NBUF>), smem));
     const long long total = (long long)a.B * a.K;
-    dense_at_kpts_kernel<GROUPS><<<(unsigned)((total + GROUPS - 1) / GROUPS), GROUPS * TPG, smem, st>>>(tmap, a);
+    const long long nblk = (total + GROUPS - 1) / GROUPS;
+    const int per_sm = (int)(220 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory
+    const long long resident = 148ll * (per_sm < 1 ? 1 : per_sm);
+    dense_at_kpts_kernel<GROUPS, NBUF><<<(unsigned)(nblk < resident ? nblk : resident), GROUPS * TPG, smem, st>>>(tmap, a);
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -966,7 +1115,7 @@ DenseWs carve_dense(void* ws, int B, int H, int W) {
 }
 
 struct SparseWs {
-    unsigned int* flags;   // (B) non-integer-pixel flags
+    unsigned int* flags;   // (B+1) non-integer-pixel flag per image, [B] = any image flagged
     unsigned int* T;       // (B, H+2pad, W+2pad)
     unsigned int* I;       // (B, H+2pad+1, ipitch)
 };
@@ -978,7 +1127,7 @@ SparseWs carve_sparse(void* ws, int B, int H, int W, int pad) {
     SparseWs d;
     char* p = (char*)ws;
     d.flags = (unsigned int*)p;
-    p += align_up((size_t)B * sizeof(unsigned int));
+    p += align_up((size_t)(B + 1) * sizeof(unsigned int));
     d.T = (unsigned int*)p;
     p += align_up((size_t)B * (H + 2 * pad) * (W + 2 * pad) * sizeof(unsigned int));
     d.I = (unsigned int*)p;
@@ -1000,7 +1149,7 @@ int build_integral(const float* image, int B, int H, int W, const DenseWs& d, cu
 size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const int pad = theta_mode == OM_THETA_NONE ? PAD_PLAIN : PAD_ORI;
-    return align_up((size_t)B * sizeof(unsigned int)) +
+    return align_up((size_t)(B + 1) * sizeof(unsigned int)) +
            align_up((size_t)B * (H + 2 * pad) * (W + 2 * pad) * sizeof(unsigned int)) +
            align_up((size_t)B * (H + 2 * pad + 1) * ipitch(W, pad) * sizeof(unsigned int));
 }
@@ -1024,7 +1173,7 @@ int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts
     const bool oriented = theta_mode != OM_THETA_NONE;
     const int pad = oriented ? PAD_ORI : PAD_PLAIN;
     const SparseWs w = carve_sparse(ws, B, H, W, pad);
-    OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)B * sizeof(unsigned int), st));
+    OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)(B + 1) * sizeof(unsigned int), st));
     OM_TRY(build_prefix<true>(image, B, H, W, pad, w.T, w.I, w.flags, st));
     SparseArgs a{};
     a.image = image; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P;

@@ -30,7 +30,8 @@ namespace {
 constexpr int CL = 8;               // CTAs per cluster == per descriptor pair
 constexpr int NW = 16;              // producer / sweep warps
 constexpr int NP = NW * 32;         // producer threads (stage the GEMM operands, run the Sinkhorn sweep)
-constexpr int NT = NP + 32;         // + one warp whose lane 0 issues the tcgen05.mma stream
+constexpr int NT = NP;              // 16 warps: 4 per SM sub-partition -> 128 registers per thread (a 17th warp
+                                    // would cap every thread at 96); thread 0 also issues the tcgen05.mma stream
 constexpr int RPC = 64;             // real score rows per CTA
 constexpr int MAXM = 512;
 constexpr int NCOL = 544;           // 17 columns per lane; columns beyond M hold -inf
@@ -83,6 +84,12 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
+// 4-byte store into a peer CTA's shared memory that also completes 4 bytes on the PEER's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t dst_cluster, float v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster),
+                 "r"(__float_as_uint(v)), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void bar_sweep() { asm volatile("bar.sync 1, %0;" ::"n"(NP) : "memory"); }
 // UMMA shared-memory descriptor, no swizzle, K-major (cute/arch/mma_sm100_desc.hpp layout)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
@@ -142,6 +149,8 @@ struct TcArgs {
         if (a.trace != nullptr && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); \
     } while (0)
 
+// XD = true: "scaling" form of the same iteration (see the block comment at the XD branch below)
+template <bool XD>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_kernel(TcArgs a) {
     extern __shared__ __align__(128) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -244,30 +253,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
                 mbar_arrive(smem_u32(&bars[5 + s]));                            // stage s is full
                 fetch(c + 2, qa, qb);
-            }
-        } else if (lane == 0) {
-            // ===== MMA issuer: one thread drives the tensor core, never touches the operands itself =====
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c & 1;
-                mbar_wait(smem_u32(&bars[5 + s]), (uint32_t)((c >> 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = stage0 + s * STAGE_BYTES;
+                if (tid == 0) {
+                    // ===== MMA issue: wait until every producer has stored chunk c, then drive the tensor core =====
+                    mbar_wait(smem_u32(&bars[5 + s]), (uint32_t)((c >> 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = stage0 + s * STAGE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint64_t bhi = umma_desc(sa + 2 * A_TILE + 2 * ks * B_LBO, B_LBO, SBO);
-                    const uint64_t blo = umma_desc(sa + 2 * A_TILE + B_TILE + 2 * ks * B_LBO, B_LBO, SBO);
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint64_t bhi = umma_desc(sa + 2 * A_TILE + 2 * ks * B_LBO, B_LBO, SBO);
+                        const uint64_t blo = umma_desc(sa + 2 * A_TILE + B_TILE + 2 * ks * B_LBO, B_LBO, SBO);
 #pragma unroll
-                    for (int mb = 0; mb < 4; ++mb) {
-                        const uint64_t ahi = umma_desc(sa + 2 * ks * A_LBO + mb * 128 * 16, A_LBO, SBO);
-                        const uint64_t alo = umma_desc(sa + A_TILE + 2 * ks * A_LBO + mb * 128 * 16, A_LBO, SBO);
-                        const uint32_t d = tmem_base + mb * 64;
-                        umma_tf32(d, ahi, bhi, (c | ks) != 0);
-                        umma_tf32(d, ahi, blo, 1u);
-                        umma_tf32(d, alo, bhi, 1u);
+                        for (int mb = 0; mb < 4; ++mb) {
+                            const uint64_t ahi = umma_desc(sa + 2 * ks * A_LBO + mb * 128 * 16, A_LBO, SBO);
+                            const uint64_t alo = umma_desc(sa + A_TILE + 2 * ks * A_LBO + mb * 128 * 16, A_LBO, SBO);
+                            const uint32_t d = tmem_base + mb * 64;
+                            umma_tf32(d, ahi, bhi, (c | ks) != 0);
+                            umma_tf32(d, ahi, blo, 1u);
+                            umma_tf32(d, alo, bhi, 1u);
+                        }
                     }
+                    umma_commit(smem_u32(&bars[s]));                    // frees stage s when these MMAs retire
+                    if (c == nchunks - 1) umma_commit(smem_u32(&bars[2]));
                 }
-                umma_commit(smem_u32(&bars[s]));                    // frees stage s when these MMAs retire
-                if (c == nchunks - 1) umma_commit(smem_u32(&bars[2]));
+
             }
         }
         __syncwarp();
@@ -320,6 +328,183 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
             for (int jj = tid; jj < M; jj += NT) sS[nreal * SPITCH + jj] = a.dustbin2;
     }
     OM_STAMP(3);                                                    // epilogue done
+
+    if constexpr (XD) {
+        // ---------------- Sinkhorn in scaling form, K resident in REGISTERS ----------------------------
+        // With K_ij = exp(S_ij), a_i = exp(u_i), b_j = exp(v_j) the log-domain updates of sinkhorn.py:138-142
+        //     u_i = log mu_i - LSE_j(S_ij + v_j),   v_j = log nu_j - LSE_i(S_ij + u_i)
+        // are  a_i = mu_i / sum_j K_ij b_j,   b_j = nu_j / sum_i K_ij a_i,  and P = a_i K_ij b_j (:145, :206).
+        // The launcher takes this path only when exp(-unused/eps) is far from underflow, so every row and
+        // column sum keeps a positive dustbin term; K entries may underflow to 0 exactly as exp() of the
+        // reference's shifted exponents does.  No exponential is evaluated inside the loop: one sweep is
+        // 2 FFMA per matrix entry on registers.  The dustbin row/column are the constant kd and are never stored:
+        //     rowsum_i = sum_j K_ij b_j + kd b_M,   rowsum_N = kd (sum_j b_j + b_M)
+        //     colsum_j = sum_i K_ij a_i + kd a_N,   colsum_M = kd (sum_i a_i + a_N)
+        // Warp w owns score rows 4w..4w+3 of this CTA, lane l columns 4l..4l+3 (+128k): row sums stay inside
+        // the warp; column sums go warp -> CTA through shared memory and CTA -> cluster as a reduce-scatter
+        // (CTA c owns columns 64c..64c+63, rank 7 also the dustbin column) followed by an all-gather of the
+        // new b, both as st.async stores that complete on the receiver's mbarrier (no cluster-wide barrier
+        // inside the loop).
+        float* sB = sV;                          // b, M+1 entries (entry M = dustbin column)
+        float* sPart = sRecv;                    // [CL][72] partial column sums of the owned columns, one row per sender
+        float* sAs = sU;                         // per-warp sum of a_i
+        const float kd = ex2(a.dustbin2);
+        const float Mf = (float)M, Nf = (float)N;
+        __syncthreads();                         // score slab complete
+        float kreg[4][16];
+        if (warp < NW) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int li = 4 * warp + rr;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c0 = 128 * k + 4 * lane;
+                    const float4 s4 = *reinterpret_cast<const float4*>(sS + li * SPITCH + c0);
+                    const bool rv = li < nreal;
+                    kreg[rr][4 * k + 0] = (rv && c0 + 0 < M) ? ex2(s4.x) : 0.0f;
+                    kreg[rr][4 * k + 1] = (rv && c0 + 1 < M) ? ex2(s4.y) : 0.0f;
+                    kreg[rr][4 * k + 2] = (rv && c0 + 2 < M) ? ex2(s4.z) : 0.0f;
+                    kreg[rr][4 * k + 3] = (rv && c0 + 3 < M) ? ex2(s4.w) : 0.0f;
+                }
+            }
+        }
+        for (int i = tid; i < NCOL; i += NT) sB[i] = i <= M ? 1.0f : 0.0f;      // u = v = 0
+        // landing zones in the peers are the same shared-memory offsets, translated per store with mapa:
+        // my row of their partial table, their b vector, their two barriers
+        const uint32_t my_part = smem_u32(sPart + rank * 72), loc_b = smem_u32(sB);
+        const uint32_t loc_bar_part = smem_u32(&bars[3]), loc_bar_b = smem_u32(&bars[4]);
+        const uint32_t part_bytes = (uint32_t)CL * (has_dust ? 65u : 64u) * 4u;   // every sender sends all owned slots
+        const uint32_t b_bytes = (uint32_t)(CL * 64 + 1) * 4u;
+        cluster.sync();      // every CTA is past its GEMM (staging aliased these buffers) and has initialised its barriers
+        OM_STAMP(4);
+
+        float breg[16], bM = 1.0f, areg[4] = {0.f, 0.f, 0.f, 0.f}, aN = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) breg[c] = (128 * (c >> 2) + 4 * lane + (c & 3)) < M ? 1.0f : 0.0f;
+        if (warp < NW) {
+            for (int it = 0; it < a.iterations; ++it) {
+                const uint32_t par = (uint32_t)(it & 1);
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(smem_u32(&bars[3]), part_bytes);
+                    mbar_arrive_expect_tx(smem_u32(&bars[4]), b_bytes);
+                }
+                // ---- a_i = mu_i / rowsum_i --------------------------------------------------------------
+                float rs[4], sb = 0.0f;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        e0 = fmaf(kreg[rr][c], breg[c], e0);
+                        e1 = fmaf(kreg[rr][c + 1], breg[c + 1], e1);
+                    }
+                    rs[rr] = e0 + e1;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) sb += breg[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) rs[rr] += __shfl_xor_sync(0xffffffffu, rs[rr], o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                }
+                float asum = 0.0f;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    areg[rr] = (4 * warp + rr < nreal) ? __fdividef(1.0f, fmaf(kd, bM, rs[rr])) : 0.0f;
+                    asum += areg[rr];
+                }
+                aN = __fdividef(Mf, kd * (sb + bM));                   // dustbin row: mu_N = M (sinkhorn.py:197-198)
+                // ---- column sums: warp partials -> CTA partials -> owners -------------------------------
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float4 t4;
+                    t4.x = fmaf(kreg[3][4 * k + 0], areg[3], fmaf(kreg[2][4 * k + 0], areg[2], fmaf(kreg[1][4 * k + 0], areg[1], kreg[0][4 * k + 0] * areg[0])));
+                    t4.y = fmaf(kreg[3][4 * k + 1], areg[3], fmaf(kreg[2][4 * k + 1], areg[2], fmaf(kreg[1][4 * k + 1], areg[1], kreg[0][4 * k + 1] * areg[0])));
+                    t4.z = fmaf(kreg[3][4 * k + 2], areg[3], fmaf(kreg[2][4 * k + 2], areg[2], fmaf(kreg[1][4 * k + 2], areg[1], kreg[0][4 * k + 2] * areg[0])));
+                    t4.w = fmaf(kreg[3][4 * k + 3], areg[3], fmaf(kreg[2][4 * k + 3], areg[2], fmaf(kreg[1][4 * k + 3], areg[1], kreg[0][4 * k + 3] * areg[0])));
+                    *reinterpret_cast<float4*>(sCW + warp * MAXM + 128 * k + 4 * lane) = t4;
+                }
+                if (lane == 0) sAs[warp] = asum;
+                bar_sweep();
+                {
+                    float s0 = sCW[tid], s1 = sCW[MAXM + tid], s2 = sCW[2 * MAXM + tid], s3 = sCW[3 * MAXM + tid];
+#pragma unroll
+                    for (int w = 4; w < NW; w += 4) {
+                        s0 += sCW[w * MAXM + tid]; s1 += sCW[(w + 1) * MAXM + tid];
+                        s2 += sCW[(w + 2) * MAXM + tid]; s3 += sCW[(w + 3) * MAXM + tid];
+                    }
+                    const int owner = tid >> 6;
+                    st_async_f32(mapa_u32(my_part + (uint32_t)(tid & 63) * 4u, (uint32_t)owner), (s0 + s1) + (s2 + s3),
+                                 mapa_u32(loc_bar_part, (uint32_t)owner));
+                    if (tid == 0) {
+                        float as = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) as += sAs[w];
+                        st_async_f32(mapa_u32(my_part + 64u * 4u, (uint32_t)(CL - 1)), kd * as, mapa_u32(loc_bar_part, (uint32_t)(CL - 1)));
+                    }
+                }
+                // ---- owners: b_j = nu_j / colsum_j, sent to every CTA -----------------------------------
+                mbar_wait(smem_u32(&bars[3]), par);
+                if (tid < 64 || (tid == 64 && has_dust)) {
+                    float t = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < CL; ++r) t += sPart[r * 72 + tid];
+                    const int c = tid == 64 ? M : 64 * rank + tid;      // global column (M = dustbin column)
+                    t = fmaf(kd, aN, t);
+                    const float bnew = (tid == 64) ? __fdividef(Nf, t) : (c < M ? __fdividef(1.0f, t) : 0.0f);   // nu_M = N (:199-200)
+                    const uint32_t slot = (uint32_t)(tid == 64 ? MAXM : c) * 4u;
+#pragma unroll
+                    for (int dst = 0; dst < CL; ++dst)
+                        st_async_f32(mapa_u32(loc_b + slot, (uint32_t)dst), bnew, mapa_u32(loc_bar_b, (uint32_t)dst));
+                }
+                mbar_wait(smem_u32(&bars[4]), par);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sB + 128 * k + 4 * lane);
+                    breg[4 * k + 0] = b4.x; breg[4 * k + 1] = b4.y; breg[4 * k + 2] = b4.z; breg[4 * k + 3] = b4.w;
+                }
+                bM = sB[MAXM];
+            }
+        }
+        OM_STAMP(5);
+        // ---------------- P = a_i K_ij b_j (sinkhorn.py:145, :206) -----------------------------------------
+        float* Pz = a.P + (size_t)z * (N + 1) * (M + 1);
+        if (warp < NW) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int li = 4 * warp + rr;
+                if (li < nreal) {                                       // warp-uniform
+                    float* stage = sS + li * SPITCH;                    // this warp's own slab row: transposes to coalesced stores
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float4 p4;
+                        p4.x = areg[rr] * kreg[rr][4 * k + 0] * breg[4 * k + 0];
+                        p4.y = areg[rr] * kreg[rr][4 * k + 1] * breg[4 * k + 1];
+                        p4.z = areg[rr] * kreg[rr][4 * k + 2] * breg[4 * k + 2];
+                        p4.w = areg[rr] * kreg[rr][4 * k + 3] * breg[4 * k + 3];
+                        *reinterpret_cast<float4*>(stage + 128 * k + 4 * lane) = p4;
+                    }
+                    __syncwarp();
+                    float* out = Pz + (size_t)(r0 + li) * (M + 1);
+#pragma unroll
+                    for (int k = 0; k < MAXM / 32; ++k) {
+                        const int c = lane + 32 * k;
+                        if (c < M) out[c] = stage[c];
+                    }
+                    if (lane == 0) out[M] = areg[rr] * kd * bM;
+                }
+            }
+            if (has_dust && warp == 0) {                                // dustbin row, b is in shared memory
+                float* out = Pz + (size_t)N * (M + 1);
+                const float f = aN * kd;
+                for (int c = lane; c < M; c += 32) out[c] = f * sB[c];
+                if (lane == 0) out[M] = f * bM;
+            }
+        }
+        OM_STAMP(6);
+        cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
+    } else {
     for (int i = tid; i < 72; i += NT) sU[i] = 0.0f;
     for (int i = tid; i < NCOL; i += NT) sV[i] = 0.0f;
     __syncthreads();
@@ -454,10 +639,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
     }
     OM_STAMP(6);
     cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
+    }   // !XD
 }
 
 }  // namespace
 
+int g_tc_allow_scaling = 1;         // test hook: 0 forces the log-domain loop of the tcgen05 kernel
 long long* g_tc_trace = nullptr;   // debug: device buffer of B*8 CTAs x 8 stamps, set through om_debug_sinkhorn_trace
 
 int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
@@ -469,8 +656,16 @@ int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, i
     a.scale2 = (float)(log2e / (double)eps);
     a.dustbin2 = (float)((-(double)unused / (double)eps) * log2e);
     const size_t smem = (size_t)SMEM_FLOATS * sizeof(float);
-    OM_TRY(set_smem(sinkhorn_tc_kernel, smem));
-    sinkhorn_tc_kernel<<<B * CL, NT, smem, st>>>(a);
+    // scaling form (no exponentials in the loop) while exp(-unused/eps) stays far from underflow (2^-60);
+    // beyond that the log-domain loop with its max-shift fallback keeps every sum finite
+    const bool scaling = g_tc_allow_scaling && (double)unused / (double)eps * log2e <= 60.0 && unused >= 0.0f;
+    if (scaling) {
+        OM_TRY(set_smem(sinkhorn_tc_kernel<true>, smem));
+        sinkhorn_tc_kernel<true><<<B * CL, NT, smem, st>>>(a);
+    } else {
+        OM_TRY(set_smem(sinkhorn_tc_kernel<false>, smem));
+        sinkhorn_tc_kernel<false><<<B * CL, NT, smem, st>>>(a);
+    }
     OM_AFTER_LAUNCH();
     return OM_OK;
 }

@@ -196,7 +196,7 @@ def test_gather_functions():
 # ------------------------------------------------------------------------------------------
 # Sinkhorn
 # ------------------------------------------------------------------------------------------
-VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic"}
+VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log"}
 
 
 def _with_variant(variant, fn):
@@ -209,7 +209,7 @@ def _with_variant(variant, fn):
 
 
 @pytest.mark.parametrize("name", G.names("sinkhorn"))
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=lambda v: VARIANTS[v])
 def test_sinkhorn_golden(name, variant):
     g = G.load(name)
     got = _with_variant(variant, lambda: om.SinkhornMatcher(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"])))
@@ -219,9 +219,10 @@ def test_sinkhorn_golden(name, variant):
     assert m64["core"] <= PR.PROB_TOL, m64
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 3], ids=lambda v: VARIANTS[v])
 @pytest.mark.parametrize("N,M,eps,unused", [(512, 512, 1.0, 1.0), (512, 512, 0.05, 1.0), (300, 512, 0.1, 0.5),
-                                            (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0)])
+                                            (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0),
+                                            (509, 511, 0.03, 1.0), (512, 512, 0.2, 0.0)])
 def test_sinkhorn_cluster_vs_oracle(N, M, eps, unused, variant):
     g = torch.Generator().manual_seed(N * 7 + M)
     d1 = torch.nn.functional.normalize(torch.randn(2, N, 256, generator=g), dim=-1)
@@ -244,7 +245,7 @@ def test_sinkhorn_variants_agree_on_matched_descriptors():
     d1 = torch.nn.functional.normalize(torch.randn(3, 512, 256, generator=g), dim=-1)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(512, generator=g)] + 0.02 * torch.randn(3, 512, 256, generator=g), dim=-1)
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.05, 1.0).float()
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         got = _with_variant(variant, lambda: om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2)))
         m = PR.prob_metrics(got, ref)
         assert PR.probs_ok(m), (VARIANTS[variant], m)
