@@ -188,8 +188,9 @@ int om_match_pairs_f32(const om_match_params* p, const float* image1, const floa
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 
-/* Route every stencil launch through the generic (runtime block size / radius) kernel instead of
- * the compile-time specialised one; lets the tests check the two against each other. */
+/* Stencil kernel selection: 0 = register sweep kernel (default for block 3/5, radius 3/5), 1 = generic
+ * (runtime block size / radius) kernel, 2 = tiled shared-memory kernel; lets the tests check them
+ * against each other. */
 void om_debug_force_generic_stencil(int on);
 
 /* Route om_sinkhorn_f32 / the fused matcher through the generic global-memory Sinkhorn kernels

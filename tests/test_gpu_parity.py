@@ -48,11 +48,14 @@ def test_score_map_bit_exact(block_size, shape):
 
 
 @pytest.mark.parametrize("block_size,nms_radius", [(3, 3), (3, 5), (5, 3), (5, 5)])
-def test_fast_and_generic_stencil_agree(block_size, nms_radius):
-    img, _ = O.texture_images(2, 150, 210, seed=7)
+@pytest.mark.parametrize("shape", [(2, 150, 210), (1, 97, 333), (1, 41, 112), (3, 200, 640)])
+def test_fast_and_generic_stencil_agree(block_size, nms_radius, shape):
+    """sweep kernel (0, default) vs generic kernel (1) vs tiled shared-memory kernel (2): scores, keypoints and
+    keypoint scores must be identical, on widths that are / are not multiples of 4 and of the tile width."""
+    img, _ = O.texture_images(*shape, seed=7)
     lib = _native.lib()
     outs = []
-    for force in (0, 1):
+    for force in (0, 1, 2):
         lib.om_debug_force_generic_stencil(force)
         try:
             sc = om.ShiTomasiScore(block_size).to(DEV)(img.to(DEV))
@@ -60,8 +63,9 @@ def test_fast_and_generic_stencil_agree(block_size, nms_radius):
         finally:
             lib.om_debug_force_generic_stencil(0)
         outs.append((sc.cpu(), k.cpu(), s.cpu()))
-    for a, b in zip(outs[0], outs[1]):
-        assert torch.equal(a, b)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("nms_radius", [0, 1, 2, 3, 5, 8])
