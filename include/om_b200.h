@@ -192,6 +192,8 @@ int om_match_pairs_f32(const om_match_params* p, const float* image1, const floa
  * (runtime block size / radius) kernel, 2 = tiled shared-memory kernel; lets the tests check them
  * against each other. */
 void om_debug_force_generic_stencil(int on);
+/* Sweep-kernel tuning: output rows per tile (0 = default 40) and resident CTAs per SM (3, or 4 = default). */
+void om_debug_sweep_tuning(int strip_rows, int min_blocks);
 
 /* Route om_sinkhorn_f32 / the fused matcher through the generic global-memory Sinkhorn kernels
  * instead of the cluster kernel. */

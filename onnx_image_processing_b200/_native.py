@@ -65,6 +65,7 @@ SIGNATURES = {
     "om_debug_dense_stage": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float,
                                      c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "om_debug_force_generic_stencil": (None, [c_int]),
+    "om_debug_sweep_tuning": (None, [c_int, c_int]),
     "om_debug_force_generic_sinkhorn": (None, [c_int]),
     "om_debug_sinkhorn_variant": (None, [c_int]),
     "om_debug_sinkhorn_trace": (None, [c_void_p]),

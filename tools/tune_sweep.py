@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Time the detector stencil kernel for a few (strip rows, CTAs/SM) settings."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from onnx_image_processing_b200 import _native as nat
+from oracle import oracle as O
+lib = nat.lib()
+B, H, W, K = 64, 480, 640, 512
+img, _ = O.texture_images(B, H, W, seed=3)
+img = img.cuda()
+nat.use_device(0)
+ws = torch.empty(lib.om_topk_workspace_bytes(B, H, W, K), dtype=torch.uint8, device="cuda")
+kp = torch.empty(B, K, 2, device="cuda"); ks = torch.empty(B, K, device="cuda")
+st = torch.cuda.current_stream()
+p = lambda t: ctypes.c_void_p(t.data_ptr())
+def run():
+    nat.check(lib.om_debug_detect_stage(p(img), B, H, W, 3, 3, 7, 0.0, K, p(kp), p(ks), p(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream), 0), "stage")
+for strip, minb in [(40, 3), (40, 4), (60, 3), (80, 3), (30, 3), (60, 4), (120, 3)]:
+    lib.om_debug_sweep_tuning(strip, minb)
+    for _ in range(3): run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(20): run()
+    b.record(); torch.cuda.synchronize()
+    print(f"strip {strip:4d} minb {minb}: {a.elapsed_time(b) / 20 * 1000:.1f} us")
