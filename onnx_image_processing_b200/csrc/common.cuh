@@ -114,7 +114,7 @@ int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const floa
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                              float* desc, void* ws, size_t ws_bytes, cudaStream_t st);
 
-extern int g_tc_allow_scaling;   // sinkhorn_tc.cu; test hook
+extern int g_tc_allow_scaling, g_tc_allow_f16;   // sinkhorn_tc.cu; test hooks
 // tcgen05 / TMEM cluster kernel (sinkhorn_tc.cu); limits: L2 cost, N <= 512, M <= 512, D % 16 == 0
 int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                         float unused, float* P, cudaStream_t st);

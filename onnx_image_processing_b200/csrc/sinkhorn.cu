@@ -490,7 +490,7 @@ int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int 
 }
 
 // 0: tcgen05 cluster kernel (scaling-form loop when safe), 1: FFMA cluster kernel, 2: generic kernels,
-// 3: tcgen05 cluster kernel with the log-domain loop forced
+// 3: tcgen05 cluster kernel with the log-domain loop forced, 4: tcgen05 cluster kernel with the 3xTF32 GEMM forced
 int g_sinkhorn_variant = 0;
 
 }  // namespace
@@ -510,8 +510,9 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
     if (B > 65535) return OM_ERR_LIMIT;
     const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && g_sinkhorn_variant != 2 &&
                       (long long)B * CL < (1ll << 31);
-    if (fast && (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 3)) {
-        g_tc_allow_scaling = g_sinkhorn_variant == 0;
+    if (fast && (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 3 || g_sinkhorn_variant == 4)) {
+        g_tc_allow_scaling = g_sinkhorn_variant != 3;
+        g_tc_allow_f16 = g_sinkhorn_variant != 4;
         return sinkhorn_cluster_tc(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
     }
     if (fast) return sinkhorn_cluster(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);

@@ -17,6 +17,7 @@
 // buffers alias the shared memory that holds the score slab afterwards.
 // Epilogue: tcgen05.ld (one TMEM lane = one column j per thread) -> cost -> base-2 log score -> smem.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -89,6 +90,11 @@ __device__ __forceinline__ void st_async_f32(uint32_t dst_cluster, float v, uint
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster),
                  "r"(__float_as_uint(v)), "r"(bar_cluster) : "memory");
 }
+__device__ __forceinline__ void st_async_f32x4(uint32_t dst_cluster, const float4& v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     dst_cluster), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                 "r"(__float_as_uint(v.w)), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void bar_sweep() { asm volatile("bar.sync 1, %0;" ::"n"(NP) : "memory"); }
 // UMMA shared-memory descriptor, no swizzle, K-major (cute/arch/mma_sm100_desc.hpp layout)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -104,6 +110,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc),
         "r"(IDESC), "r"(accumulate) : "memory");
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, N=64, M=128
+constexpr uint32_t IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc),
+        "r"(IDESC_F16), "r"(accumulate) : "memory");
+}
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi); four values -> 2 x 8 bytes
+__device__ __forceinline__ void split_f16(const float4& v, uint2& hi, uint2& lo) {
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+__device__ __forceinline__ float amax4(const float4& v, float m) {
+    return fmaxf(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))), m);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -150,7 +176,11 @@ struct TcArgs {
     } while (0)
 
 // XD = true: "scaling" form of the same iteration (see the block comment at the XD branch below)
-template <bool XD>
+// F16 = true: operands split into two fp16 terms and multiplied with kind::f16 (K = 16 per MMA) instead of two
+// TF32 terms with kind::tf32 (K = 8): same three products hi*hi + hi*lo + lo*hi, a quarter of the MMA instructions
+// and half the staged bytes.  x = hi + lo holds 22 bits, so the dot products are as accurate as FP32 FFMA.  fp16
+// overflows at 65504: the producers watch max|x| and a CTA that saw |x| >= 60000 recomputes its dots with FFMA.
+template <bool XD, bool F16>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_kernel(TcArgs a) {
     extern __shared__ __align__(128) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -183,8 +213,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         mbar_init(smem_u32(&bars[2]), 1);
         mbar_init(smem_u32(&bars[3]), 1);
         mbar_init(smem_u32(&bars[4]), 1);
-        mbar_init(smem_u32(&bars[5]), NP);
-        mbar_init(smem_u32(&bars[6]), NP);
+        mbar_init(smem_u32(&bars[5]), F16 ? 15 * 32 : NP);        // producers of a stage (F16: warp 15 is the MMA issuer)
+        mbar_init(smem_u32(&bars[6]), F16 ? 15 * 32 : NP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -203,6 +233,121 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         const uint32_t stage0 = smem_u32(sm);
         const float* A = a.d2 + (size_t)z * M * D;                 // MMA "A": 512 rows j of d2
         const float* Bm = a.d1 + ((size_t)z * N + r0) * D;          // MMA "B": this CTA's 64 rows i of d1
+        int overflow = 0;                                           // F16: some |x| >= 60000 seen by this CTA
+        if constexpr (F16) {
+            // ===== fp16 split.  Stage = 32 floats of K (two K=16 MMA steps) =====
+            // Tile layout (bytes): element (row, k) at (k/8)*LBO + row*16 + (k%8)*2 -- the same core-matrix
+            // geometry as the TF32 tiles (8 rows x 16 bytes, LBO between K groups, SBO = 128 between row groups).
+            // Work item = (16-row block, K group of 8): a warp stores 16 rows x 16 bytes = 256 contiguous bytes per
+            // item (conflict-free 8-byte stores) and reads 16 x 32-byte sectors.  144 items per stage (128 of the d2
+            // tile, 16 of the d1 tile) are dealt round-robin to warps 0..14; warp 15 only issues the MMAs, so that
+            // staging stage c+1 and the tensor core working on stage c overlap (the tensor pipe paces at ~2.1k cycles
+            // per stage, a producer warp needs ~1.9k).
+            constexpr int KC2 = 32, NPW = 15, NITEM = 144, IPW = (NITEM + NPW - 1) / NPW;
+            const int nchunks = D / KC2;
+            const int prow = lane >> 1, half = lane & 1;
+            float mx = 0.f;
+            const bool trc = a.trace != nullptr && tid == NPW * 32;
+            long long y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+            if (warp < NPW) {
+                float4 cur[IPW];
+                float acc[IPW];
+                const float* src[IPW];                              // global address of this thread's float4 in chunk 0 (or null)
+                uint32_t dst[IPW];                                  // byte offset of the hi half inside a stage
+#pragma unroll
+                for (int t = 0; t < IPW; ++t) {
+                    const int i = warp + NPW * t;
+                    acc[t] = 0.f;
+                    src[t] = nullptr;
+                    dst[t] = 0;
+                    if (i < 128) {                                  // d2 tile (MMA "A")
+                        const int j = 16 * (i >> 2) + prow, kg = i & 3;
+                        if (j < M) src[t] = A + (size_t)j * D + 8 * kg + 4 * half;
+                        dst[t] = (uint32_t)(kg * A_LBO + j * 16 + half * 8);
+                    } else if (i < NITEM) {                         // d1 tile (MMA "B")
+                        const int r = 16 * ((i - 128) >> 2) + prow, kg = (i - 128) & 3;
+                        if (r < nreal) src[t] = Bm + (size_t)r * D + 8 * kg + 4 * half;
+                        dst[t] = (uint32_t)(2 * A_TILE + kg * B_LBO + r * 16 + half * 8);
+                    }
+                }
+                auto fetch = [&](int c) {
+#pragma unroll
+                    for (int t = 0; t < IPW; ++t)
+                        cur[t] = (src[t] != nullptr && c < nchunks) ? __ldg(reinterpret_cast<const float4*>(src[t] + c * KC2))
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                fetch(0);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int s = c & 1;
+                    if (c >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 done
+                    char* st = reinterpret_cast<char*>(sm) + s * STAGE_BYTES;
+#pragma unroll
+                    for (int t = 0; t < IPW; ++t) {
+                        const int i = warp + NPW * t;
+                        if (i < NITEM) {                            // warp-uniform
+                            uint2 hi, lo;
+                            acc[t] = sq4(cur[t], acc[t]);
+                            mx = amax4(cur[t], mx);
+                            split_f16(cur[t], hi, lo);
+                            *reinterpret_cast<uint2*>(st + dst[t]) = hi;
+                            *reinterpret_cast<uint2*>(st + dst[t] + (i < 128 ? A_TILE : B_TILE)) = lo;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
+                    mbar_arrive(smem_u32(&bars[5 + s]));                            // stage s is full
+                    fetch(c + 1);                                   // lands while the next stage-free wait passes
+                }
+                // squared norms, sinkhorn.py:98-99: the lane pair holds one K group of a row; the 4 K groups of a row sit
+                // in different warps -> partial sums through shared memory (sCW is free now), combined in fixed order
+#pragma unroll
+                for (int t = 0; t < IPW; ++t) {
+                    const int i = warp + NPW * t;
+                    const float v = acc[t] + __shfl_xor_sync(0xffffffffu, acc[t], 1);
+                    if (half == 0 && i < 128) sCW[(i & 3) * MAXM + 16 * (i >> 2) + prow] = v;
+                    else if (half == 0 && i < NITEM) sCW[4 * MAXM + ((i - 128) & 3) * B_ROWS + 16 * ((i - 128) >> 2) + prow] = v;
+                }
+            } else if (lane == 0) {
+                // ===== MMA issuer (warp 15): wait until the producers have stored chunk c, then drive the tensor core =====
+                for (int c = 0; c < nchunks; ++c) {
+                    const int s = c & 1;
+                    const long long c2 = trc ? clock64() : 0;
+                    mbar_wait(smem_u32(&bars[5 + s]), (uint32_t)((c >> 1) & 1));
+                    const long long c3 = trc ? clock64() : 0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = stage0 + s * STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < KC2 / 16; ++ks) {
+                        const uint64_t bhi = umma_desc(sa + 2 * A_TILE + 2 * ks * B_LBO, B_LBO, SBO);
+                        const uint64_t blo = umma_desc(sa + 2 * A_TILE + B_TILE + 2 * ks * B_LBO, B_LBO, SBO);
+#pragma unroll
+                        for (int mb = 0; mb < 4; ++mb) {
+                            const uint64_t ahi = umma_desc(sa + 2 * ks * A_LBO + mb * 128 * 16, A_LBO, SBO);
+                            const uint64_t alo = umma_desc(sa + A_TILE + 2 * ks * A_LBO + mb * 128 * 16, A_LBO, SBO);
+                            const uint32_t d = tmem_base + mb * 64;
+                            umma_f16(d, ahi, bhi, (c | ks) != 0);
+                            umma_f16(d, ahi, blo, 1u);
+                            umma_f16(d, alo, bhi, 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&bars[s]));                    // frees stage s when these MMAs retire
+                    if (c == nchunks - 1) umma_commit(smem_u32(&bars[2]));
+                    if (trc) { y2 += c3 - c2; y3 += clock64() - c3; }
+                }
+                if (trc) {
+                    long long* y = a.trace + (size_t)gridDim.x * 12 + (size_t)blockIdx.x * 4;
+                    y[0] = y0; y[1] = y1; y[2] = y2; y[3] = y3;
+                }
+            }
+            __syncwarp();
+            overflow = __syncthreads_or(mx >= 60000.0f ? 1 : 0);
+            for (int r = tid; r < MAXM + B_ROWS; r += NT) {
+                if (r < MAXM) sN2[r] = (sCW[r] + sCW[MAXM + r]) + (sCW[2 * MAXM + r] + sCW[3 * MAXM + r]);
+                else {
+                    const float* q = sCW + 4 * MAXM + (r - MAXM);
+                    sN1[r - MAXM] = (q[0] + q[B_ROWS]) + (q[2 * B_ROWS] + q[3 * B_ROWS]);
+                }
+            }
+        } else {
         const int lrow = tid >> 2, lkq = tid & 3;                   // loader: row (+128q), 16-byte K unit
         float nb[4] = {0.f, 0.f, 0.f, 0.f}, na = 0.f;
         const int nchunks = D / KC;
@@ -291,6 +436,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         na += __shfl_xor_sync(0xffffffffu, na, 2);
         if (lkq == 0 && tid < 4 * B_ROWS) sN1[lrow] = na;
 
+        }
         OM_STAMP(1);                                                // all chunks staged, last MMAs in flight
         mbar_wait(smem_u32(&bars[2]), 0u);                          // every MMA has completed
         OM_STAMP(2);
@@ -313,6 +459,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     const float cost = fmaxf(__fsub_rn(__fadd_rn(sN1[li], n2j), __fmul_rn(2.0f, dot)), 0.0f);   // :98-103
                     sS[li * SPITCH + j] = __fmul_rn(-cost, a.scale2);
                 }
+            }
+        }
+        if (F16 && overflow) {                                      // out of fp16 range: plain FP32 dot products (slow, rare)
+            for (int li = 0; li < nreal; ++li) {
+                const float* x = Bm + (size_t)li * D;
+                const float* y = A + (size_t)min(j, M - 1) * D;
+                float dot = 0.0f;
+                for (int k = 0; k < D; ++k) dot = fmaf(__ldg(x + k), __ldg(y + k), dot);
+                const float cost = fmaxf(__fsub_rn(__fadd_rn(sN1[li], n2j), __fmul_rn(2.0f, dot)), 0.0f);
+                sS[li * SPITCH + j] = __fmul_rn(-cost, a.scale2);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -351,7 +507,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         const float kd = ex2(a.dustbin2);
         const float Mf = (float)M, Nf = (float)N;
         __syncthreads();                         // score slab complete
-        float kreg[4][16];
+        // K as pairs: kreg[rr][2k], kreg[rr][2k+1] = columns 128k+4l+{0,1}, 128k+4l+{2,3} of row 4w+rr
+        float2 kreg[4][8];
         if (warp < NW) {
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
@@ -361,10 +518,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     const int c0 = 128 * k + 4 * lane;
                     const float4 s4 = *reinterpret_cast<const float4*>(sS + li * SPITCH + c0);
                     const bool rv = li < nreal;
-                    kreg[rr][4 * k + 0] = (rv && c0 + 0 < M) ? ex2(s4.x) : 0.0f;
-                    kreg[rr][4 * k + 1] = (rv && c0 + 1 < M) ? ex2(s4.y) : 0.0f;
-                    kreg[rr][4 * k + 2] = (rv && c0 + 2 < M) ? ex2(s4.z) : 0.0f;
-                    kreg[rr][4 * k + 3] = (rv && c0 + 3 < M) ? ex2(s4.w) : 0.0f;
+                    kreg[rr][2 * k].x = (rv && c0 + 0 < M) ? ex2(s4.x) : 0.0f;
+                    kreg[rr][2 * k].y = (rv && c0 + 1 < M) ? ex2(s4.y) : 0.0f;
+                    kreg[rr][2 * k + 1].x = (rv && c0 + 2 < M) ? ex2(s4.z) : 0.0f;
+                    kreg[rr][2 * k + 1].y = (rv && c0 + 3 < M) ? ex2(s4.w) : 0.0f;
                 }
             }
         }
@@ -378,35 +535,40 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         cluster.sync();      // every CTA is past its GEMM (staging aliased these buffers) and has initialised its barriers
         OM_STAMP(4);
 
-        float breg[16], bM = 1.0f, areg[4] = {0.f, 0.f, 0.f, 0.f}, aN = 0.0f;
+        float2 breg[8];
+        float bM = 1.0f, areg[4] = {0.f, 0.f, 0.f, 0.f}, aN = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) breg[c] = (128 * (c >> 2) + 4 * lane + (c & 3)) < M ? 1.0f : 0.0f;
+        for (int c = 0; c < 8; ++c) {
+            const int col = 128 * (c >> 1) + 4 * lane + 2 * (c & 1);
+            breg[c] = make_float2(col < M ? 1.0f : 0.0f, col + 1 < M ? 1.0f : 0.0f);
+        }
+        const bool trx = a.trace != nullptr && tid == 0;
+        long long x0 = 0, x1 = 0, x2 = 0, x3 = 0;
         if (warp < NW) {
             for (int it = 0; it < a.iterations; ++it) {
                 const uint32_t par = (uint32_t)(it & 1);
+                const long long i0 = trx ? clock64() : 0;
                 if (tid == 0) {
                     mbar_arrive_expect_tx(smem_u32(&bars[3]), part_bytes);
                     mbar_arrive_expect_tx(smem_u32(&bars[4]), b_bytes);
                 }
                 // ---- a_i = mu_i / rowsum_i --------------------------------------------------------------
-                float rs[4], sb = 0.0f;
+                // (packed fma.rn.f32x2 was measured slower than scalar FFMA here: 1578 vs 1424 cycles per sweep)
+                float rs[4];
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     float e0 = 0.0f, e1 = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 16; c += 2) {
-                        e0 = fmaf(kreg[rr][c], breg[c], e0);
-                        e1 = fmaf(kreg[rr][c + 1], breg[c + 1], e1);
+                    for (int c = 0; c < 8; ++c) {
+                        e0 = fmaf(kreg[rr][c].x, breg[c].x, e0);
+                        e1 = fmaf(kreg[rr][c].y, breg[c].y, e1);
                     }
                     rs[rr] = e0 + e1;
                 }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) sb += breg[c];
-#pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) rs[rr] += __shfl_xor_sync(0xffffffffu, rs[rr], o);
-                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
                 }
                 float asum = 0.0f;
 #pragma unroll
@@ -414,29 +576,37 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     areg[rr] = (4 * warp + rr < nreal) ? __fdividef(1.0f, fmaf(kd, bM, rs[rr])) : 0.0f;
                     asum += areg[rr];
                 }
-                aN = __fdividef(Mf, kd * (sb + bM));                   // dustbin row: mu_N = M (sinkhorn.py:197-198)
+                if (warp < 3 || it == a.iterations - 1) {              // only the owner threads (tid <= 64) and the final P need a_N
+                    float sb = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) sb += breg[c].x + breg[c].y;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    aN = __fdividef(Mf, kd * (sb + bM));               // dustbin row: mu_N = M (sinkhorn.py:197-198)
+                }
                 // ---- column sums: warp partials -> CTA partials -> owners -------------------------------
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float4 t4;
-                    t4.x = fmaf(kreg[3][4 * k + 0], areg[3], fmaf(kreg[2][4 * k + 0], areg[2], fmaf(kreg[1][4 * k + 0], areg[1], kreg[0][4 * k + 0] * areg[0])));
-                    t4.y = fmaf(kreg[3][4 * k + 1], areg[3], fmaf(kreg[2][4 * k + 1], areg[2], fmaf(kreg[1][4 * k + 1], areg[1], kreg[0][4 * k + 1] * areg[0])));
-                    t4.z = fmaf(kreg[3][4 * k + 2], areg[3], fmaf(kreg[2][4 * k + 2], areg[2], fmaf(kreg[1][4 * k + 2], areg[1], kreg[0][4 * k + 2] * areg[0])));
-                    t4.w = fmaf(kreg[3][4 * k + 3], areg[3], fmaf(kreg[2][4 * k + 3], areg[2], fmaf(kreg[1][4 * k + 3], areg[1], kreg[0][4 * k + 3] * areg[0])));
+                    t4.x = fmaf(kreg[3][2 * k].x, areg[3], fmaf(kreg[2][2 * k].x, areg[2], fmaf(kreg[1][2 * k].x, areg[1], kreg[0][2 * k].x * areg[0])));
+                    t4.y = fmaf(kreg[3][2 * k].y, areg[3], fmaf(kreg[2][2 * k].y, areg[2], fmaf(kreg[1][2 * k].y, areg[1], kreg[0][2 * k].y * areg[0])));
+                    t4.z = fmaf(kreg[3][2 * k + 1].x, areg[3], fmaf(kreg[2][2 * k + 1].x, areg[2], fmaf(kreg[1][2 * k + 1].x, areg[1], kreg[0][2 * k + 1].x * areg[0])));
+                    t4.w = fmaf(kreg[3][2 * k + 1].y, areg[3], fmaf(kreg[2][2 * k + 1].y, areg[2], fmaf(kreg[1][2 * k + 1].y, areg[1], kreg[0][2 * k + 1].y * areg[0])));
                     *reinterpret_cast<float4*>(sCW + warp * MAXM + 128 * k + 4 * lane) = t4;
                 }
                 if (lane == 0) sAs[warp] = asum;
+                const long long i1 = trx ? clock64() : 0;
                 bar_sweep();
-                {
+                {   // one column per thread: CTA partial -> the column's owner (measured faster than 128 threads x float4)
                     float s0 = sCW[tid], s1 = sCW[MAXM + tid], s2 = sCW[2 * MAXM + tid], s3 = sCW[3 * MAXM + tid];
 #pragma unroll
                     for (int w = 4; w < NW; w += 4) {
                         s0 += sCW[w * MAXM + tid]; s1 += sCW[(w + 1) * MAXM + tid];
                         s2 += sCW[(w + 2) * MAXM + tid]; s3 += sCW[(w + 3) * MAXM + tid];
                     }
-                    const int owner = tid >> 6;
-                    st_async_f32(mapa_u32(my_part + (uint32_t)(tid & 63) * 4u, (uint32_t)owner), (s0 + s1) + (s2 + s3),
-                                 mapa_u32(loc_bar_part, (uint32_t)owner));
+                    const uint32_t owner = (uint32_t)tid >> 6;
+                    st_async_f32(mapa_u32(my_part + (uint32_t)(tid & 63) * 4u, owner), (s0 + s1) + (s2 + s3),
+                                 mapa_u32(loc_bar_part, owner));
                     if (tid == 0) {
                         float as = 0.0f;
 #pragma unroll
@@ -445,6 +615,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     }
                 }
                 // ---- owners: b_j = nu_j / colsum_j, sent to every CTA -----------------------------------
+                const long long i2 = trx ? clock64() : 0;
                 mbar_wait(smem_u32(&bars[3]), par);
                 if (tid < 64 || (tid == 64 && has_dust)) {
                     float t = 0.0f;
@@ -458,16 +629,23 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     for (int dst = 0; dst < CL; ++dst)
                         st_async_f32(mapa_u32(loc_b + slot, (uint32_t)dst), bnew, mapa_u32(loc_bar_b, (uint32_t)dst));
                 }
+                const long long i3 = trx ? clock64() : 0;
                 mbar_wait(smem_u32(&bars[4]), par);
+                if (trx) { x0 += i1 - i0; x1 += i2 - i1; x2 += i3 - i2; x3 += clock64() - i3; }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float4 b4 = *reinterpret_cast<const float4*>(sB + 128 * k + 4 * lane);
-                    breg[4 * k + 0] = b4.x; breg[4 * k + 1] = b4.y; breg[4 * k + 2] = b4.z; breg[4 * k + 3] = b4.w;
+                    breg[2 * k] = make_float2(b4.x, b4.y);
+                    breg[2 * k + 1] = make_float2(b4.z, b4.w);
                 }
                 bM = sB[MAXM];
             }
         }
         OM_STAMP(5);
+        if (trx) {
+            long long* x = a.trace + (size_t)gridDim.x * 8 + (size_t)blockIdx.x * 4;
+            x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;
+        }
         // ---------------- P = a_i K_ij b_j (sinkhorn.py:145, :206) -----------------------------------------
         float* Pz = a.P + (size_t)z * (N + 1) * (M + 1);
         if (warp < NW) {
@@ -479,10 +657,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float4 p4;
-                        p4.x = areg[rr] * kreg[rr][4 * k + 0] * breg[4 * k + 0];
-                        p4.y = areg[rr] * kreg[rr][4 * k + 1] * breg[4 * k + 1];
-                        p4.z = areg[rr] * kreg[rr][4 * k + 2] * breg[4 * k + 2];
-                        p4.w = areg[rr] * kreg[rr][4 * k + 3] * breg[4 * k + 3];
+                        p4.x = areg[rr] * kreg[rr][2 * k].x * breg[2 * k].x;
+                        p4.y = areg[rr] * kreg[rr][2 * k].y * breg[2 * k].y;
+                        p4.z = areg[rr] * kreg[rr][2 * k + 1].x * breg[2 * k + 1].x;
+                        p4.w = areg[rr] * kreg[rr][2 * k + 1].y * breg[2 * k + 1].y;
                         *reinterpret_cast<float4*>(stage + 128 * k + 4 * lane) = p4;
                     }
                     __syncwarp();
@@ -645,6 +823,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
 }  // namespace
 
 int g_tc_allow_scaling = 1;         // test hook: 0 forces the log-domain loop of the tcgen05 kernel
+int g_tc_allow_f16 = 1;             // test hook: 0 forces the 3xTF32 similarity GEMM
 long long* g_tc_trace = nullptr;   // debug: device buffer of B*8 CTAs x 8 stamps, set through om_debug_sinkhorn_trace
 
 int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
@@ -659,12 +838,19 @@ int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, i
     // scaling form (no exponentials in the loop) while exp(-unused/eps) stays far from underflow (2^-60);
     // beyond that the log-domain loop with its max-shift fallback keeps every sum finite
     const bool scaling = g_tc_allow_scaling && (double)unused / (double)eps * log2e <= 60.0 && unused >= 0.0f;
-    if (scaling) {
-        OM_TRY(set_smem(sinkhorn_tc_kernel<true>, smem));
-        sinkhorn_tc_kernel<true><<<B * CL, NT, smem, st>>>(a);
+    const bool f16 = g_tc_allow_f16 && D % 32 == 0;
+    if (scaling && f16) {
+        OM_TRY(set_smem((sinkhorn_tc_kernel<true, true>), smem));
+        sinkhorn_tc_kernel<true, true><<<B * CL, NT, smem, st>>>(a);
+    } else if (scaling) {
+        OM_TRY(set_smem((sinkhorn_tc_kernel<true, false>), smem));
+        sinkhorn_tc_kernel<true, false><<<B * CL, NT, smem, st>>>(a);
+    } else if (f16) {
+        OM_TRY(set_smem((sinkhorn_tc_kernel<false, true>), smem));
+        sinkhorn_tc_kernel<false, true><<<B * CL, NT, smem, st>>>(a);
     } else {
-        OM_TRY(set_smem(sinkhorn_tc_kernel<false>, smem));
-        sinkhorn_tc_kernel<false><<<B * CL, NT, smem, st>>>(a);
+        OM_TRY(set_smem((sinkhorn_tc_kernel<false, false>), smem));
+        sinkhorn_tc_kernel<false, false><<<B * CL, NT, smem, st>>>(a);
     }
     OM_AFTER_LAUNCH();
     return OM_OK;

@@ -200,7 +200,7 @@ def test_gather_functions():
 # ------------------------------------------------------------------------------------------
 # Sinkhorn
 # ------------------------------------------------------------------------------------------
-VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log"}
+VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32"}
 
 
 def _with_variant(variant, fn):
@@ -213,7 +213,7 @@ def _with_variant(variant, fn):
 
 
 @pytest.mark.parametrize("name", G.names("sinkhorn"))
-@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=lambda v: VARIANTS[v])
 def test_sinkhorn_golden(name, variant):
     g = G.load(name)
     got = _with_variant(variant, lambda: om.SinkhornMatcher(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"])))
@@ -223,7 +223,7 @@ def test_sinkhorn_golden(name, variant):
     assert m64["core"] <= PR.PROB_TOL, m64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4], ids=lambda v: VARIANTS[v])
 @pytest.mark.parametrize("N,M,eps,unused", [(512, 512, 1.0, 1.0), (512, 512, 0.05, 1.0), (300, 512, 0.1, 0.5),
                                             (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0),
                                             (509, 511, 0.03, 1.0), (512, 512, 0.2, 0.0)])
@@ -249,10 +249,22 @@ def test_sinkhorn_variants_agree_on_matched_descriptors():
     d1 = torch.nn.functional.normalize(torch.randn(3, 512, 256, generator=g), dim=-1)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(512, generator=g)] + 0.02 * torch.randn(3, 512, 256, generator=g), dim=-1)
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.05, 1.0).float()
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         got = _with_variant(variant, lambda: om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2)))
         m = PR.prob_metrics(got, ref)
         assert PR.probs_ok(m), (VARIANTS[variant], m)
+
+
+def test_sinkhorn_descriptors_beyond_fp16_range():
+    """|x| > 65504 cannot be split into fp16 terms: the kernel must notice and fall back to FP32 dot products."""
+    g = torch.Generator().manual_seed(5)
+    d1 = torch.nn.functional.normalize(torch.randn(2, 200, 256, generator=g), dim=-1)
+    d2 = torch.nn.functional.normalize(d1[:, torch.randperm(200, generator=g)] + 0.2 * torch.randn(2, 200, 256, generator=g), dim=-1)
+    scale = 3.0e6                                        # largest entries ~ 3e6 * 0.2
+    eps, unused = 0.5 * scale * scale, scale * scale     # the same problem as unit descriptors at eps 0.5, unused 1
+    ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.5, 1.0).float()
+    got = om.SinkhornMatcher(20, eps, unused).to(DEV)(*_cuda(d1 * scale, d2 * scale))
+    assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
 
 
 def test_sinkhorn_large_k_generic_path():

@@ -20,15 +20,14 @@ torch.cuda.synchronize()
 nat.lib().om_debug_sinkhorn_trace(ctypes.c_void_p(0))
 t = buf[:B * 64].view(B * 8, 8).cpu().double()
 x = buf[B * 64:B * 96].view(B * 8, 4).cpu().double() / 20.0
-y = buf[B * 96:].view(B * 8, 4).cpu().double() / 16.0
+y = buf[B * 96:].view(B * 8, 4).cpu().double() / 8.0
 names = ["staging loop (16 chunks)", "wait last MMAs", "epilogue TMEM->smem", "init u,v + cluster.sync", "20 iterations", "write P"]
 for i, n in enumerate(names):
     d = t[:, i + 1] - t[:, i]
     print(f"{n:28s} mean {d.mean():9.0f} cyc  min {d.min():9.0f}  max {d.max():9.0f}")
 print(f"{'  of which waiting partials':28s} mean {t[:, 7].mean():9.0f} cyc  min {t[:,7].min():9.0f} max {t[:,7].max():9.0f}")
 print(f"{'total':28s} mean {(t[:, 6] - t[:, 0]).mean():9.0f} cyc")
-for i, n in enumerate(["sweep (thread 0 view)", "sync+reduce+push", "v update + reload"]):
+for i, n in enumerate(["sweep (thread 0 view)", "barrier+reduce+send", "wait partials", "owner + wait b"]):
     print(f"  per iteration {n:24s} mean {x[:, i].mean():8.0f} cyc  min {x[:, i].min():8.0f}  max {x[:, i].max():8.0f}")
-print(f"  per iteration wait partials            mean {t[:, 7].mean() / 20:8.0f} cyc")
-for i, n in enumerate(["wait stage free", "split + store + fence", "__syncthreads", "MMA issue (thread 0)"]):
+for i, n in enumerate(["wait stage free", "split + store + arrive + fetch", "wait stage full", "MMA issue (thread 0)"]):
     print(f"  per chunk (thread 0) {n:24s} mean {y[:, i].mean():8.0f} cyc  min {y[:, i].min():8.0f}  max {y[:, i].max():8.0f}")
