@@ -270,21 +270,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                         dst[t] = (uint32_t)(2 * A_TILE + kg * B_LBO + r * 16 + half * 8);
                     }
                 }
-                auto fetch = [&](int c) {
+                // items are handled in two halves: as soon as a half is staged its registers are refilled with the next
+                // chunk, so those loads are in flight while the other half is being staged (no second register set)
+                constexpr int HALF = IPW / 2;
+                auto fetch = [&](int c, int t0, int t1) {
 #pragma unroll
                     for (int t = 0; t < IPW; ++t)
-                        cur[t] = (src[t] != nullptr && c < nchunks) ? __ldg(reinterpret_cast<const float4*>(src[t] + c * KC2))
-                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t >= t0 && t < t1)
+                            cur[t] = (src[t] != nullptr && c < nchunks) ? __ldg(reinterpret_cast<const float4*>(src[t] + c * KC2))
+                                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 };
-                fetch(0);
-                for (int c = 0; c < nchunks; ++c) {
-                    const int s = c & 1;
-                    if (c >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 done
-                    char* st = reinterpret_cast<char*>(sm) + s * STAGE_BYTES;
+                auto stage = [&](char* st, int t0, int t1) {
 #pragma unroll
                     for (int t = 0; t < IPW; ++t) {
                         const int i = warp + NPW * t;
-                        if (i < NITEM) {                            // warp-uniform
+                        if (t >= t0 && t < t1 && i < NITEM) {       // warp-uniform
                             uint2 hi, lo;
                             acc[t] = sq4(cur[t], acc[t]);
                             mx = amax4(cur[t], mx);
@@ -293,9 +293,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                             *reinterpret_cast<uint2*>(st + dst[t] + (i < 128 ? A_TILE : B_TILE)) = lo;
                         }
                     }
+                };
+                fetch(0, 0, IPW);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int s = c & 1;
+                    if (c >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 done
+                    char* st = reinterpret_cast<char*>(sm) + s * STAGE_BYTES;
+                    stage(st, 0, HALF);
+                    fetch(c + 1, 0, HALF);
+                    stage(st, HALF, IPW);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
                     mbar_arrive(smem_u32(&bars[5 + s]));                            // stage s is full
-                    fetch(c + 1);                                   // lands while the next stage-free wait passes
+                    fetch(c + 1, HALF, IPW);
                 }
                 // squared norms, sinkhorn.py:98-99: the lane pair holds one K group of a row; the 4 K groups of a row sit
                 // in different warps -> partial sums through shared memory (sCW is free now), combined in fixed order
