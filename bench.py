@@ -22,7 +22,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -109,37 +108,55 @@ def run_reference(args, rank: int):
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons through NVML (in-process: an nvidia-smi child starting up stalls driver calls
+    for ~1 s, and a polling thread was seen to stall kernel launches).  NVML is initialised before the timed
+    region; sample() is called from the main thread after all timed steps have been enqueued, while the GPU is
+    still executing them."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.rows, self.h, self.nv, self.max_sm, self.err = [], None, None, None, ""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def sample(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.rows.append((sm, fn(self.h), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+    def sample_until(self, event, max_samples: int = 40, period_s: float = 0.004):
+        """Sample while `event` (recorded after the last timed step) has not completed."""
+        for _ in range(max_samples):
+            if event.query():
+                break
+            self.sample()
+            time.sleep(period_s)
+
+    def result(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = [r[0] for r in self.rows]
+        reasons = [n for n, bit in names.items() if any(r[1] & bit for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max((r[2] for r in self.rows), default=None),
+                "how": "NVML, sampled while the queued timed steps were executing"}
 
 
 def event_time_ms(fn, steps: int, warmup: int, stream) -> float:
@@ -261,43 +278,63 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         return float(t.item())
 
     # ---- device-resident throughput ----------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             model(d1, d2)
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         n0 = nat.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
             out = model(d1, d2)
         e1.record(stream)
+        if rank == 0:
+            sampler.sample_until(e1)             # the GPU is still working through the queued steps
         barrier()
         launches = nat.launch_count() - n0
         ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.result() if rank == 0 else None
     value = world * B / (ms_step * 1e-3)
 
     # ---- end to end through the host API -----------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        hb = HostBatchMatcher(model, chunk=max(1, min(16, B // 4 or 1)), n_streams=3)
-        for _ in range(2):
-            hb(h1, h2)
+    def time_e2e(a1, a2, join):
+        hb = HostBatchMatcher(model, chunk=max(1, min(8, B // 4 or 1)), n_streams=4, depth=2, join=join)
+        for _ in range(3):
+            hb(a1, a2)
+        hb.synchronize()
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record(stream)
         for _ in range(args.steps):
-            res = hb(h1, h2)
+            res = hb(a1, a2)
+        if not join:
+            for s in hb.streams:                 # the timed region ends when every step's D2H has landed
+                stream.wait_stream(s)
         t1.record(stream)
         barrier()
-        ms_e2e = max_over_ranks(t0.elapsed_time(t1) / args.steps)
+        return max_over_ranks(t0.elapsed_time(t1) / args.steps), res
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, res = time_e2e(h1, h2, join=False)
+        ms_join, _ = time_e2e(h1, h2, join=True)
+        u1, u2 = h1.to(torch.uint8).pin_memory(), h2.to(torch.uint8).pin_memory()
+        ms_u8, res8 = time_e2e(u1, u2, join=False)
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "pairs/s",
                "h2d_bytes_per_step": 2 * B * H * W * 4,
                "d2h_bytes_per_step": B * (2 * K * 2 * 4 + (K + 1) * (K + 1) * 4),
-               "ms_per_step": ms_e2e, "api": "HostBatchMatcher(model)(image1_host, image2_host)",
+               "ms_per_step": ms_e2e,
+               "api": "HostBatchMatcher(model, chunk=8, n_streams=4, depth=2, join=False)(image1_host_f32, image2_host_f32)",
+               "note": "float32 pinned host images in, pinned host (kpts1, kpts2, P) out; consecutive steps overlap "
+                       "(two result sets); every step's H2D and D2H complete inside the timed region",
+               "serialized_steps": {"value": world * B / (ms_join * 1e-3), "ms_per_step": ms_join,
+                                    "note": "join=True: each call is joined to the current stream before the next starts"},
+               "uint8_host_images": {"value": world * B / (ms_u8 * 1e-3), "ms_per_step": ms_u8,
+                                     "h2d_bytes_per_step": 2 * B * H * W,
+                                     "note": "same pixels as uint8 (exact widening on the device); an extension, the "
+                                             "reference's callers pass float32",
+                                     "checksum": float(res8[2][0, :K, :K].sum())},
                "checksum": float(res[2][0, :K, :K].sum())}
 
     # ---- per-kernel times and roofline (rank 0) ------------------------------------------------

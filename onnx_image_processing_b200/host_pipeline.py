@@ -38,23 +38,44 @@ class HostBatchMatcher:
     The batch is cut into chunks; chunk c uses stream c % n_streams, so the H2D copy of one chunk,
     the kernels of the previous one and the D2H copy of the one before overlap.  Inputs should be
     pinned (they are pinned on first use otherwise); outputs are pinned host tensors.
+
+    ``depth`` result sets are kept (default 2) and calls rotate through them, so consecutive calls
+    overlap as well: call k+1 may start copying in while call k is still copying out.  With
+    ``join=True`` (default) the caller's current stream waits for the whole call, i.e. the usual
+    torch semantics (results are valid once the current stream is synchronised); with ``join=False``
+    nothing waits -- call :meth:`synchronize` (or wait on the returned tensors' producer streams)
+    before reading results; a result set is overwritten ``depth`` calls later.
+
+    uint8 host images are accepted (4x less PCIe traffic): they are widened to float32 on the device,
+    which is exact, so results are identical to passing the same values as float32.
     """
 
-    def __init__(self, model: torch.nn.Module, chunk: int = 16, n_streams: int = 3, device=None):
+    def __init__(self, model: torch.nn.Module, chunk: int = 8, n_streams: int = 4, device=None, depth: int = 2,
+                 join: bool = True):
         self.model = model
         self.chunk = int(chunk)
+        self.depth = max(1, int(depth))
+        self.join = bool(join)
         self.device = torch.device(device) if device is not None else next(model.buffers()).device
         if self.device.type != "cuda":
             raise RuntimeError("HostBatchMatcher needs the model on a CUDA device (no CPU path)")
         self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
-        self._out = None
+        self._out = [None] * self.depth
+        self._calls = 0
 
     def _outputs(self, B: int, K: int):
-        if self._out is None or self._out[0].shape[0] != B or self._out[0].shape[1] != K:
-            self._out = (torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
-                         torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
-                         torch.empty((B, K + 1, K + 1), dtype=torch.float32).pin_memory())
-        return self._out
+        slot = self._calls % self.depth
+        cur = self._out[slot]
+        if cur is None or cur[0].shape[0] != B or cur[0].shape[1] != K:
+            cur = (torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
+                   torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
+                   torch.empty((B, K + 1, K + 1), dtype=torch.float32).pin_memory())
+            self._out[slot] = cur
+        return cur
+
+    def synchronize(self) -> None:
+        for s in self.streams:
+            s.synchronize()
 
     @torch.no_grad()
     def __call__(self, image1: torch.Tensor, image2: torch.Tensor):
@@ -67,19 +88,24 @@ class HostBatchMatcher:
         B = image1.shape[0]
         K = int(self.model.max_keypoints)
         o1, o2, op = self._outputs(B, K)
+        self._calls += 1
         cur = torch.cuda.current_stream(self.device)
-        for s in self.streams:
-            s.wait_stream(cur)
+        if self.join:
+            for s in self.streams:
+                s.wait_stream(cur)
         for ci, lo in enumerate(range(0, B, self.chunk)):
             hi = min(lo + self.chunk, B)
             s = self.streams[ci % len(self.streams)]
             with torch.cuda.stream(s):
                 d1 = image1[lo:hi].to(self.device, non_blocking=True)
                 d2 = image2[lo:hi].to(self.device, non_blocking=True)
+                if d1.dtype != torch.float32:
+                    d1, d2 = d1.float(), d2.float()
                 k1, k2, p = self.model(d1, d2)
                 o1[lo:hi].copy_(k1, non_blocking=True)
                 o2[lo:hi].copy_(k2, non_blocking=True)
                 op[lo:hi].copy_(p, non_blocking=True)
-        for s in self.streams:
-            cur.wait_stream(s)
+        if self.join:
+            for s in self.streams:
+                cur.wait_stream(s)
         return o1, o2, op
