@@ -293,7 +293,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             sampler.sample_until(e1)             # the GPU is still working through the queued steps
         barrier()
         launches = nat.launch_count() - n0
-        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        ms_local = e0.elapsed_time(e1) / args.steps
+        ms_step = max_over_ranks(ms_local)
+        ms_ranks = [ms_local]
+        if world > 1:
+            tl = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(tl, torch.tensor([ms_local], device=dev, dtype=torch.float64))
+            ms_ranks = [float(t.item()) for t in tl]
         clocks = sampler.result() if rank == 0 else None
     value = world * B / (ms_step * 1e-3)
 
@@ -384,7 +390,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_ranks": ms_ranks,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "image": [H, W], "k": K, "num_pairs": P,
                        "pairs_per_gpu_per_step": B, "sinkhorn_iterations": model.matcher.iterations,
