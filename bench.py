@@ -121,6 +121,8 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.sample()                        # the FIRST call of each NVML query takes 3-14 ms (measured, tools/nvml_cost.py)
+            self.rows.clear()                    # and would land inside the timed region otherwise; later calls take ~10 us
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
             self.h = None
@@ -136,13 +138,19 @@ class ClockSampler:
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
 
-    def sample_until(self, event, max_samples: int = 40, period_s: float = 0.004):
-        """Sample while `event` (recorded after the last timed step) has not completed."""
+    def sample_during(self, event, expected_s: float, max_samples: int = 24):
+        """Samples spread over the queued timed steps (the GPU is executing them while the host waits here)."""
+        if os.environ.get("OM_BENCH_NO_NVML") or self.h is None:
+            return
+        period = max(0.002, expected_s / (max_samples + 1))
         for _ in range(max_samples):
+            time.sleep(period)
             if event.query():
                 break
             self.sample()
-            time.sleep(period_s)
+        if not self.rows:                        # region shorter than one period: sample right behind it
+            self.sample()
+            self.after = True
 
     def result(self):
         if self.h is None:
@@ -156,7 +164,9 @@ class ClockSampler:
         reasons = [n for n, bit in names.items() if any(r[1] & bit for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
                 "samples": len(sm), "power_w_max": max((r[2] for r in self.rows), default=None),
-                "how": "NVML, sampled while the queued timed steps were executing"}
+                "how": "NVML from the main thread, " + ("right after the timed steps (shorter than one sampling period)"
+                                                         if getattr(self, "after", False) else
+                                                         "while the queued timed steps were executing")}
 
 
 def event_time_ms(fn, steps: int, warmup: int, stream) -> float:
@@ -280,9 +290,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- device-resident throughput ----------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 3) - 1):
             model(d1, d2)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        model(d1, d2)                            # last warm-up step, timed to know how long the timed region will be
+        w1.record(stream)
         barrier()
+        est_s = w0.elapsed_time(w1) * 1e-3 * args.steps
         n0 = nat.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -290,7 +305,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             out = model(d1, d2)
         e1.record(stream)
         if rank == 0:
-            sampler.sample_until(e1)             # the GPU is still working through the queued steps
+            sampler.sample_during(e1, est_s)     # the GPU is still working through the queued steps
         barrier()
         launches = nat.launch_count() - n0
         ms_local = e0.elapsed_time(e1) / args.steps
