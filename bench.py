@@ -319,8 +319,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     value = world * B / (ms_step * 1e-3)
 
     # ---- end to end through the host API -----------------------------------------------------
-    def time_e2e(a1, a2, join):
-        hb = HostBatchMatcher(model, chunk=max(1, min(8, B // 4 or 1)), n_streams=4, depth=2, join=join)
+    def time_e2e(a1, a2, join, chunk):
+        hb = HostBatchMatcher(model, chunk=max(1, min(chunk, B)), n_streams=4, depth=2, join=join)
         for _ in range(3):
             hb(a1, a2)
         hb.synchronize()
@@ -338,15 +338,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     e2e = None
     if not args.no_e2e:
-        ms_e2e, res = time_e2e(h1, h2, join=False)
-        ms_join, _ = time_e2e(h1, h2, join=True)
+        # chunk sizes from tools/e2e_sweep.py: float32 input is PCIe-bound (fewer, larger copies win), uint8 is not
+        ms_e2e, res = time_e2e(h1, h2, join=False, chunk=32)
+        ms_join, _ = time_e2e(h1, h2, join=True, chunk=32)
         u1, u2 = h1.to(torch.uint8).pin_memory(), h2.to(torch.uint8).pin_memory()
-        ms_u8, res8 = time_e2e(u1, u2, join=False)
+        ms_u8, res8 = time_e2e(u1, u2, join=False, chunk=16)
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "pairs/s",
                "h2d_bytes_per_step": 2 * B * H * W * 4,
                "d2h_bytes_per_step": B * (2 * K * 2 * 4 + (K + 1) * (K + 1) * 4),
                "ms_per_step": ms_e2e,
-               "api": "HostBatchMatcher(model, chunk=8, n_streams=4, depth=2, join=False)(image1_host_f32, image2_host_f32)",
+               "api": "HostBatchMatcher(model, chunk=32, n_streams=4, depth=2, join=False)(image1_host_f32, image2_host_f32)",
                "note": "float32 pinned host images in, pinned host (kpts1, kpts2, P) out; consecutive steps overlap "
                        "(two result sets); every step's H2D and D2H complete inside the timed region",
                "serialized_steps": {"value": world * B / (ms_join * 1e-3), "ms_per_step": ms_join,

@@ -50,7 +50,7 @@ class HostBatchMatcher:
     which is exact, so results are identical to passing the same values as float32.
     """
 
-    def __init__(self, model: torch.nn.Module, chunk: int = 8, n_streams: int = 4, device=None, depth: int = 2,
+    def __init__(self, model: torch.nn.Module, chunk: int = 16, n_streams: int = 4, device=None, depth: int = 2,
                  join: bool = True):
         self.model = model
         self.chunk = int(chunk)
