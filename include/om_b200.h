@@ -155,6 +155,19 @@ int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M,
                     int iterations, float epsilon, float unused_score, int distance_l1,
                     float* P, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- match extraction -------------------------------------------------------------------- */
+
+size_t om_mutual_matches_workspace_bytes(int B, int N, int M);
+
+/* MutualNearestNeighborMatcher.forward, matching/match_extraction.py:46-184 (used behind every matcher by
+ * feature_detection/match_extraction_wrapper.py:82-113): mutual row/column argmax of the core block of
+ * probs (B,N+1,M+1), probability threshold, the max_matches best in descending order.  Outputs:
+ * matched_kpts1/2 (B,max_matches,2), scores (B,max_matches; -1 for rejected rows, 0 for padding beyond N),
+ * valid (B,max_matches) bytes 0/1.  Equal scores come out in ascending row order.  Limit: N <= 16384. */
+int om_mutual_matches_f32(const float* probs, const float* kpts1, const float* kpts2, int B, int N, int M,
+                          int max_matches, float threshold, float* matched_kpts1, float* matched_kpts2,
+                          float* scores, unsigned char* valid, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- fused matcher ----------------------------------------------------------------------- */
 
 typedef struct om_match_params {

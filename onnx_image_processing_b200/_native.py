@@ -57,6 +57,9 @@ SIGNATURES = {
     "om_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "om_sinkhorn_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "om_mutual_matches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "om_mutual_matches_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "om_match_workspace_bytes": (c_size_t, [POINTER(MatchParams)]),
     "om_match_pairs_f32": (c_int, [POINTER(MatchParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -262,6 +262,33 @@ def _(desc1, desc2, iterations, epsilon, unused_score, distance_l1):
     return desc1.new_empty((desc1.shape[0], desc1.shape[1] + 1, desc2.shape[1] + 1), dtype=torch.float32)
 
 
+@torch.library.custom_op("b200match::mutual_matches", mutates_args=(), device_types="cuda")
+def mutual_matches(probs: torch.Tensor, keypoints1: torch.Tensor, keypoints2: torch.Tensor, max_matches: int,
+                   threshold: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    p = _f32(probs, "P")
+    k1 = _f32(keypoints1, "keypoints1")
+    k2 = _f32(keypoints2, "keypoints2")
+    B, N, M = int(p.shape[0]), int(k1.shape[1]), int(k2.shape[1])
+    if p.shape[1] != N + 1 or p.shape[2] != M + 1:
+        raise RuntimeError(f"P must be (B,{N + 1},{M + 1}) for these keypoints, got {tuple(p.shape)}")
+    lib, st = _begin(p)
+    mk1 = torch.empty((B, max_matches, 2), dtype=torch.float32, device=p.device)
+    mk2 = torch.empty((B, max_matches, 2), dtype=torch.float32, device=p.device)
+    sc = torch.empty((B, max_matches), dtype=torch.float32, device=p.device)
+    valid = torch.empty((B, max_matches), dtype=torch.uint8, device=p.device)
+    ws = _ws(lib.om_mutual_matches_workspace_bytes(B, N, M), p)
+    nat.check(lib.om_mutual_matches_f32(_p(p), _p(k1), _p(k2), B, N, M, int(max_matches), float(threshold), _p(mk1),
+                                        _p(mk2), _p(sc), _p(valid), _p(ws), ws.numel(), st), "om_mutual_matches_f32")
+    return mk1, mk2, sc, valid.to(torch.bool)
+
+
+@mutual_matches.register_fake
+def _(probs, keypoints1, keypoints2, max_matches, threshold):
+    B = probs.shape[0]
+    return (probs.new_empty((B, max_matches, 2), dtype=torch.float32), probs.new_empty((B, max_matches, 2), dtype=torch.float32),
+            probs.new_empty((B, max_matches), dtype=torch.float32), probs.new_empty((B, max_matches), dtype=torch.bool))
+
+
 def make_match_params(flavour: int, B: int, H: int, W: int, K: int, block_size: int, nms_radius: int,
                       border_margin: int, score_threshold: float, P: int, mode: int, temperature: float,
                       normalize: bool, sampling: int, patch_size: int, iterations: int, epsilon: float,

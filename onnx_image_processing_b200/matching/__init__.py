@@ -1,3 +1,4 @@
 from .sinkhorn import SinkhornMatcher, SinkhornMatcherWithScores
+from .match_extraction import MutualNearestNeighborMatcher
 
-__all__ = ["SinkhornMatcher", "SinkhornMatcherWithScores"]
+__all__ = ["SinkhornMatcher", "SinkhornMatcherWithScores", "MutualNearestNeighborMatcher"]

@@ -290,6 +290,29 @@ def sinkhorn(d1: torch.Tensor, d2: torch.Tensor, iterations: int = 20, epsilon: 
 # --------------------------------------------------------------------------------------
 # a10: unified pipelines (feature_detection/*.py)
 # --------------------------------------------------------------------------------------
+def mutual_matches(P: torch.Tensor, keypoints1: torch.Tensor, keypoints2: torch.Tensor, max_matches: int = 100,
+                   threshold: float = 0.1):
+    """matching/match_extraction.py:46-184 with the same ATen ops in the same order."""
+    B, N, M = P.shape[0], keypoints1.shape[1], keypoints2.shape[1]
+    core = P[:, :N, :M]                                                  # :72
+    max_j_for_i = torch.argmax(core, dim=2)                              # :76
+    max_prob_i = torch.max(core, dim=2).values                           # :77
+    max_i_for_j = torch.argmax(core, dim=1)                              # :80
+    matched_i = torch.gather(max_i_for_j, 1, max_j_for_i)                # :95-99
+    is_mutual = matched_i == torch.arange(N).unsqueeze(0).expand(B, -1)  # :102-103
+    valid = is_mutual & (max_prob_i >= threshold)                        # :106-109
+    s = torch.where(valid, max_prob_i, torch.tensor(-1.0, dtype=P.dtype))            # :117-121
+    ss, si = torch.topk(s, k=min(max_matches, N), dim=1, largest=True, sorted=True)  # :124-130
+    if N < max_matches:                                                  # :133-142
+        ss = torch.cat([ss, torch.zeros(B, max_matches - N, dtype=P.dtype)], dim=1)
+        si = torch.cat([si, torch.zeros(B, max_matches - N, dtype=torch.long)], dim=1)
+    idx = si.clamp(0, N - 1)
+    mk1 = torch.gather(keypoints1, 1, idx.unsqueeze(-1).expand(-1, -1, 2))           # :151-160
+    j = torch.gather(max_j_for_i, 1, idx).clamp(0, M - 1)                            # :164-172
+    mk2 = torch.gather(keypoints2, 1, j.unsqueeze(-1).expand(-1, -1, 2))             # :174-178
+    return mk1, mk2, ss, ss > 0.0                                        # :181-184
+
+
 def detect(image, max_keypoints, block_size=3, nms_radius=3, score_threshold=0.0, border_margin=0):
     sc = shi_tomasi_score(image, block_size).squeeze(1)
     return select_topk(sc, nms_mask(sc, nms_radius), max_keypoints, score_threshold, border_margin)

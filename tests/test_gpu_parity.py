@@ -324,6 +324,61 @@ def test_sparse_matcher_golden(name):
     assert torch.equal(model.descriptor(g["image1"].to(DEV), kk), d1)
 
 
+def _same_matches(got, ref):
+    """Same scores / valid mask everywhere; same (kpt1, kpt2) pairs wherever valid, where matches with EQUAL scores may
+    come in any order (torch.topk leaves the order of ties unspecified; the kernel emits them in ascending row order)."""
+    g1, g2, gs, gv = [t.cpu() for t in got]
+    r1, r2, rs, rv = [t.cpu() for t in ref]
+    if not (torch.equal(gs, rs) and torch.equal(gv, rv.bool())):
+        return False
+    for b in range(rs.shape[0]):
+        for sv in rs[b][rv[b].bool()].unique().tolist():
+            m = (rs[b] == sv) & rv[b].bool()
+            a = sorted(tuple(x) for x in torch.cat([g1[b][m], g2[b][m]], dim=1).tolist())
+            r = sorted(tuple(x) for x in torch.cat([r1[b][m], r2[b][m]], dim=1).tolist())
+            # the cut at max_matches may fall inside a group of equal scores: then only the group sizes must agree
+            if a != r and not (bool(m[-1]) and len(a) == len(r)):
+                return False
+    return True
+
+
+@pytest.mark.parametrize("name", G.names("matches"))
+def test_mutual_matches_golden(name):
+    """MutualNearestNeighborMatcher on the GPU vs the reference's outputs: same scores / valid mask everywhere, same
+    keypoint pairs wherever valid (rejected rows all carry score -1, their order is unspecified in torch.topk)."""
+    g = G.load(name)
+    src = G.load(g["source"])
+    mm = om.MutualNearestNeighborMatcher(g["max_matches"], g["threshold"]).to(DEV)
+    got = mm(*_cuda(src["P"], src["kpts1"], src["kpts2"]))
+    assert got[3].dtype == torch.bool
+    assert _same_matches(got, (g["mk1"], g["mk2"], g["scores"], g["valid"]))
+
+
+@pytest.mark.parametrize("N,M,max_matches,thr", [(512, 512, 100, 0.1), (300, 257, 400, 0.0), (40, 77, 100, 0.2), (1, 1, 5, 0.5)])
+def test_mutual_matches_vs_oracle(N, M, max_matches, thr):
+    g = torch.Generator().manual_seed(N + M)
+    P = torch.rand(3, N + 1, M + 1, generator=g) ** 4
+    P[0, : min(N, M), : min(N, M)] += torch.eye(min(N, M)) * 0.8            # plenty of mutual matches
+    k1 = torch.rand(3, N, 2, generator=g) * 400
+    k2 = torch.rand(3, M, 2, generator=g) * 400
+    ref = O.mutual_matches(P, k1, k2, max_matches, thr)
+    got = om.MutualNearestNeighborMatcher(max_matches, thr).to(DEV)(*_cuda(P, k1, k2))
+    assert _same_matches(got, ref)
+
+
+def test_match_extraction_wrapper_end_to_end():
+    i1, i2 = O.texture_images(2, 120, 160, seed=4)
+    base = om.ShiTomasiSparseBADSinkhornMatcher(96).to(DEV).eval()
+    mk1, mk2, sc, valid = om.MatchExtractionWrapper(base, max_matches=50, match_threshold=0.05)(i1.to(DEV), i2.to(DEV))
+    rk1, rk2, rp = O.sparse_matcher(i1, i2, 96)[:3]
+    ref = O.mutual_matches(rp, rk1, rk2, 50, 0.05)
+    assert mk1.shape == (2, 50, 2) and valid.dtype == torch.bool
+    v = ref[3]
+    assert float((valid.cpu() == v).float().mean()) >= 0.98               # P differs by <= 1e-4 -> a threshold case may flip
+    both = v & valid.cpu()
+    assert torch.equal(mk1.cpu()[both], ref[0][both]) or float((mk1.cpu()[both] == ref[0][both]).float().mean()) > 0.95
+
+
 def test_constant_image_has_no_keypoints():
     g = G.load("sparse_constant_image")
     model = om.ShiTomasiSparseBADSinkhornMatcher(g["K"]).to(DEV)

@@ -79,6 +79,18 @@ def test_sinkhorn(name):
     assert torch.equal(p, g["P"])
 
 
+@pytest.mark.parametrize("name", G.names("matches"))
+def test_mutual_matches(name):
+    """oracle.mutual_matches == the reference's MutualNearestNeighborMatcher (golden minted by make_golden_matches.py)."""
+    g = G.load(name)
+    src = G.load(g["source"])
+    mk1, mk2, sc, valid = O.mutual_matches(src["P"], src["kpts1"], src["kpts2"], g["max_matches"], g["threshold"])
+    assert torch.equal(sc, g["scores"]) and torch.equal(valid, g["valid"].bool())
+    v = valid
+    assert torch.equal(mk1[v], g["mk1"][v]) and torch.equal(mk2[v], g["mk2"][v])
+    assert int(valid.sum()) > 0
+
+
 def test_constant_image():
     g = G.load("sparse_constant_image")
     with torch.no_grad():
