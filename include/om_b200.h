@@ -155,6 +155,12 @@ int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M,
                     int iterations, float epsilon, float unused_score, int distance_l1,
                     float* P, void* ws, size_t ws_bytes, void* stream);
 
+/* SinkhornMatcherWithFilters epilogue, matching/sinkhorn.py:311-465, IN PLACE on probs (B,N+1,M+1): rows that fail
+ * the best/second-best ratio test (ratio_threshold <= 0 disables it) or the best-minus-dustbin margin test
+ * (dustbin_margin < 0 disables it) get their core zeroed and their dustbin entry set to 1; valid (B,N) bytes 0/1. */
+int om_sinkhorn_filter_rows_f32(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin,
+                                unsigned char* valid, void* stream);
+
 /* ---- match extraction -------------------------------------------------------------------- */
 
 size_t om_mutual_matches_workspace_bytes(int B, int N, int M);

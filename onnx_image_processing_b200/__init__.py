@@ -7,7 +7,7 @@ from . import _native  # noqa: F401
 from .detector import ShiTomasiScore
 from .descriptor import BADDescriptor, SparseBAD
 from .orientation import AngleEstimator
-from .matching import SinkhornMatcher, SinkhornMatcherWithScores, MutualNearestNeighborMatcher
+from .matching import SinkhornMatcher, SinkhornMatcherWithScores, SinkhornMatcherWithFilters, MutualNearestNeighborMatcher
 from .utils import apply_nms_maxpool, select_topk_keypoints
 from .feature_detection import (
     ShiTomasiBADDetector,
@@ -17,6 +17,7 @@ from .feature_detection import (
     ShiTomasiAngleSparseBAD,
     ShiTomasiAngleSparseBADDetector,
     ShiTomasiAngleSparseBADSinkhornMatcher,
+    ShiTomasiAngleSparseBADSinkhornMatcherWithFilters,
     MatchExtractionWrapper,
 )
 
@@ -25,5 +26,6 @@ __all__ = [
     "SinkhornMatcherWithScores", "apply_nms_maxpool", "select_topk_keypoints", "ShiTomasiBADDetector",
     "ShiTomasiBADSinkhornMatcher", "ShiTomasiSparseBADSinkhornMatcher", "ShiTomasiWithAngle",
     "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector", "ShiTomasiAngleSparseBADSinkhornMatcher",
-    "MutualNearestNeighborMatcher", "MatchExtractionWrapper",
+    "MutualNearestNeighborMatcher", "MatchExtractionWrapper", "SinkhornMatcherWithFilters",
+    "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters",
 ]

@@ -262,6 +262,23 @@ def _(desc1, desc2, iterations, epsilon, unused_score, distance_l1):
     return desc1.new_empty((desc1.shape[0], desc1.shape[1] + 1, desc2.shape[1] + 1), dtype=torch.float32)
 
 
+@torch.library.custom_op("b200match::filter_rows", mutates_args=(), device_types="cuda")
+def filter_rows(probs: torch.Tensor, ratio_threshold: float, dustbin_margin: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(filtered copy of P, valid mask): the outlier filters of SinkhornMatcherWithFilters."""
+    p = _f32(probs, "P").clone()
+    B, N, M = int(p.shape[0]), int(p.shape[1]) - 1, int(p.shape[2]) - 1
+    lib, st = _begin(p)
+    valid = torch.empty((B, N), dtype=torch.uint8, device=p.device)
+    nat.check(lib.om_sinkhorn_filter_rows_f32(_p(p), B, N, M, float(ratio_threshold), float(dustbin_margin), _p(valid), st),
+              "om_sinkhorn_filter_rows_f32")
+    return p, valid.to(torch.bool)
+
+
+@filter_rows.register_fake
+def _(probs, ratio_threshold, dustbin_margin):
+    return probs.new_empty(tuple(probs.shape)), probs.new_empty((probs.shape[0], probs.shape[1] - 1), dtype=torch.bool)
+
+
 @torch.library.custom_op("b200match::mutual_matches", mutates_args=(), device_types="cuda")
 def mutual_matches(probs: torch.Tensor, keypoints1: torch.Tensor, keypoints2: torch.Tensor, max_matches: int,
                    threshold: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -118,6 +118,42 @@ __global__ void __launch_bounds__(MT) match_select_kernel(const float* row_max, 
     }
 }
 
+// SinkhornMatcherWithFilters epilogue, matching/sinkhorn.py:311-465, one warp per keypoint row i < N, in place on P:
+//   ratio filter   best / (second + 1e-8) >= ratio_threshold over the core row (:332-346; topk(2): the two largest
+//                  values, a duplicate maximum counts twice)
+//   margin filter  best - P[i][M] >= dustbin_margin (:366-376)
+//   rewrite        rejected rows: core -> 0, dustbin column -> 1 (:448-457); accepted rows unchanged
+__global__ void __launch_bounds__(MT) filter_rows_kernel(float* P, int N, int M, float ratio_threshold, float dustbin_margin,
+                                                         unsigned char* valid) {
+    const int z = blockIdx.y;
+    const int i = blockIdx.x * (MT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= N) return;
+    float* row = P + ((size_t)z * (N + 1) + i) * (M + 1);
+    float b1 = -CUDART_INF_F, b2 = -CUDART_INF_F;                       // largest, second largest
+    for (int j = lane; j < M; j += 32) {
+        const float v = row[j];
+        if (v > b1) { b2 = b1; b1 = v; } else if (v > b2) b2 = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+        const float n1 = fmaxf(b1, o1);
+        b2 = fmaxf(fminf(b1, o1), fmaxf(b2, o2));
+        b1 = n1;
+    }
+    bool ok = true;
+    if (ratio_threshold > 0.0f) {
+        const float second = M >= 2 ? b2 : 0.0f;                        // :339-341
+        ok = ok && (__fdiv_rn(b1, __fadd_rn(second, 1e-8f)) >= ratio_threshold);
+    }
+    if (dustbin_margin >= 0.0f) ok = ok && (__fsub_rn(b1, row[M]) >= dustbin_margin);
+    if (!ok) {
+        for (int j = lane; j < M; j += 32) row[j] = 0.0f;               // P * 0 (probabilities are finite and >= 0)
+        if (lane == 0) row[M] = 1.0f;
+    }
+    if (lane == 0) valid[(size_t)z * N + i] = ok ? 1 : 0;
+}
+
 int next_pow2(int v) {
     int p = 2;
     while (p < v) p <<= 1;
@@ -129,6 +165,17 @@ int next_pow2(int v) {
 }  // namespace om
 
 using namespace om;
+
+extern "C" int om_sinkhorn_filter_rows_f32(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin,
+                                           unsigned char* valid, void* stream) {
+    if (probs == nullptr || valid == nullptr) return OM_ERR_NULL;
+    if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
+    if (B > 65535) return OM_ERR_LIMIT;
+    filter_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, (cudaStream_t)stream>>>(probs, N, M, ratio_threshold,
+                                                                                               dustbin_margin, valid);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
 
 extern "C" size_t om_mutual_matches_workspace_bytes(int B, int N, int M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;

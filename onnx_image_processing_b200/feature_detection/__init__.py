@@ -2,11 +2,13 @@ from .shi_tomasi_bad import ShiTomasiBADDetector
 from .shi_tomasi_bad_sinkhorn import ShiTomasiBADSinkhornMatcher
 from .shi_tomasi_sparse_bad_sinkhorn import ShiTomasiSparseBADSinkhornMatcher
 from .shi_tomasi_angle import ShiTomasiWithAngle, ShiTomasiAngleSparseBAD, ShiTomasiAngleSparseBADDetector
-from .shi_tomasi_angle_sparse_bad_sinkhorn import ShiTomasiAngleSparseBADSinkhornMatcher
+from .shi_tomasi_angle_sparse_bad_sinkhorn import (ShiTomasiAngleSparseBADSinkhornMatcher,
+                                                   ShiTomasiAngleSparseBADSinkhornMatcherWithFilters)
 from .match_extraction_wrapper import MatchExtractionWrapper
 
 __all__ = [
     "ShiTomasiBADDetector", "ShiTomasiBADSinkhornMatcher", "ShiTomasiSparseBADSinkhornMatcher",
     "ShiTomasiWithAngle", "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector",
-    "ShiTomasiAngleSparseBADSinkhornMatcher", "MatchExtractionWrapper",
+    "ShiTomasiAngleSparseBADSinkhornMatcher", "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters",
+    "MatchExtractionWrapper",
 ]

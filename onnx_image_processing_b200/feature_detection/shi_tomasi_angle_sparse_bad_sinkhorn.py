@@ -5,7 +5,7 @@ from torch import nn
 
 from .. import _ops
 from ..descriptor.bad import SparseBAD
-from ..matching.sinkhorn import SinkhornMatcher
+from ..matching.sinkhorn import SinkhornMatcher, SinkhornMatcherWithFilters
 from .shi_tomasi_angle import ShiTomasiWithAngle
 
 
@@ -44,3 +44,26 @@ class ShiTomasiAngleSparseBADSinkhornMatcher(nn.Module):
     def forward(self, image1: torch.Tensor, image2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         k1, k2, probs, _, _ = self.match(image1, image2)
         return k1, k2, probs
+
+
+class ShiTomasiAngleSparseBADSinkhornMatcherWithFilters(ShiTomasiAngleSparseBADSinkhornMatcher):
+    """The rotation-invariant matcher with the outlier filters built into the matching step
+    (shi_tomasi_angle_sparse_bad_sinkhorn.py:183-340): returns (kpts1, kpts2, filtered P, valid_mask)."""
+
+    def __init__(self, max_keypoints: int, block_size: int = 5, patch_size: int = 15, sigma: float = 2.5,
+                 num_pairs: int = 256, binarize: bool = False, soft_binarize: bool = True, temperature: float = 10.0,
+                 sinkhorn_iterations: int = 20, epsilon: float = 1.0, unused_score: float = 1.0,
+                 distance_type: str = "l2", ratio_threshold: float = None, dustbin_margin: float = None,
+                 nms_radius: int = 3, score_threshold: float = 0.0, normalize_descriptors: bool = True,
+                 sampling_mode: str = "nearest", border_margin: int | None = None) -> None:
+        super().__init__(max_keypoints, block_size, patch_size, sigma, num_pairs, binarize, soft_binarize, temperature,
+                         sinkhorn_iterations, epsilon, unused_score, distance_type, nms_radius, score_threshold,
+                         normalize_descriptors, sampling_mode, border_margin)
+        self.matcher = SinkhornMatcherWithFilters(iterations=sinkhorn_iterations, epsilon=epsilon, unused_score=unused_score,
+                                                  distance_type=distance_type, ratio_threshold=ratio_threshold,
+                                                  dustbin_margin=dustbin_margin)
+
+    def forward(self, image1: torch.Tensor, image2: torch.Tensor):
+        k1, k2, probs, _, _ = self.match(image1, image2)
+        probs, valid = _ops.filter_rows(probs, float(self.matcher.ratio_threshold), float(self.matcher.dustbin_margin))
+        return k1, k2, probs, valid

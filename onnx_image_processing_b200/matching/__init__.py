@@ -1,4 +1,4 @@
-from .sinkhorn import SinkhornMatcher, SinkhornMatcherWithScores
+from .sinkhorn import SinkhornMatcher, SinkhornMatcherWithScores, SinkhornMatcherWithFilters
 from .match_extraction import MutualNearestNeighborMatcher
 
-__all__ = ["SinkhornMatcher", "SinkhornMatcherWithScores", "MutualNearestNeighborMatcher"]
+__all__ = ["SinkhornMatcher", "SinkhornMatcherWithScores", "SinkhornMatcherWithFilters", "MutualNearestNeighborMatcher"]

@@ -34,3 +34,18 @@ class SinkhornMatcherWithScores(SinkhornMatcher):
         P = super().forward(desc1, desc2)
         core = P[:, :desc1.shape[1], :desc2.shape[1]]
         return P, core.max(dim=-1).values, core.max(dim=-2).values
+
+
+class SinkhornMatcherWithFilters(SinkhornMatcher):
+    """Sinkhorn + probability-ratio and dustbin-margin outlier filters (sinkhorn.py:262-465): returns
+    (P with rejected rows sent to the dustbin, valid_mask (B,N) bool)."""
+
+    def __init__(self, iterations: int = 20, epsilon: float = 1.0, unused_score: float = 1.0, distance_type: str = "l2",
+                 ratio_threshold: float = None, dustbin_margin: float = None) -> None:
+        super().__init__(iterations, epsilon, unused_score, distance_type)
+        self.ratio_threshold = ratio_threshold if ratio_threshold is not None else -1.0
+        self.dustbin_margin = dustbin_margin if dustbin_margin is not None else -1.0
+
+    def forward(self, desc1: torch.Tensor, desc2: torch.Tensor):
+        P = super().forward(desc1, desc2)
+        return _ops.filter_rows(P, float(self.ratio_threshold), float(self.dustbin_margin))

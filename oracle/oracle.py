@@ -290,6 +290,26 @@ def sinkhorn(d1: torch.Tensor, d2: torch.Tensor, iterations: int = 20, epsilon: 
 # --------------------------------------------------------------------------------------
 # a10: unified pipelines (feature_detection/*.py)
 # --------------------------------------------------------------------------------------
+def filter_rows(P: torch.Tensor, ratio_threshold: float = -1.0, dustbin_margin: float = -1.0):
+    """The filtering part of SinkhornMatcherWithFilters.forward, matching/sinkhorn.py:311-465, same ATen ops."""
+    B, N, M = P.shape[0], P.shape[1] - 1, P.shape[2] - 1
+    valid = torch.ones(B, N, dtype=torch.bool)
+    core = P[:, :N, :M]
+    if ratio_threshold > 0:                                              # :332-346
+        if M >= 2:
+            top2 = torch.topk(core, k=2, dim=2, largest=True, sorted=True).values
+            best, second = top2[:, :, 0], top2[:, :, 1]
+        else:
+            best = core[:, :, 0]
+            second = torch.zeros_like(best)
+        valid = valid & ((best / (second + 1e-8)) >= ratio_threshold)
+    if dustbin_margin >= 0:                                              # :366-376
+        valid = valid & ((core.max(dim=2).values - P[:, :N, M]) >= dustbin_margin)
+    vf = valid.unsqueeze(-1).float()                                     # :448-457
+    rows = torch.cat([P[:, :N, :M] * vf, (1.0 - vf) + vf * P[:, :N, M:M + 1]], dim=-1)
+    return torch.cat([rows, P[:, N:N + 1, :]], dim=1), valid
+
+
 def mutual_matches(P: torch.Tensor, keypoints1: torch.Tensor, keypoints2: torch.Tensor, max_matches: int = 100,
                    threshold: float = 0.1):
     """matching/match_extraction.py:46-184 with the same ATen ops in the same order."""

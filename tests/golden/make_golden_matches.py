@@ -33,3 +33,20 @@ for src, max_matches, thr in (("sparse_full_default", 100, 0.0035), ("sparse_sma
     np.savez_compressed(out, kind="matches", source=src, max_matches=max_matches, threshold=thr, mk1=mk1.numpy(), mk2=mk2.numpy(),
                         scores=sc.numpy(), valid=valid.numpy())
     print(out, int(valid.sum()), "valid of", valid.numel())
+
+# ---- outlier filters (SinkhornMatcherWithFilters): thresholds at the medians so that about half of the rows pass
+from pytorch_model.matching.sinkhorn import SinkhornMatcherWithFilters  # noqa: E402
+
+for src in G.names("sinkhorn"):
+    g = G.load(src)
+    N, M = g["desc1"].shape[1], g["desc2"].shape[1]
+    core = g["P"][:, :N, :M]
+    top2 = torch.topk(core, 2, dim=2).values
+    ratio = float((top2[..., 0] / (top2[..., 1] + 1e-8)).median())
+    margin = float((top2[..., 0] - g["P"][:, :N, M]).median())
+    with torch.no_grad():
+        pf, valid = SinkhornMatcherWithFilters(**g["kwargs"], ratio_threshold=ratio, dustbin_margin=margin)(g["desc1"], g["desc2"])
+    out = os.path.join(HERE, f"filters_{src}.npz")
+    np.savez_compressed(out, kind="filters", source=src, ratio_threshold=ratio, dustbin_margin=margin, valid=valid.numpy(),
+                        row_sums=pf.sum(dim=2).numpy(), dust_col=pf[:, :N, M].numpy())
+    print(out, int(valid.sum()), "valid of", valid.numel())

@@ -366,6 +366,51 @@ def test_mutual_matches_vs_oracle(N, M, max_matches, thr):
     assert _same_matches(got, ref)
 
 
+@pytest.mark.parametrize("name", G.names("filters"))
+def test_filter_rows_golden(name):
+    """The outlier-filter epilogue on the reference's own P: identical mask and identical filtered matrix."""
+    g = G.load(name)
+    src = G.load(g["source"])
+    pf, valid = _ops.filter_rows(src["P"].to(DEV), g["ratio_threshold"], g["dustbin_margin"])
+    ref_pf, ref_valid = O.filter_rows(src["P"], g["ratio_threshold"], g["dustbin_margin"])
+    assert torch.equal(valid.cpu(), g["valid"].bool()) and torch.equal(valid.cpu(), ref_valid)
+    assert torch.equal(pf.cpu(), ref_pf)
+
+
+@pytest.mark.parametrize("ratio,margin", [(None, None), (1.05, None), (None, 0.0), (1.02, 0.001)])
+def test_sinkhorn_with_filters_module(ratio, margin):
+    g = torch.Generator().manual_seed(9)
+    d1 = torch.nn.functional.normalize(torch.randn(2, 200, 256, generator=g), dim=-1)
+    d2 = torch.nn.functional.normalize(d1[:, torch.randperm(200, generator=g)[:150]] + 0.3 * torch.randn(2, 150, 256, generator=g), dim=-1)
+    m = om.SinkhornMatcherWithFilters(20, 0.1, 1.0, "l2", ratio, margin).to(DEV)
+    pf, valid = m(*_cuda(d1, d2))
+    p_ref = O.sinkhorn(d1, d2, 20, 0.1, 1.0)
+    ref_pf, ref_valid = O.filter_rows(p_ref, m.ratio_threshold, m.dustbin_margin)
+    assert valid.dtype == torch.bool and pf.shape == (2, 201, 151)
+    agree = (valid.cpu() == ref_valid).float().mean()
+    assert float(agree) >= 0.98, float(agree)                            # P differs by <= 1e-4: a threshold case may flip
+    same = valid.cpu() == ref_valid
+    assert float((pf.cpu() - ref_pf)[:, :200][same].abs().max()) <= PR.PROB_TOL
+    if ratio is None and margin is None:
+        assert bool(valid.all())
+
+
+def test_angle_matcher_with_filters_like_the_reference_test():
+    """The reference's only integration test (test_filters_pytorch.py:9-57): random-noise inputs, K=128, 10 iterations,
+    filters on, then off -- shapes, dtypes and the everything-passes case."""
+    g = torch.Generator().manual_seed(0)
+    i1 = torch.randn(1, 1, 240, 320, generator=g).to(DEV)
+    i2 = torch.randn(1, 1, 240, 320, generator=g).to(DEV)
+    kw = dict(max_keypoints=128, sinkhorn_iterations=10, epsilon=1.0)
+    k1, k2, p, valid = om.ShiTomasiAngleSparseBADSinkhornMatcherWithFilters(ratio_threshold=2.0, dustbin_margin=0.3, **kw).to(DEV)(i1, i2)
+    assert k1.shape == (1, 128, 2) and k2.shape == (1, 128, 2) and p.shape == (1, 129, 129) and valid.shape == (1, 128)
+    assert valid.dtype == torch.bool and bool(torch.isfinite(p).all())
+    rejected = ~valid[0]
+    assert float((p[0, :128, :128][rejected]).abs().max()) == 0.0 and bool((p[0, :128, 128][rejected] == 1.0).all())
+    _, _, p2, valid2 = om.ShiTomasiAngleSparseBADSinkhornMatcherWithFilters(**kw).to(DEV)(i1, i2)
+    assert bool(valid2.all())
+
+
 def test_match_extraction_wrapper_end_to_end():
     i1, i2 = O.texture_images(2, 120, 160, seed=4)
     base = om.ShiTomasiSparseBADSinkhornMatcher(96).to(DEV).eval()

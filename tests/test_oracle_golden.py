@@ -91,6 +91,17 @@ def test_mutual_matches(name):
     assert int(valid.sum()) > 0
 
 
+@pytest.mark.parametrize("name", G.names("filters"))
+def test_filter_rows(name):
+    """oracle.filter_rows == the reference's SinkhornMatcherWithFilters on the golden P."""
+    g = G.load(name)
+    src = G.load(g["source"])
+    pf, valid = O.filter_rows(src["P"], g["ratio_threshold"], g["dustbin_margin"])
+    N = valid.shape[1]
+    assert torch.equal(valid, g["valid"].bool()) and 0 < int(valid.sum()) < valid.numel()
+    assert torch.equal(pf[:, :N, -1], g["dust_col"]) and torch.equal(pf.sum(dim=2), g["row_sums"])
+
+
 def test_constant_image():
     g = G.load("sparse_constant_image")
     with torch.no_grad():
