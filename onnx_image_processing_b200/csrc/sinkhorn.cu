@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* d, long long r
 
 // S[b][i][j] = -clamp(n1_i + n2_j - 2 a_i.b_j, 0) / eps for i<N, j<M; dustbin elsewhere (sinkhorn.py:98-103, :178-187)
 __global__ void __launch_bounds__(256) cost_l2_kernel(const float* d1, const float* d2, const float* n1, const float* n2,
-                                                      int N, int M, int D, float eps, float dustbin, float* S) {
+                                                      int N, int M, int D, float eps, float dustbin, int as_exp, float* S) {
     __shared__ __align__(16) float As[16][68];
     __shared__ __align__(16) float Bs[16][68];
     const int z = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
@@ -92,13 +92,13 @@ __global__ void __launch_bounds__(256) cost_l2_kernel(const float* d1, const flo
                                                    __fmul_rn(2.0f, acc[r][c])), 0.0f);
                 v = __fdiv_rn(-cost, eps);
             }
-            Sz[(size_t)i * (M + 1) + j] = v;
+            Sz[(size_t)i * (M + 1) + j] = as_exp ? expf(v) : v;
         }
     }
 }
 
 __global__ void __launch_bounds__(256) cost_l1_kernel(const float* d1, const float* d2, int N, int M, int D, float eps,
-                                                      float dustbin, float* S) {
+                                                      float dustbin, int as_exp, float* S) {
     const int z = blockIdx.z;
     const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (i > N || j > M) return;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) cost_l1_kernel(const float* d1, const flo
         for (int k = 0; k < D; ++k) acc += fabsf(a[k] - b[k]);            // sinkhorn.py:106-108
         v = __fdiv_rn(-acc, eps);
     }
-    S[(size_t)z * (N + 1) * (M + 1) + (size_t)i * (M + 1) + j] = v;
+    S[(size_t)z * (N + 1) * (M + 1) + (size_t)i * (M + 1) + j] = as_exp ? expf(v) : v;
 }
 
 // u_i = log_mu_i - logsumexp_j(S_ij + v_j)   (sinkhorn.py:140), one warp per row
@@ -171,8 +171,72 @@ __global__ void __launch_bounds__(256) finalize_kernel(float* S, const float* u,
     }
 }
 
+// ---- scaling form of the same iteration for matrices that do not fit a cluster (K = exp(S) in global memory / L2) ----
+// a_i = mu_i / sum_j K_ij b_j,  b_j = nu_j / sum_i K_ij a_i  (== sinkhorn.py:138-142 with a = exp(u), b = exp(v)),
+// used while exp(-unused/eps) is far from underflow.  One sweep of K per iteration: a CTA owns XR rows, computes their
+// row sums (one warp per row) and at once their contribution to every column sum (the rows are re-read from L1);
+// the per-CTA column partials are combined in a fixed order by xd_col_kernel (no floating-point atomics).
+constexpr int XR = 16;
+
+__global__ void __launch_bounds__(XR * 32) xd_row_kernel(const float* K, const float* b, float* a, float* Tpart, int N, int M,
+                                                         float mu_dust) {
+    __shared__ float sA[XR];
+    const int z = blockIdx.y, blk = blockIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blk * XR, i = i0 + w;
+    const float* Kz = K + (size_t)z * (N + 1) * (M + 1);
+    const float* bz = b + (size_t)z * (M + 1);
+    float av = 0.0f;
+    if (i <= N) {
+        const float* row = Kz + (size_t)i * (M + 1);
+        float s0 = 0.0f, s1 = 0.0f;
+        int j = lane;
+        for (; j + 32 <= M; j += 64) { s0 = fmaf(row[j], bz[j], s0); s1 = fmaf(row[j + 32], bz[j + 32], s1); }
+        for (; j <= M; j += 32) s0 = fmaf(row[j], bz[j], s0);
+        const float rs = warp_sum(s0 + s1);
+        av = __fdividef(i == N ? mu_dust : 1.0f, rs);
+        if (lane == 0) a[(size_t)z * (N + 1) + i] = av;
+    }
+    if (lane == 0) sA[w] = av;
+    __syncthreads();
+    const int rows = min(XR, N + 1 - i0);
+    float* tp = Tpart + ((size_t)z * gridDim.x + blk) * (M + 1);
+    for (int j = threadIdx.x; j <= M; j += XR * 32) {
+        float t = 0.0f;
+        for (int r = 0; r < rows; ++r) t = fmaf(Kz[(size_t)(i0 + r) * (M + 1) + j], sA[r], t);
+        tp[j] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) xd_col_kernel(const float* Tpart, float* b, int nblk, int M, float nu_dust) {
+    const int z = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j > M) return;
+    const float* tp = Tpart + (size_t)z * nblk * (M + 1) + j;
+    float t0 = 0.0f, t1 = 0.0f;
+    int q = 0;
+    for (; q + 1 < nblk; q += 2) { t0 += tp[(size_t)q * (M + 1)]; t1 += tp[(size_t)(q + 1) * (M + 1)]; }
+    if (q < nblk) t0 += tp[(size_t)q * (M + 1)];
+    b[(size_t)z * (M + 1) + j] = __fdividef(j == M ? nu_dust : 1.0f, t0 + t1);
+}
+
+// P = a_i K_ij b_j in place (sinkhorn.py:145, :206)
+__global__ void __launch_bounds__(256) xd_finalize_kernel(float* K, const float* a, const float* b, int N, int M) {
+    const int z = blockIdx.y;
+    const size_t n = (size_t)(N + 1) * (M + 1);
+    float* Kz = K + (size_t)z * n;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (size_t)gridDim.x * 256) {
+        const int i = (int)(e / (M + 1)), j = (int)(e % (M + 1));
+        Kz[e] = a[(size_t)z * (N + 1) + i] * Kz[e] * b[(size_t)z * (M + 1) + j];
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* p, size_t n, float v) {
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (size_t)gridDim.x * 256) p[e] = v;
+}
+
 struct SkWs {
-    float *n1, *n2, *u, *v;
+    float *n1, *n2, *u, *v, *tpart;
 };
 
 SkWs carve_sk(void* ws, int B, int N, int M) {
@@ -181,23 +245,43 @@ SkWs carve_sk(void* ws, int B, int N, int M) {
     w.n1 = (float*)p; p += align_up((size_t)B * N * sizeof(float));
     w.n2 = (float*)p; p += align_up((size_t)B * M * sizeof(float));
     w.u = (float*)p;  p += align_up((size_t)B * (N + 1) * sizeof(float));
-    w.v = (float*)p;
+    w.v = (float*)p;  p += align_up((size_t)B * (M + 1) * sizeof(float));
+    w.tpart = (float*)p;
     return w;
 }
+
+int g_generic_allow_scaling = 1;   // test hook: 0 forces the log-domain generic kernels
 
 int sinkhorn_generic(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                      float dustbin, int l1, float* P, void* ws, cudaStream_t st) {
     const SkWs w = carve_sk(ws, B, N, M);
+    // scaling form while exp(dustbin) = exp(-unused/eps) stays far from underflow (2^-60), as in the cluster kernel
+    const int scaling = g_generic_allow_scaling && dustbin <= 0.0f && -(double)dustbin * 1.4426950408889634 <= 60.0;
     if (l1) {
-        cost_l1_kernel<<<dim3((M + 32) / 32, (N + 8) / 8, B), 256, 0, st>>>(d1, d2, N, M, D, eps, dustbin, P);
+        cost_l1_kernel<<<dim3((M + 32) / 32, (N + 8) / 8, B), 256, 0, st>>>(d1, d2, N, M, D, eps, dustbin, scaling, P);
         OM_AFTER_LAUNCH();
     } else {
         sqnorm_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, st>>>(d1, (long long)B * N, D, w.n1);
         OM_AFTER_LAUNCH();
         sqnorm_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(d2, (long long)B * M, D, w.n2);
         OM_AFTER_LAUNCH();
-        cost_l2_kernel<<<dim3((M + 64) / 64, (N + 64) / 64, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, P);
+        cost_l2_kernel<<<dim3((M + 64) / 64, (N + 64) / 64, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, scaling, P);
         OM_AFTER_LAUNCH();
+    }
+    if (scaling) {
+        const int nblk = (N + 1 + XR - 1) / XR;
+        fill_kernel<<<64, 256, 0, st>>>(w.v, (size_t)B * (M + 1), 1.0f);              // b = exp(v) = 1
+        OM_AFTER_LAUNCH();
+        for (int it = 0; it < iterations; ++it) {
+            xd_row_kernel<<<dim3(nblk, B), XR * 32, 0, st>>>(P, w.v, w.u, w.tpart, N, M, (float)M);   // mu_N = M (:197-198)
+            OM_AFTER_LAUNCH();
+            xd_col_kernel<<<dim3((M + 256) / 256, B), 256, 0, st>>>(w.tpart, w.v, nblk, M, (float)N);  // nu_M = N (:199-200)
+            OM_AFTER_LAUNCH();
+        }
+        const size_t n = (size_t)(N + 1) * (M + 1);
+        xd_finalize_kernel<<<dim3((unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), B), 256, 0, st>>>(P, w.u, w.v, N, M);
+        OM_AFTER_LAUNCH();
+        return OM_OK;
     }
     OM_CUDA(cudaMemsetAsync(w.v, 0, (size_t)B * (M + 1) * sizeof(float), st));
     const float log_m = (float)log((double)M), log_n = (float)log((double)N);       // sinkhorn.py:197-198
@@ -490,7 +574,8 @@ int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int 
 }
 
 // 0: tcgen05 cluster kernel (scaling-form loop when safe), 1: FFMA cluster kernel, 2: generic kernels,
-// 3: tcgen05 cluster kernel with the log-domain loop forced, 4: tcgen05 cluster kernel with the 3xTF32 GEMM forced
+// 3: tcgen05 cluster kernel with the log-domain loop forced, 4: tcgen05 cluster kernel with the 3xTF32 GEMM forced,
+// 5: generic kernels with the log-domain loop forced (2 = generic kernels, scaling form when safe)
 int g_sinkhorn_variant = 0;
 
 }  // namespace
@@ -499,7 +584,8 @@ size_t sinkhorn_workspace_bytes(int B, int N, int M, int D) {
     (void)D;
     if (B <= 0 || N <= 0 || M <= 0) return 0;
     return align_up((size_t)B * N * sizeof(float)) + align_up((size_t)B * M * sizeof(float)) +
-           align_up((size_t)B * (N + 1) * sizeof(float)) + align_up((size_t)B * (M + 1) * sizeof(float));
+           align_up((size_t)B * (N + 1) * sizeof(float)) + align_up((size_t)B * (M + 1) * sizeof(float)) +
+           align_up((size_t)B * ((N + 1 + XR - 1) / XR) * (M + 1) * sizeof(float));   // column partials of the scaling-form generic path
 }
 
 int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
@@ -509,7 +595,8 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
     if (iterations <= 0 || !(epsilon > 0.0f)) return OM_ERR_PARAM;        // sinkhorn.py:66-69
     if (B > 65535) return OM_ERR_LIMIT;
     const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && g_sinkhorn_variant != 2 &&
-                      (long long)B * CL < (1ll << 31);
+                      g_sinkhorn_variant != 5 && (long long)B * CL < (1ll << 31);
+    g_generic_allow_scaling = g_sinkhorn_variant != 5;
     if (fast && (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 3 || g_sinkhorn_variant == 4)) {
         g_tc_allow_scaling = g_sinkhorn_variant != 3;
         g_tc_allow_f16 = g_sinkhorn_variant != 4;

@@ -200,7 +200,7 @@ def test_gather_functions():
 # ------------------------------------------------------------------------------------------
 # Sinkhorn
 # ------------------------------------------------------------------------------------------
-VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32"}
+VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32", 5: "generic-log"}
 
 
 def _with_variant(variant, fn):
@@ -213,7 +213,7 @@ def _with_variant(variant, fn):
 
 
 @pytest.mark.parametrize("name", G.names("sinkhorn"))
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=lambda v: VARIANTS[v])
 def test_sinkhorn_golden(name, variant):
     g = G.load(name)
     got = _with_variant(variant, lambda: om.SinkhornMatcher(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"])))
@@ -223,7 +223,7 @@ def test_sinkhorn_golden(name, variant):
     assert m64["core"] <= PR.PROB_TOL, m64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=lambda v: VARIANTS[v])
 @pytest.mark.parametrize("N,M,eps,unused", [(512, 512, 1.0, 1.0), (512, 512, 0.05, 1.0), (300, 512, 0.1, 0.5),
                                             (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0),
                                             (509, 511, 0.03, 1.0), (512, 512, 0.2, 0.0)])
@@ -249,7 +249,7 @@ def test_sinkhorn_variants_agree_on_matched_descriptors():
     d1 = torch.nn.functional.normalize(torch.randn(3, 512, 256, generator=g), dim=-1)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(512, generator=g)] + 0.02 * torch.randn(3, 512, 256, generator=g), dim=-1)
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.05, 1.0).float()
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1, 2, 3, 4, 5):
         got = _with_variant(variant, lambda: om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2)))
         m = PR.prob_metrics(got, ref)
         assert PR.probs_ok(m), (VARIANTS[variant], m)
@@ -267,12 +267,17 @@ def test_sinkhorn_descriptors_beyond_fp16_range():
     assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
 
 
-def test_sinkhorn_large_k_generic_path():
+@pytest.mark.parametrize("variant", [0, 5], ids=lambda v: {0: "scaling", 5: "log-domain"}[v])
+@pytest.mark.parametrize("N,M,eps,dist", [(700, 700, 0.05, "l2"), (1024, 1024, 0.05, "l2"), (600, 901, 1.0, "l2"), (530, 520, 0.2, "l1")])
+def test_sinkhorn_large_k_generic_path(N, M, eps, dist, variant):
+    """Beyond the cluster kernel's 512 x 512 (the export default K = 1024 and config 5's K = 2048 live here): the
+    global-memory kernels in scaling form and in log-domain form against the oracle."""
     g = torch.Generator().manual_seed(5)
-    d1 = torch.nn.functional.normalize(torch.randn(1, 700, 256, generator=g), dim=-1)
-    d2 = torch.nn.functional.normalize(d1[:, torch.randperm(700, generator=g)] + 0.2 * torch.randn(1, 700, 256, generator=g), dim=-1)
-    ref = O.sinkhorn(d1, d2, 20, 0.05)
-    got = om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2))
+    d1 = torch.nn.functional.normalize(torch.randn(2, N, 256, generator=g), dim=-1)
+    pick = (torch.randperm(max(N, M), generator=g) % N)[:M]
+    d2 = torch.nn.functional.normalize(d1[:, pick] + 0.2 * torch.randn(2, M, 256, generator=g), dim=-1)
+    ref = O.sinkhorn(d1, d2, 20, eps, 1.0, dist)
+    got = _with_variant(variant, lambda: om.SinkhornMatcher(20, eps, 1.0, dist).to(DEV)(*_cuda(d1, d2)))
     m = PR.prob_metrics(got, ref)
     assert PR.probs_ok(m), m
 
