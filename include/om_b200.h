@@ -207,9 +207,9 @@ int om_match_pairs_f32(const om_match_params* p, const float* image1, const floa
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 
-/* Stencil kernel selection: 0 = register sweep kernel (default for block 3/5, radius 3/5), 1 = generic
- * (runtime block size / radius) kernel, 2 = tiled shared-memory kernel; lets the tests check them
- * against each other. */
+/* Stencil kernel selection: 0 = default routing (block 3/5: register sweep kernel for radius 3, tiled
+ * shared-memory kernel for radius 5), 1 = generic (runtime block size / radius) kernel, 2 = tiled kernel,
+ * 3 = sweep kernel; lets the tests check them against each other. */
 void om_debug_force_generic_stencil(int on);
 /* Sweep-kernel tuning: output rows per tile (0 = default 40) and resident CTAs per SM (3, or 4 = default). */
 void om_debug_sweep_tuning(int strip_rows, int min_blocks);

@@ -14,9 +14,11 @@ ws = torch.empty(lib.om_topk_workspace_bytes(B, H, W, K), dtype=torch.uint8, dev
 kp = torch.empty(B, K, 2, device="cuda"); ks = torch.empty(B, K, device="cuda")
 st = torch.cuda.current_stream()
 p = lambda t: ctypes.c_void_p(t.data_ptr())
+BS, R = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3, 3)
 def run():
-    nat.check(lib.om_debug_detect_stage(p(img), B, H, W, 3, 3, 7, 0.0, K, p(kp), p(ks), p(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream), 0), "stage")
-for strip, minb in [(40, 3), (40, 4), (60, 3), (80, 3), (30, 3), (60, 4), (120, 3)]:
+    nat.check(lib.om_debug_detect_stage(p(img), B, H, W, BS, R, 7, 0.0, K, p(kp), p(ks), p(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream), 0), "stage")
+print("block", BS, "radius", R)
+for strip, minb in [(40, 3), (40, 4), (60, 3), (30, 4), (48, 4)]:
     lib.om_debug_sweep_tuning(strip, minb)
     for _ in range(3): run()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -24,3 +26,13 @@ for strip, minb in [(40, 3), (40, 4), (60, 3), (80, 3), (30, 3), (60, 4), (120, 
     for _ in range(20): run()
     b.record(); torch.cuda.synchronize()
     print(f"strip {strip:4d} minb {minb}: {a.elapsed_time(b) / 20 * 1000:.1f} us")
+lib.om_debug_sweep_tuning(40, 4)
+for mode, name in ((2, "tiled shared-memory kernel"), (1, "generic kernel")):
+    lib.om_debug_force_generic_stencil(mode)
+    for _ in range(3): run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(10): run()
+    b.record(); torch.cuda.synchronize()
+    print(f"{name}: {a.elapsed_time(b) / 10 * 1000:.1f} us")
+lib.om_debug_force_generic_stencil(0)
