@@ -429,6 +429,56 @@ def test_match_extraction_wrapper_end_to_end():
     assert torch.equal(mk1.cpu()[both], ref[0][both]) or float((mk1.cpu()[both] == ref[0][both]).float().mean()) > 0.95
 
 
+def _random_cases(n, seed):
+    import random
+    rnd = random.Random(seed)
+    cases = []
+    for _ in range(n):
+        H, W = rnd.randint(24, 200), rnd.randint(24, 260)
+        cases.append(dict(B=rnd.randint(1, 3), H=H, W=W, K=rnd.choice([1, 7, 64, 200, 513]), bs=rnd.choice([3, 5]),
+                          r=rnd.choice([1, 3, 5]), margin=rnd.choice([0, 0, 3, 7, 11]), thr=rnd.choice([0.0, 0.0, 500.0]),
+                          family=rnd.choice(["texture", "texture", "noise"]), seed=rnd.randint(0, 10 ** 6)))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_cases(24, 20261018), ids=lambda c: f"{c['B']}x{c['H']}x{c['W']}-k{c['K']}-b{c['bs']}r{c['r']}m{c['margin']}")
+def test_random_shapes_detector_and_sparse_descriptor(case):
+    """Seeded random shapes / parameters (ragged sizes, K larger than the number of candidates, every kernel routing):
+    keypoints and scores against the oracle, descriptors at those keypoints against the oracle."""
+    c = case
+    if c["K"] > c["H"] * c["W"]:
+        pytest.skip("K > H*W raises in the reference too")
+    img = (O.texture_images(c["B"], c["H"], c["W"], seed=c["seed"])[0] if c["family"] == "texture"
+           else O.noise_images(c["B"], c["H"], c["W"], seed=c["seed"]))
+    rk, rs = O.detect(img, c["K"], c["bs"], c["r"], c["thr"], c["margin"])
+    gk, gs = _ops.detect(img.to(DEV), c["K"], c["bs"], c["r"], c["thr"], c["margin"])
+    if PR.keypoint_mismatches(gk, rk, rs) != 0:
+        d = (gk.cpu() != rk).any(-1).nonzero().tolist()
+        detail = [(b, i, rk[b, i].tolist(), float(rs[b, i]), gk[b, i].tolist(), float(gs[b, i])) for b, i in d[:8]]
+        raise AssertionError(f"keypoints differ from the oracle at (image, slot, ref yx, ref score, gpu yx, gpu score): {detail}")
+    assert PR.scores_close(gs, rs)
+    ref = O.sparse_bad(img, rk, None)
+    got = om.SparseBAD().to(DEV)(img.to(DEV), rk.to(DEV))
+    m = PR.desc_metrics(got, ref)
+    assert m["rows_within"] == 1.0, m
+
+
+@pytest.mark.parametrize("cfg", [(1, 75, 108, 200, 3, 1, 0, 500.0), (3, 120, 160, 300, 3, 3, 7, 0.0), (2, 97, 333, 513, 5, 5, 0, 0.0)],
+                         ids=lambda c: f"{c[0]}x{c[1]}x{c[2]}-b{c[4]}r{c[5]}")
+def test_detector_is_deterministic(cfg):
+    """Candidate lists are filled with atomics in arbitrary order; the keypoints must not depend on that order.
+    The same input 60 times, interleaved with a call of another shape (workspace reuse), bit-identical every time."""
+    B, H, W, K, bs, r, margin, thr = cfg
+    img = O.texture_images(B, H, W, seed=77)[0].to(DEV)
+    other = img[:, :, : H // 2, : W // 2].contiguous()
+    k0, s0 = _ops.detect(img, K, bs, r, thr, margin)
+    for it in range(60):
+        if it % 3 == 0:
+            _ops.detect(other, 7, 3, 3, 0.0, 0)
+        k, s = _ops.detect(img, K, bs, r, thr, margin)
+        assert torch.equal(k, k0) and torch.equal(s, s0), it
+
+
 def test_constant_image_has_no_keypoints():
     g = G.load("sparse_constant_image")
     model = om.ShiTomasiSparseBADSinkhornMatcher(g["K"]).to(DEV)
