@@ -207,11 +207,14 @@ int om_match_pairs_f32(const om_match_params* p, const float* image1, const floa
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 
-/* Stencil kernel selection: 0 = default routing (block 3/5: register sweep kernel for radius 3, tiled
- * shared-memory kernel for radius 5), 1 = generic (runtime block size / radius) kernel, 2 = tiled kernel,
- * 3 = sweep kernel; lets the tests check them against each other. */
+/* Stencil kernel selection: 0 = default routing (block 3 / radius 3: split register-sweep kernels, i.e. a score
+ * kernel and an NMS kernel; other block 3/5, radius 3/5: tiled shared-memory kernel), 1 = generic (runtime block
+ * size / radius) kernel, 2 = tiled kernel, 3 = fused sweep kernel, 4 = split sweep kernels; lets the tests check
+ * them against each other. */
 void om_debug_force_generic_stencil(int on);
-/* Sweep-kernel tuning: output rows per tile (0 = default 40) and resident CTAs per SM (3, or 4 = default). */
+/* Sweep-kernel tuning.  min_blocks 3 or 4: fused sweep kernel, output rows per tile (0 = default 40) and resident
+ * CTAs per SM.  min_blocks 99: split kernels, strip_rows for both; 100 + n: strip_rows for the score kernel, n rows
+ * for the NMS kernel.  (0, 0) restores every default. */
 void om_debug_sweep_tuning(int strip_rows, int min_blocks);
 
 /* Route om_sinkhorn_f32 / the fused matcher through the generic global-memory Sinkhorn kernels

@@ -50,12 +50,12 @@ def test_score_map_bit_exact(block_size, shape):
 @pytest.mark.parametrize("block_size,nms_radius", [(3, 3), (3, 5), (5, 3), (5, 5)])
 @pytest.mark.parametrize("shape", [(2, 150, 210), (1, 97, 333), (1, 41, 112), (3, 200, 640)])
 def test_fast_and_generic_stencil_agree(block_size, nms_radius, shape):
-    """default routing (0) vs generic kernel (1) vs tiled shared-memory kernel (2) vs sweep kernel (3): scores,
-    keypoints and keypoint scores must be identical, on widths that are / are not multiples of 4 and of the tile width."""
+    """default routing (0) vs generic kernel (1) vs tiled shared-memory kernel (2) vs fused sweep kernel (3) vs split
+    sweep kernels (4): scores, keypoints and keypoint scores must be identical, on widths that are / are not multiples of 4 and of the tile width."""
     img, _ = O.texture_images(*shape, seed=7)
     lib = _native.lib()
     outs = []
-    for force in (0, 1, 2, 3):
+    for force in (0, 1, 2, 3, 4):
         lib.om_debug_force_generic_stencil(force)
         try:
             sc = om.ShiTomasiScore(block_size).to(DEV)(img.to(DEV))

@@ -18,15 +18,16 @@ BS, R = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3, 3)
 def run():
     nat.check(lib.om_debug_detect_stage(p(img), B, H, W, BS, R, 7, 0.0, K, p(kp), p(ks), p(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream), 0), "stage")
 print("block", BS, "radius", R)
-for strip, minb in [(40, 3), (40, 4), (60, 3), (30, 4), (48, 4)]:
+for strip, minb in [(40, 3), (40, 4), (60, 3), (30, 4), (48, 4), (24, 99), (16, 99), (20, 99), (16, 124), (24, 116), (24, 132), (32, 124), (12, 124), (24, 140)]:   # 99 = split score/NMS kernels
     lib.om_debug_sweep_tuning(strip, minb)
+    lib.om_debug_force_generic_stencil(4 if minb >= 99 else 3)
     for _ in range(3): run()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); a.record()
     for _ in range(20): run()
     b.record(); torch.cuda.synchronize()
     print(f"strip {strip:4d} minb {minb}: {a.elapsed_time(b) / 20 * 1000:.1f} us")
-lib.om_debug_sweep_tuning(40, 4)
+lib.om_debug_sweep_tuning(0, 0)
 for mode, name in ((2, "tiled shared-memory kernel"), (1, "generic kernel")):
     lib.om_debug_force_generic_stencil(mode)
     for _ in range(3): run()
@@ -36,3 +37,11 @@ for mode, name in ((2, "tiled shared-memory kernel"), (1, "generic kernel")):
     b.record(); torch.cuda.synchronize()
     print(f"{name}: {a.elapsed_time(b) / 10 * 1000:.1f} us")
 lib.om_debug_force_generic_stencil(0)
+
+# default routing
+for _ in range(3): run()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); a.record()
+for _ in range(20): run()
+b.record(); torch.cuda.synchronize()
+print(f"default routing: {a.elapsed_time(b) / 20 * 1000:.1f} us")
