@@ -70,6 +70,7 @@ SIGNATURES = {
                                      c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "om_debug_force_generic_stencil": (None, [c_int]),
     "om_debug_sweep_tuning": (None, [c_int, c_int]),
+    "om_debug_nms_variant": (None, [c_int]),
     "om_debug_force_generic_sinkhorn": (None, [c_int]),
     "om_debug_sinkhorn_variant": (None, [c_int]),
     "om_debug_sinkhorn_trace": (None, [c_void_p]),

@@ -38,6 +38,18 @@ for mode, name in ((2, "tiled shared-memory kernel"), (1, "generic kernel")):
     print(f"{name}: {a.elapsed_time(b) / 10 * 1000:.1f} us")
 lib.om_debug_force_generic_stencil(0)
 
+# NMS kernel variants of the split form
+for v, name in ((0, "any-radius nms_sweep_kernel"), (2, "nms3 at 6 CTAs/SM"), (1, "nms3 at 5 CTAs/SM (default)")):
+    lib.om_debug_nms_variant(v)
+    for strip_b in (24, 32, 48, 64):
+        lib.om_debug_sweep_tuning(24, 100 + strip_b)
+        for _ in range(3): run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record()
+        for _ in range(20): run()
+        b.record(); torch.cuda.synchronize()
+        print(f"{name}, NMS strip {strip_b}: {a.elapsed_time(b) / 20 * 1000:.1f} us")
+lib.om_debug_sweep_tuning(0, 0)
 # default routing
 for _ in range(3): run()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
