@@ -215,6 +215,9 @@ void om_debug_force_generic_stencil(int on);
 /* NMS kernel of the split sweep form at radius 3: 1 = nms3_sweep_kernel (default), 2 = the same at 6 CTAs per SM,
  * 0 = the any-radius nms_sweep_kernel (cross-check). */
 void om_debug_nms_variant(int v);
+/* Score kernel of the split sweep form at block size 3: 1 = score3_sweep_kernel (default), 2 = the same at 6 CTAs
+ * per SM, 0 = stencil_sweep_kernel<.., NMS = false> (cross-check). */
+void om_debug_score_variant(int v);
 /* Sweep-kernel tuning.  min_blocks 3 or 4: fused sweep kernel, output rows per tile (0 = default 40) and resident
  * CTAs per SM.  min_blocks 99: split kernels, strip_rows for both; 100 + n: strip_rows for the score kernel, n rows
  * for the NMS kernel.  (0, 0) restores every default. */

@@ -55,16 +55,19 @@ def test_fast_and_generic_stencil_agree(block_size, nms_radius, shape):
     img, _ = O.texture_images(*shape, seed=7)
     lib = _native.lib()
     outs = []
-    # (stencil routing, NMS kernel variant of the split form: 1 radius-3 kernel, 2 same at 6 CTAs/SM, 0 any-radius kernel)
-    for force, nms in ((0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (4, 0), (4, 2)):
+    # (stencil routing, NMS kernel variant of the split form: 1 radius-3 kernel, 2 same at 6 CTAs/SM, 0 any-radius kernel,
+    #  score kernel variant of the split form: 1 block-3 kernel, 2 same at 6 CTAs/SM, 0 sweep kernel without its NMS half)
+    for force, nms, score in ((0, 1, 1), (1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (4, 0, 0), (4, 2, 2), (4, 0, 1), (4, 1, 0)):
         lib.om_debug_force_generic_stencil(force)
         lib.om_debug_nms_variant(nms)
+        lib.om_debug_score_variant(score)
         try:
             sc = om.ShiTomasiScore(block_size).to(DEV)(img.to(DEV))
             k, s = _ops.detect(img.to(DEV), 300, block_size, nms_radius, 0.0, 4)
         finally:
             lib.om_debug_force_generic_stencil(0)
             lib.om_debug_nms_variant(1)
+            lib.om_debug_score_variant(1)
         outs.append((sc.cpu(), k.cpu(), s.cpu()))
     for other in outs[1:]:
         for a, b in zip(outs[0], other):

@@ -38,18 +38,23 @@ for mode, name in ((2, "tiled shared-memory kernel"), (1, "generic kernel")):
     print(f"{name}: {a.elapsed_time(b) / 10 * 1000:.1f} us")
 lib.om_debug_force_generic_stencil(0)
 
-# NMS kernel variants of the split form
-for v, name in ((0, "any-radius nms_sweep_kernel"), (2, "nms3 at 6 CTAs/SM"), (1, "nms3 at 5 CTAs/SM (default)")):
-    lib.om_debug_nms_variant(v)
-    for strip_b in (24, 32, 48, 64):
-        lib.om_debug_sweep_tuning(24, 100 + strip_b)
-        for _ in range(3): run()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); a.record()
-        for _ in range(20): run()
-        b.record(); torch.cuda.synchronize()
-        print(f"{name}, NMS strip {strip_b}: {a.elapsed_time(b) / 20 * 1000:.1f} us")
+# kernel variants of the split form (score variant, NMS variant): 0 = generic sweep kernels, 1 = lean kernels at 5 CTAs/SM, 2 = at 6
+def t_run(n=20):
+    for _ in range(3): run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(n): run()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1000
+lib.om_debug_force_generic_stencil(4)
+for sv, nv in ((0, 0), (0, 1), (1, 1), (2, 1), (1, 2), (2, 2)):
+    lib.om_debug_score_variant(sv); lib.om_debug_nms_variant(nv)
+    for strip_a, strip_b in ((24, 32), (32, 32), (40, 32), (48, 32), (60, 32), (32, 64), (60, 64)):
+        lib.om_debug_sweep_tuning(strip_a, 100 + strip_b)
+        print(f"score variant {sv}, NMS variant {nv}, strips {strip_a}/{strip_b}: {t_run():.1f} us")
+lib.om_debug_score_variant(1); lib.om_debug_nms_variant(1)
 lib.om_debug_sweep_tuning(0, 0)
+lib.om_debug_force_generic_stencil(0)
 # default routing
 for _ in range(3): run()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
