@@ -299,15 +299,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     with torch.no_grad():
         # clock ramp: a fresh process finds the GPU at idle clocks and three 1 ms steps do not bring them up (measured:
         # 1.35 instead of 1.07 ms/step in the first bench of a box); run untimed steps for 0.3 s before the W warm-ups
+        # every untimed step keeps its result alive exactly like the timed loop does (`out = model(...)`), so that the
+        # caching allocator has all blocks of the steady state before the timed region (a cudaMalloc inside it was
+        # measured as 0.3 ... 7 ms/step of noise)
+        out = None
         t_ramp = time.perf_counter()
         while time.perf_counter() - t_ramp < 0.3:
-            model(d1, d2)
+            out = model(d1, d2)
             torch.cuda.synchronize()
         for _ in range(max(args.warmup, 3) - 1):
-            model(d1, d2)
+            out = model(d1, d2)
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record(stream)
-        model(d1, d2)                            # last warm-up step, timed to know how long the timed region will be
+        out = model(d1, d2)                      # last warm-up step, timed to know how long the timed region will be
         w1.record(stream)
         barrier()
         est_s = w0.elapsed_time(w1) * 1e-3 * args.steps
@@ -334,8 +338,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- end to end through the host API -----------------------------------------------------
     def time_e2e(a1, a2, join, chunk):
         hb = HostBatchMatcher(model, chunk=max(1, min(chunk, B)), n_streams=4, depth=2, join=join)
+        res = None
         for _ in range(3):
-            hb(a1, a2)
+            res = hb(a1, a2)                     # results kept alive as in the timed loop (allocator steady state)
         hb.synchronize()
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)

@@ -925,7 +925,25 @@ __device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long k
     const bool interior = iy0 >= 15 && iy0 + 1 + 14 <= H - 1 && ix0 >= 15 && ix0 + 1 + 14 <= W - 1;
     const char* lbytes = reinterpret_cast<const char*>(L);
     auto ldl = [&](unsigned int byte_off) -> float { return *reinterpret_cast<const float*>(lbytes + byte_off); };
-    if (interior) {
+    if (interior && w == 0.0f && s == 0.0f) {
+        // keypoint on the pixel grid (every detector output): the weights are exactly {1, 0, 0, 0}, one neighbour, no
+        // per-neighbour tests; 0 + value * 1 of the general path is value (up to the sign of a zero)
+#pragma unroll
+        for (int q = 0; q < MAXPP; ++q) {
+            const int p = t + q * TPG;
+            d[q] = 0.0f;
+            if (p < a.P) {
+                const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+                const float4 tb = sThr[p];
+                const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(ta.x), ldl(ta.y)), ldl(ta.z)), ldl(ta.w));
+                const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(tc.x), ldl(tc.y)), ldl(tc.z)), ldl(tc.w));
+                const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));           // bad.py:99, :110
+                const float v = __fadd_rn(0.0f, finish_value(diff, tb.x, a.mode, a.temperature));
+                d[q] = v;
+                ss = fmaf(v, v, ss);
+            }
+        }
+    } else if (interior) {
 #pragma unroll
         for (int q = 0; q < MAXPP; ++q) {
             const int p = t + q * TPG;
