@@ -174,6 +174,21 @@ int om_mutual_matches_f32(const float* probs, const float* kpts1, const float* k
                           int max_matches, float threshold, float* matched_kpts1, float* matched_kpts2,
                           float* scores, unsigned char* valid, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- essential-matrix head --------------------------------------------------------------- */
+
+/* Weighted 8-point essential matrix from the Sinkhorn matrix, one 3x3 per pair (the reference handles one pair per
+ * call): EssentialMatrixEstimator.forward, geometry/essential_matrix_estimator.py:292-392 (grid points, valid1 = valid2
+ * = NULL, pts_batched = 0: one point set for all pairs) and _estimate_essential_matrix,
+ * feature_detection/shi_tomasi_angle_sparse_bad_sinkhorn_essential_matrix.py:184-271 (keypoints, validity masks,
+ * pts_batched = 1).  probs (B,N+1,M+1); pts1 (B|1,N,2), pts2 (B|1,M,2): normalised (x, y) = K^-1 [x, y, 1];
+ * valid1 (B,N), valid2 (B,M): bytes 0/1, both or neither; E (B,3,3).  Bidirectional top_k mask AND P > 0.01, Hartley
+ * normalisation, 9x9 normal equations, n_iter shifted power iterations, denormalisation, projection onto singular
+ * values (s, s, 0) with n_iter_manifold power iterations.  Limits: top_k <= 8, N, M <= 8192; top_k > N or M is
+ * OM_ERR_SHAPE (torch.topk raises). */
+int om_essential_matrix_f32(const float* probs, const float* pts1, const float* pts2, const unsigned char* valid1,
+                            const unsigned char* valid2, int B, int N, int M, int pts_batched, int top_k, int n_iter,
+                            int n_iter_manifold, float* E, void* stream);
+
 /* ---- fused matcher ----------------------------------------------------------------------- */
 
 typedef struct om_match_params {

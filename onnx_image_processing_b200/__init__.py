@@ -9,6 +9,7 @@ from .descriptor import BADDescriptor, SparseBAD
 from .orientation import AngleEstimator
 from .matching import SinkhornMatcher, SinkhornMatcherWithScores, SinkhornMatcherWithFilters, MutualNearestNeighborMatcher
 from .utils import apply_nms_maxpool, select_topk_keypoints
+from .geometry import EssentialMatrixEstimator
 from .feature_detection import (
     ShiTomasiBADDetector,
     ShiTomasiBADSinkhornMatcher,
@@ -19,6 +20,7 @@ from .feature_detection import (
     ShiTomasiAngleSparseBADSinkhornMatcher,
     ShiTomasiAngleSparseBADSinkhornMatcherWithFilters,
     MatchExtractionWrapper,
+    ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix,
 )
 
 __all__ = [
@@ -27,5 +29,6 @@ __all__ = [
     "ShiTomasiBADSinkhornMatcher", "ShiTomasiSparseBADSinkhornMatcher", "ShiTomasiWithAngle",
     "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector", "ShiTomasiAngleSparseBADSinkhornMatcher",
     "MutualNearestNeighborMatcher", "MatchExtractionWrapper", "SinkhornMatcherWithFilters",
-    "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters",
+    "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters", "EssentialMatrixEstimator",
+    "ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix",
 ]

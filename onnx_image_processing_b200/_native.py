@@ -58,6 +58,8 @@ SIGNATURES = {
     "om_sinkhorn_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "om_sinkhorn_filter_rows_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "om_essential_matrix_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_void_p]),
     "om_mutual_matches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "om_mutual_matches_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -306,6 +306,38 @@ def _(probs, keypoints1, keypoints2, max_matches, threshold):
             probs.new_empty((B, max_matches), dtype=torch.float32), probs.new_empty((B, max_matches), dtype=torch.bool))
 
 
+@torch.library.custom_op("b200match::essential_matrix", mutates_args=(), device_types="cuda")
+def essential_matrix(probs: torch.Tensor, pts1: torch.Tensor, pts2: torch.Tensor, valid1: Optional[torch.Tensor],
+                     valid2: Optional[torch.Tensor], top_k: int, n_iter: int, n_iter_manifold: int) -> torch.Tensor:
+    """probs (B,N+1,M+1); pts1 (B,N,2) or (N,2), pts2 (B,M,2) or (M,2): normalised (x, y); valid1/2 (B,N)/(B,M) bool or
+    None -> E (B,3,3)."""
+    p = _f32(probs, "P")
+    a, b = _f32(pts1, "pts1"), _f32(pts2, "pts2")
+    B, N, M = int(p.shape[0]), int(p.shape[1]) - 1, int(p.shape[2]) - 1
+    batched = a.dim() == 3
+    if (b.dim() == 3) != batched or tuple(a.shape[-2:]) != (N, 2) or tuple(b.shape[-2:]) != (M, 2) or \
+            (batched and (a.shape[0] != B or b.shape[0] != B)):
+        raise RuntimeError(f"points must be ([B,]{N},2) and ([B,]{M},2) for P {tuple(p.shape)}, got {tuple(a.shape)}, {tuple(b.shape)}")
+    if top_k > min(N, M):
+        raise RuntimeError("selected index k out of range")              # torch.topk's message
+    v1 = v2 = None
+    if valid1 is not None:
+        v1 = valid1.to(device=p.device, dtype=torch.uint8).contiguous()
+        v2 = valid2.to(device=p.device, dtype=torch.uint8).contiguous()
+        if tuple(v1.shape) != (B, N) or tuple(v2.shape) != (B, M):
+            raise RuntimeError(f"valid masks must be ({B},{N}) and ({B},{M}), got {tuple(v1.shape)}, {tuple(v2.shape)}")
+    lib, st = _begin(p)
+    E = torch.empty((B, 3, 3), dtype=torch.float32, device=p.device)
+    nat.check(lib.om_essential_matrix_f32(_p(p), _p(a), _p(b), _p(v1), _p(v2), B, N, M, int(batched), int(top_k), int(n_iter),
+                                          int(n_iter_manifold), _p(E), st), "om_essential_matrix_f32")
+    return E
+
+
+@essential_matrix.register_fake
+def _(probs, pts1, pts2, valid1, valid2, top_k, n_iter, n_iter_manifold):
+    return probs.new_empty((probs.shape[0], 3, 3), dtype=torch.float32)
+
+
 def make_match_params(flavour: int, B: int, H: int, W: int, K: int, block_size: int, nms_radius: int,
                       border_margin: int, score_threshold: float, P: int, mode: int, temperature: float,
                       normalize: bool, sampling: int, patch_size: int, iterations: int, epsilon: float,

@@ -4,11 +4,12 @@ from .shi_tomasi_sparse_bad_sinkhorn import ShiTomasiSparseBADSinkhornMatcher
 from .shi_tomasi_angle import ShiTomasiWithAngle, ShiTomasiAngleSparseBAD, ShiTomasiAngleSparseBADDetector
 from .shi_tomasi_angle_sparse_bad_sinkhorn import (ShiTomasiAngleSparseBADSinkhornMatcher,
                                                    ShiTomasiAngleSparseBADSinkhornMatcherWithFilters)
+from .shi_tomasi_angle_sparse_bad_sinkhorn_essential_matrix import ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix
 from .match_extraction_wrapper import MatchExtractionWrapper
 
 __all__ = [
     "ShiTomasiBADDetector", "ShiTomasiBADSinkhornMatcher", "ShiTomasiSparseBADSinkhornMatcher",
     "ShiTomasiWithAngle", "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector",
     "ShiTomasiAngleSparseBADSinkhornMatcher", "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters",
-    "MatchExtractionWrapper",
+    "MatchExtractionWrapper", "ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix",
 ]

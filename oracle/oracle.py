@@ -333,6 +333,102 @@ def mutual_matches(P: torch.Tensor, keypoints1: torch.Tensor, keypoints2: torch.
     return mk1, mk2, ss, ss > 0.0                                        # :181-184
 
 
+# --------------------------------------------------------------------------------------
+# essential-matrix head: geometry/essential_matrix_estimator.py,
+# feature_detection/shi_tomasi_angle_sparse_bad_sinkhorn_essential_matrix.py:184-271
+# --------------------------------------------------------------------------------------
+def _det3(M):
+    """geometry/essential_matrix_estimator.py:126-130"""
+    return (M[0, 0] * (M[1, 1] * M[2, 2] - M[1, 2] * M[2, 1]) - M[0, 1] * (M[1, 0] * M[2, 2] - M[1, 2] * M[2, 0])
+            + M[0, 2] * (M[1, 0] * M[2, 1] - M[1, 1] * M[2, 0]))
+
+
+def _hartley(pts, w):
+    """weighted centroid / RMS-distance normalisation, essential_matrix_estimator.py:242-290"""
+    w_sum = w.sum() + 1e-8
+    c = (w.unsqueeze(-1) * pts).sum(dim=0) / w_sum
+    d2 = ((pts - c) ** 2).sum(dim=-1)
+    mean_dist = torch.sqrt((w * d2).sum() / w_sum + 1e-8)
+    s = math.sqrt(2.0) / (mean_dist + 1e-8)
+    z, o = torch.zeros((), dtype=pts.dtype), torch.ones((), dtype=pts.dtype)
+    T = torch.stack([torch.stack([s, z, -s * c[0]]), torch.stack([z, s, -s * c[1]]), torch.stack([z, z, o])])
+    return T, s, c
+
+
+def essential_weights(P, valid1=None, valid2=None, top_k=3):
+    """Pair weights: validity masking (..._essential_matrix.py:212-219), bidirectional top-k mask AND P > 0.01
+    (:221-239; the grid form: essential_matrix_estimator.py:307-330)."""
+    N, M = P.shape[0] - 1, P.shape[1] - 1
+    core = P[:N, :M]
+    if valid1 is not None:
+        core = core * valid1.to(core).unsqueeze(1) * valid2.to(core).unsqueeze(0)
+    thr_row = torch.topk(core, k=top_k, dim=1).values[:, top_k - 1:top_k]
+    thr_col = torch.topk(core, k=top_k, dim=0).values[top_k - 1:top_k, :]
+    mask = (core >= thr_row) & (core >= thr_col) & (core > 0.01)
+    return core * mask.to(core.dtype)
+
+
+def essential_matrix(P, pts1_n, pts2_n, valid1=None, valid2=None, top_k=3, n_iter=30, n_iter_manifold=10,
+                     dtype=torch.float32):
+    """Weighted 8-point essential matrix of ONE pair from its Sinkhorn matrix P (N+1, M+1) and the normalised (x, y)
+    points of both images (..._essential_matrix.py:184-271 == essential_matrix_estimator.py:292-392 with grid points).
+    dtype=float64 gives the same algorithm without float32 rounding (used to size test tolerances)."""
+    P, pts1_n, pts2_n = P.to(dtype), pts1_n.to(dtype), pts2_n.to(dtype)
+    N, M = P.shape[0] - 1, P.shape[1] - 1
+    w = essential_weights(P, valid1, valid2, top_k)
+    T1, s1, c1 = _hartley(pts1_n, w.sum(dim=1))
+    T2, s2, c2 = _hartley(pts2_n, w.sum(dim=0))
+    f1 = torch.cat([(pts1_n - c1) * s1, torch.ones(N, 1, dtype=dtype)], dim=-1)
+    f2 = torch.cat([(pts2_n - c2) * s2, torch.ones(M, 1, dtype=dtype)], dim=-1)
+    F1 = (f1.unsqueeze(-1) * f1.unsqueeze(-2)).reshape(N, 9)
+    F2 = (f2.unsqueeze(-1) * f2.unsqueeze(-2)).reshape(M, 9)
+    M_flat = F1.T @ (w @ F2)                                                     # :249-251
+    M_mat = M_flat.reshape(3, 3, 3, 3).permute(0, 2, 1, 3).reshape(9, 9)
+    # minimum eigenvector by shifted power iteration, essential_matrix_estimator.py:150-172
+    M_s = torch.einsum("ii", M_mat) * torch.eye(9, dtype=dtype) - M_mat
+    v = torch.ones(9, dtype=dtype) / 3.0
+    for _ in range(n_iter):
+        v = M_s @ v
+        v = v / (v.norm() + 1e-8)
+    E = T2.T @ v.reshape(3, 3) @ T1                                              # :259
+    # projection onto singular values (s, s, 0), essential_matrix_estimator.py:174-240
+    B = E.T @ E
+    lam = torch.einsum("ii", B)
+    v1 = torch.ones(3, dtype=dtype) / math.sqrt(3.0)
+    for _ in range(n_iter_manifold):
+        v1 = B @ v1
+        v1 = v1 / (v1.norm() + 1e-8)
+    B_s = lam * torch.eye(3, dtype=dtype) - B
+    v3 = torch.ones(3, dtype=dtype) / math.sqrt(3.0)
+    for _ in range(n_iter_manifold):
+        v3 = B_s @ v3
+        v3 = v3 / (v3.norm() + 1e-8)
+    v2 = torch.linalg.cross(v3, v1)
+    v2 = v2 / (v2.norm() + 1e-8)
+    V = torch.stack([v1, v2, v3], dim=-1)
+    V = V @ torch.diag(torch.stack([torch.ones((), dtype=dtype), torch.ones((), dtype=dtype), torch.sign(_det3(V))]))
+    sigma1, sigma2 = (E @ V[:, 0]).norm(), (E @ V[:, 1]).norm()
+    s_avg = (sigma1 + sigma2) / 2.0
+    u1, u2 = E @ V[:, 0] / (sigma1 + 1e-8), E @ V[:, 1] / (sigma2 + 1e-8)
+    U = torch.stack([u1, u2, torch.linalg.cross(u1, u2)], dim=-1)
+    U = U @ torch.diag(torch.stack([torch.ones((), dtype=dtype), torch.ones((), dtype=dtype), torch.sign(_det3(U))]))
+    return U @ torch.diag(torch.stack([s_avg, s_avg, torch.zeros((), dtype=dtype)])) @ V.T
+
+
+def normalised_points(keypoints_yx, K_inv):
+    """(y, x) pixel keypoints -> (x, y) normalised image coordinates, ..._essential_matrix.py:341-352"""
+    xy = torch.stack([keypoints_yx[:, 1], keypoints_yx[:, 0]], dim=-1)
+    return (torch.cat([xy, torch.ones(xy.shape[0], 1, dtype=xy.dtype)], dim=-1) @ K_inv.T.to(xy))[:, :2]
+
+
+def grid_points(n, image_shape, K_inv):
+    """essential_matrix_estimator.py:85-105: feature i sits at pixel (i % W, i // W)"""
+    H, W = image_shape
+    idx = torch.arange(H * W, dtype=torch.float32)
+    h = torch.stack([idx % W, idx // W, torch.ones(H * W)], dim=-1)
+    return (h @ K_inv.T)[:n, :2]
+
+
 def detect(image, max_keypoints, block_size=3, nms_radius=3, score_threshold=0.0, border_margin=0):
     sc = shi_tomasi_score(image, block_size).squeeze(1)
     return select_topk(sc, nms_mask(sc, nms_radius), max_keypoints, score_threshold, border_margin)

@@ -594,3 +594,112 @@ def test_library_reports_launches():
     n0 = _native.launch_count()
     om.ShiTomasiScore(3).to(DEV)(torch.zeros(1, 1, 32, 32, device=DEV))
     assert _native.launch_count() == n0 + 1
+
+
+# ------------------------------------------------------------------------------------------
+# essential-matrix head
+# ------------------------------------------------------------------------------------------
+# float32 rounding of the reference's own sums / matrix products moves E by ~5e-6 of max|E| (oracle float32 vs float64 on
+# the goldens, tests/test_oracle_golden.py); the kernel accumulates the long sums in double, bound: 5e-5 of max|E|
+E_RTOL = 5e-5
+
+
+def _essential_case(g):
+    from tests.test_oracle_golden import _essential_inputs
+    P, p1, p2, v1, v2 = _essential_inputs(g)
+    kw = {k: v for k, v in g["kwargs"].items() if k in ("top_k", "n_iter", "n_iter_manifold")}
+    return P, p1, p2, v1, v2, kw
+
+
+@pytest.mark.parametrize("name", G.names("essential_grid") + G.names("essential_module"))
+def test_essential_matrix_golden(name):
+    """om_essential_matrix_f32 on the reference's own P and points vs the reference's E."""
+    g = G.load(name)
+    P, p1, p2, v1, v2, kw = _essential_case(g)
+    args = dict(top_k=3, n_iter=30, n_iter_manifold=10)
+    args.update(kw)
+    vb = (None, None) if v1 is None else (v1[None].to(DEV), v2[None].to(DEV))
+    E = _ops.essential_matrix(P[None].to(DEV), p1[None].to(DEV), p2[None].to(DEV), vb[0], vb[1], args["top_k"],
+                              args["n_iter"], args["n_iter_manifold"]).cpu()[0]
+    scale = float(g["E"].abs().max())
+    assert float((E - g["E"]).abs().max()) <= E_RTOL * scale, (E, g["E"])
+
+
+@pytest.mark.parametrize("name", G.names("essential_grid"))
+def test_essential_estimator_module(name):
+    """EssentialMatrixEstimator: same ctor / buffers / forward(P) as the reference; a batch of matrices gives the same
+    3x3 per matrix as one call each (the reference has no batch form)."""
+    g = G.load(name)
+    shape = tuple(int(v) for v in g["image_shape"])
+    est = om.EssentialMatrixEstimator(g["K"], image_shape=shape, **g["kwargs"]).to(DEV)
+    assert set(dict(est.named_buffers())) == {"K", "K_inv", "pixel_coords", "pixel_coords_n"}
+    E = est(g["P"].to(DEV)).cpu()
+    assert E.shape == (3, 3)
+    assert float((E - g["E"]).abs().max()) <= E_RTOL * float(g["E"].abs().max())
+    gen = torch.Generator().manual_seed(11)
+    Pb = torch.rand((5,) + tuple(g["P"].shape), generator=gen)
+    Pb[2] = g["P"]
+    Eb = est(Pb.to(DEV)).cpu()
+    assert Eb.shape == (5, 3, 3) and torch.equal(Eb[2], E)
+    for b in (0, 4):
+        assert torch.equal(est(Pb[b].to(DEV)).cpu(), Eb[b])
+        K_inv = torch.linalg.inv(g["K"])
+        ref = O.essential_matrix(Pb[b], O.grid_points(Pb.shape[1] - 1, shape, K_inv), O.grid_points(Pb.shape[2] - 1, shape, K_inv),
+                                 dtype=torch.float64, **g["kwargs"])
+        assert float((Eb[b].double() - ref).abs().max()) <= E_RTOL * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("name", G.names("essential_module"))
+def test_essential_matcher_module(name):
+    """ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix end to end: keypoints as the reference's, P within the Sinkhorn
+    bar, and E equal to the oracle's head evaluated on the kernel's own (keypoints, P) -- that isolates the head from the
+    1e-6-level differences of P, which can move a probability across the 0.01 / top-k mask of the reference run."""
+    g = G.load(name)
+    K = int(g["max_keypoints"])
+    model = om.ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix(g["K"], K, **g["kwargs"]).to(DEV).eval()
+    names = set(dict(model.named_buffers()))
+    assert {"K_inv", "estimator.K", "estimator.K_inv", "estimator.pixel_coords", "estimator.pixel_coords_n"} <= names
+    with torch.no_grad():
+        k1, k2, P, E = model(g["image1"].to(DEV), g["image2"].to(DEV))
+    k1, k2, P, E = k1.cpu(), k2.cpu(), P.cpu(), E.cpu()
+    assert E.shape == (3, 3) and P.shape == g["P"].shape
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    m = PR.prob_metrics(P, g["P"])
+    assert PR.probs_ok(m), m
+    K_inv = torch.linalg.inv(g["K"])
+    kw = {k: v for k, v in g["kwargs"].items() if k in ("top_k", "n_iter", "n_iter_manifold")}
+    ref = O.essential_matrix(P[0], O.normalised_points(k1[0], K_inv), O.normalised_points(k2[0], K_inv), k1[0, :, 0] >= 0,
+                             k2[0, :, 0] >= 0, dtype=torch.float64, **kw)
+    scale = float(ref.abs().max())
+    assert scale > 1.0 and float((E.double() - ref).abs().max()) <= E_RTOL * scale
+    # and against the reference run itself, loosely (mask flips excluded by the bound above, not here)
+    assert float((E - g["E"]).abs().max()) <= 2e-2 * float(g["E"].abs().max())
+
+
+def test_essential_matcher_batched_and_degenerate():
+    """B > 1 pairs give (B,3,3), each equal to the pair run alone; the default epsilon at K = 512 leaves every probability
+    below the 0.01 threshold, which must give E = 0 (no NaN), as in the reference."""
+    Kc = torch.tensor([[525.0, 0.0, 320.0], [0.0, 525.0, 240.0], [0.0, 0.0, 1.0]])
+    i1, i2 = O.texture_images(3, 120, 160, seed=21)
+    model = om.ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix(Kc, 64).to(DEV).eval()
+    with torch.no_grad():
+        _, _, Pb, Eb = model(i1.to(DEV), i2.to(DEV))
+        assert Eb.shape == (3, 3, 3) and bool(torch.isfinite(Eb).all())
+        for b in range(3):
+            _, _, _, E1 = model(i1[b:b + 1].to(DEV), i2[b:b + 1].to(DEV))
+            assert E1.shape == (3, 3) and torch.equal(E1, Eb[b])
+        big = om.ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix(Kc, 512).to(DEV).eval()
+        j1, j2 = O.texture_images(1, 480, 640, seed=22)
+        _, _, P, E = big(j1.to(DEV), j2.to(DEV))
+        assert float(P[0, :512, :512].max()) < 0.01 and torch.equal(E.cpu(), torch.zeros(3, 3))
+
+
+def test_essential_matrix_argument_errors():
+    P = torch.rand(1, 9, 9, device=DEV)
+    pts = torch.rand(1, 8, 2, device=DEV)
+    with pytest.raises(RuntimeError):
+        _ops.essential_matrix(P, pts, pts, None, None, 9, 30, 10)          # top_k > N: torch.topk raises in the reference
+    with pytest.raises(RuntimeError):
+        _ops.essential_matrix(P, pts[:, :7], pts, None, None, 3, 30, 10)
+    with pytest.raises(RuntimeError):
+        om.EssentialMatrixEstimator(torch.eye(3), image_shape=(2, 2)).to(DEV)(P[0])   # grid smaller than N

@@ -102,6 +102,45 @@ def test_filter_rows(name):
     assert torch.equal(pf[:, :N, -1], g["dust_col"]) and torch.equal(pf.sum(dim=2), g["row_sums"])
 
 
+def _essential_inputs(g):
+    """(P, pts1_n, pts2_n, valid1, valid2) of one essential-matrix golden, batch dimension stripped."""
+    K_inv = torch.linalg.inv(g["K"])
+    if g["kind"] == "essential_grid":
+        P = g["P"]
+        shape = tuple(int(v) for v in g["image_shape"])
+        return P, O.grid_points(P.shape[0] - 1, shape, K_inv), O.grid_points(P.shape[1] - 1, shape, K_inv), None, None
+    k1, k2 = g["kpts1"][0], g["kpts2"][0]
+    return g["P"][0], O.normalised_points(k1, K_inv), O.normalised_points(k2, K_inv), k1[:, 0] >= 0, k2[:, 0] >= 0
+
+
+@pytest.mark.parametrize("name", G.names("essential_grid") + G.names("essential_module"))
+def test_essential_matrix(name):
+    """oracle.essential_matrix vs the reference's EssentialMatrixEstimator / ...WithEssentialMatrix head (goldens minted by
+    make_golden_essential.py): the float32 restatement agrees to float rounding of the sums, the float64 one to the
+    float32 error of the reference itself (5e-6 of max|E| measured; bound 5e-5)."""
+    g = G.load(name)
+    P, p1, p2, v1, v2 = _essential_inputs(g)
+    kw = {k: v for k, v in g["kwargs"].items() if k in ("top_k", "n_iter", "n_iter_manifold")}
+    E32 = O.essential_matrix(P, p1, p2, v1, v2, **kw)
+    E64 = O.essential_matrix(P, p1, p2, v1, v2, dtype=torch.float64, **kw)
+    scale = float(g["E"].abs().max())
+    assert scale > 1.0
+    assert float((E32 - g["E"]).abs().max()) <= 1e-5 * scale
+    assert float((E64 - g["E"].double()).abs().max()) <= 5e-5 * scale
+    # on the manifold: singular values (s, s, 0)
+    sv = torch.linalg.svdvals(g["E"].double())
+    assert float(sv[2]) <= 1e-4 * float(sv[0]) and abs(float(sv[0] - sv[1])) <= 1e-4 * float(sv[0])
+
+
+def test_essential_matrix_no_weights():
+    """every probability below the 0.01 threshold (the default epsilon = 1 at K = 512 does this): weights are all zero
+    and the guarded divisions give E = 0 without NaN, as the reference does."""
+    P = torch.full((33, 33), 0.005)
+    pts = O.grid_points(32, (8, 8), torch.eye(3))
+    E = O.essential_matrix(P, pts, pts)
+    assert torch.equal(E, torch.zeros(3, 3))
+
+
 def test_constant_image():
     g = G.load("sparse_constant_image")
     with torch.no_grad():
