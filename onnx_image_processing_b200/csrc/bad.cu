@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "pair_order.inc"
 
 namespace om {
 
@@ -400,13 +401,68 @@ __device__ __forceinline__ bool win_needed(const SparseArgs& a, long long kidx, 
     return ky >= 0.0f && a.flags[z] == 0u;
 }
 
-// one keypoint whose window `win` is in flight / has landed on mbarrier `bar` (phase `parity`)
+// per-keypoint context of the general (border / oriented / bilinear) pair evaluation
+struct SparseKpCtx {
+    const unsigned int* Wn;      // window column 0
+    float yc, xc, ct, st;        // clamped keypoint, cos / sin of its orientation
+    int iy0, ix0;                // rounded keypoint
+    float sy, sx;                // grid_sample scales
+    int H, W;
+};
+
+// One pair at one keypoint through the full sampling pipeline (bad.py:504-557).  Kept out of line: inlined into the
+// unrolled pair loop it made the kernel several hundred KB of code, and the kernels stalled on instruction fetch.
 template <int HS, bool ORIENTED, bool BILINEAR>
+__device__ __noinline__ float sparse_pair_general(const SparseKpCtx& c, const float* table, int p, int mode, float temperature) {
+    using G = WinGeom<HS>;
+    constexpr int S = G::S, WP = G::WP;
+    const int H = c.H, W = c.W;
+    const float hy = (float)(H - 1) * 0.5f, hx = (float)(W - 1) * 0.5f;
+    const float my = (float)(H - 1), mx = (float)(W - 1);
+    const unsigned int* Wn = c.Wn;
+    auto box_mean = [&](int cy, int cx, int r, float inv_area) -> float {
+        // cy,cx: integer sample centre in image coords (already clipped to the image by grid_sample's
+        // border mode); the box may reach into the replicate padding, which the integral contains
+        const int wy = clampi(cy - c.iy0 + HS, r, S - 1 - r), wx = clampi(cx - c.ix0 + HS, r, S - 1 - r);
+        const int y0 = wy - r, y1 = wy + r + 1, x0 = wx - r, x1 = wx + r + 1;
+        const unsigned int s = (Wn[y1 * WP + x1] - Wn[y0 * WP + x1]) - (Wn[y1 * WP + x0] - Wn[y0 * WP + x0]);
+        return __fmul_rn((float)s, inv_area);
+    };
+    auto sample = [&](float oy, float ox, int r, float inv_area) -> float {
+        float py, px;
+        if (ORIENTED) {                                                     // bad.py:504-517
+            const float dy = __fadd_rn(__fmul_rn(ox, c.st), __fmul_rn(oy, c.ct));
+            const float dx = __fsub_rn(__fmul_rn(ox, c.ct), __fmul_rn(oy, c.st));
+            py = __fadd_rn(c.yc, dy);
+            px = __fadd_rn(c.xc, dx);
+        } else {                                                            // bad.py:518-525
+            py = __fadd_rn(c.yc, oy);
+            px = __fadd_rn(c.xc, ox);
+        }
+        const float uy = sample_coord(py, c.sy, hy, my), ux = sample_coord(px, c.sx, hx, mx);
+        if (!BILINEAR) return box_mean((int)nearbyintf(uy), (int)nearbyintf(ux), r, inv_area);   // half-to-even
+        const float fy = floorf(uy), fx = floorf(ux);
+        const float w = ux - fx, e = 1.0f - w, s = uy - fy, n = 1.0f - s;   // ATen bilinear weights
+        const int y_n = (int)fy, x_w = (int)fx;
+        const int y_s = min(y_n + 1, H - 1), x_e = min(x_w + 1, W - 1);     // weight is 0 where this clamps
+        const float nw = box_mean(y_n, x_w, r, inv_area), ne = box_mean(y_n, x_e, r, inv_area);
+        const float sw = box_mean(y_s, x_w, r, inv_area), se = box_mean(y_s, x_e, r, inv_area);
+        return nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
+    };
+    const PairRow row = load_pair(table, p);
+    const int r = (int)row.r;
+    const float side = (float)(2 * r + 1);
+    const float inv_area = __fdiv_rn(1.0f, side * side);
+    const float diff = __fsub_rn(sample(row.oy1, row.ox1, r, inv_area), sample(row.oy2, row.ox2, r, inv_area));
+    return finish_value(diff, row.thr, mode, temperature);
+}
+
+// one keypoint whose window `win` is in flight / has landed on mbarrier `bar` (phase `parity`).  NPP = pairs per
+// thread (ceil(P / 64)): the pair loops are unrolled over exactly NPP slots.
+template <int HS, bool ORIENTED, bool BILINEAR, int NPP>
 __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long kidx, int z, float ky, float kx,
                                                  const unsigned int* win, uint32_t bar, uint32_t parity, float* red,
                                                  float* sTheta, const uint4* sTap, const float2* sThr, int g, int t) {
-    using G = WinGeom<HS>;
-    constexpr int S = G::S, WP = G::WP;
     constexpr bool FAST = !ORIENTED && !BILINEAR;
     const int H = a.H, W = a.W;
     float* out = a.desc + (size_t)kidx * a.P;
@@ -450,8 +506,7 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
     }
     mbar_wait(bar, parity);                      // window has landed
 
-    constexpr int MAXPP = 8;   // pairs per thread: P <= 512
-    float d[MAXPP];
+    float d[NPP];
     float ss = 0.0f;
     const bool fast = FAST && ky == (float)iy0 && kx == (float)ix0 && iy0 >= 15 && iy0 + 14 <= H - 1 && ix0 >= 15 &&
                       ix0 + 14 <= W - 1;
@@ -459,7 +514,7 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
     auto ldw = [&](unsigned int byte_off) -> unsigned int { return *reinterpret_cast<const unsigned int*>(wbytes + byte_off); };
     if (fast) {
 #pragma unroll
-        for (int q = 0; q < MAXPP; ++q) {
+        for (int q = 0; q < NPP; ++q) {
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
@@ -473,48 +528,14 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
             }
         }
     } else {
-        const float hy = (float)(H - 1) * 0.5f, hx = (float)(W - 1) * 0.5f;
-        const float my = (float)(H - 1), mx = (float)(W - 1);
-        auto box_mean = [&](int cy, int cx, int r, float inv_area) -> float {
-            // cy,cx: integer sample centre in image coords (already clipped to the image by grid_sample's
-            // border mode); the box may reach into the replicate padding, which the integral contains
-            const int wy = clampi(cy - iy0 + HS, r, S - 1 - r), wx = clampi(cx - ix0 + HS, r, S - 1 - r);
-            const int y0 = wy - r, y1 = wy + r + 1, x0 = wx - r, x1 = wx + r + 1;
-            const unsigned int s = (Wn[y1 * WP + x1] - Wn[y0 * WP + x1]) - (Wn[y1 * WP + x0] - Wn[y0 * WP + x0]);
-            return __fmul_rn((float)s, inv_area);
-        };
-        auto sample = [&](float oy, float ox, int r, float inv_area) -> float {
-            float py, px;
-            if (ORIENTED) {                                                     // bad.py:504-517
-                const float dy = __fadd_rn(__fmul_rn(ox, st), __fmul_rn(oy, ct));
-                const float dx = __fsub_rn(__fmul_rn(ox, ct), __fmul_rn(oy, st));
-                py = __fadd_rn(yc, dy);
-                px = __fadd_rn(xc, dx);
-            } else {                                                            // bad.py:518-525
-                py = __fadd_rn(yc, oy);
-                px = __fadd_rn(xc, ox);
-            }
-            const float uy = sample_coord(py, a.sy, hy, my), ux = sample_coord(px, a.sx, hx, mx);
-            if (!BILINEAR) return box_mean((int)nearbyintf(uy), (int)nearbyintf(ux), r, inv_area);   // half-to-even
-            const float fy = floorf(uy), fx = floorf(ux);
-            const float w = ux - fx, e = 1.0f - w, s = uy - fy, n = 1.0f - s;   // ATen bilinear weights
-            const int y_n = (int)fy, x_w = (int)fx;
-            const int y_s = min(y_n + 1, H - 1), x_e = min(x_w + 1, W - 1);     // weight is 0 where this clamps
-            const float nw = box_mean(y_n, x_w, r, inv_area), ne = box_mean(y_n, x_e, r, inv_area);
-            const float sw = box_mean(y_s, x_w, r, inv_area), se = box_mean(y_s, x_e, r, inv_area);
-            return nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
-        };
+        SparseKpCtx c;
+        c.Wn = Wn; c.yc = yc; c.xc = xc; c.ct = ct; c.st = st; c.iy0 = iy0; c.ix0 = ix0; c.sy = a.sy; c.sx = a.sx; c.H = H; c.W = W;
 #pragma unroll
-        for (int q = 0; q < MAXPP; ++q) {
+        for (int q = 0; q < NPP; ++q) {
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                const PairRow row = load_pair(a.table, p);
-                const int r = (int)row.r;
-                const float side = (float)(2 * r + 1);
-                const float inv_area = __fdiv_rn(1.0f, side * side);
-                const float diff = __fsub_rn(sample(row.oy1, row.ox1, r, inv_area), sample(row.oy2, row.ox2, r, inv_area));
-                d[q] = finish_value(diff, row.thr, a.mode, a.temperature);
+                d[q] = sparse_pair_general<HS, ORIENTED, BILINEAR>(c, a.table, p, a.mode, a.temperature);
                 ss = fmaf(d[q], d[q], ss);
             }
         }
@@ -525,7 +546,7 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
         inv = 1.0f / fmaxf(nrm, 1e-12f);
     }
 #pragma unroll
-    for (int q = 0; q < MAXPP; ++q) {
+    for (int q = 0; q < NPP; ++q) {
         const int p = t + q * TPG;
         if (p < a.P) out[p] = d[q] * inv;
     }
@@ -535,8 +556,8 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
 // pipeline, the TMA box of keypoint n+1 is in flight while keypoint n is evaluated; NBUF = 1: one window per group
 // and twice the resident groups instead (measured faster on B200: the kernel is bound by shared-memory wavefronts
 // of the random taps, not by the TMA latency, so more warps beat prefetching).
-template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR, int NBUF>
-__global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_constant__ CUtensorMap tmap, SparseArgs a) {
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR, int NBUF, int NPP>
+__global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __grid_constant__ CUtensorMap tmap, SparseArgs a) {
     using G = WinGeom<HS>;
     constexpr bool FAST = !ORIENTED && !BILINEAR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -593,7 +614,7 @@ __global__ void __launch_bounds__(GROUPS * TPG) sparse_win_kernel(const __grid_c
         float ky, kx;
         int z;
         if (win_needed(a, kidx, ky, kx, z)) {
-            sparse_win_group<HS, ORIENTED, BILINEAR>(a, kidx, z, ky, kx, wbuf + buf * G::GSTRIDE, bar0 + 8u * buf, phase[buf],
+            sparse_win_group<HS, ORIENTED, BILINEAR, NPP>(a, kidx, z, ky, kx, wbuf + buf * G::GSTRIDE, bar0 + 8u * buf, phase[buf],
                                                      red, sTheta, sTap, sThr, g, t);
             phase[buf] ^= 1u;
         } else if (!(ky >= 0.0f)) {                                 // bad.py:461, :570 -> the row is all zeros
@@ -614,13 +635,18 @@ int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t s
     constexpr int NBUF = 1;
     const size_t smem = (size_t)GROUPS * NBUF * G::GSTRIDE * 4 +
                         ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (2 * sizeof(uint4) + sizeof(float2)) : 0);
-    auto kernel = sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF>;
-    OM_TRY(set_smem(kernel, smem));
     const long long total = (long long)a.B * a.K;
     const long long nblk = (total + GROUPS - 1) / GROUPS;
     const int per_sm = (int)(228 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (228 KB, 1 KB reserved per CTA)
     const long long resident = 148ll * (per_sm < 1 ? 1 : per_sm);
-    kernel<<<(unsigned)(nblk < resident ? nblk : resident), GROUPS * TPG, smem, st>>>(tmap, a);
+    const unsigned grid = (unsigned)(nblk < resident ? nblk : resident);
+    auto go = [&](auto kernel) -> int {
+        OM_TRY(set_smem(kernel, smem));
+        kernel<<<grid, GROUPS * TPG, smem, st>>>(tmap, a);
+        return OM_OK;
+    };
+    if (a.P <= 4 * TPG) OM_TRY(go(sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF, 4>));   // pairs per thread
+    else OM_TRY(go(sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF, 8>));
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -871,6 +897,7 @@ struct DenseKpArgs {
     float temperature;
     int normalize;
     float* desc;
+    int dbg;                   // diagnosis: bit 1 = skip the window fetch, bit 2 = skip the pair arithmetic
 };
 
 // Dense-path descriptors at the K keypoints only: bilinear blend of the dense map's values at the
@@ -903,6 +930,33 @@ __device__ __forceinline__ DenseKp dense_kp_pos(float ky, float kx, int H, int W
 }
 
 // one keypoint whose window `Lbox` is in flight / has landed on mbarrier `bar` (phase `parity`)
+// value of one pair at a keypoint near the image border (centre clamps, bad.py:81-82): rare, kept out of line so that the
+// two interior paths stay small
+__device__ __noinline__ float dense_pair_border(const float* table, int pair, const float* L, int H, int W, int oy, int ox,
+                                                int iy0, int ix0, float w0, float w1, float w2, float w3, int mode,
+                                                float temperature) {
+    constexpr int SPAN = DK_SPAN;
+    const PairRow row = load_pair(table, pair);
+    const int r = (int)row.r;
+    const int ys = min(iy0 + 1, H - 1), xe = min(ix0 + 1, W - 1);
+    const int py[4] = {iy0, iy0, ys, ys}, px[4] = {ix0, xe, ix0, xe};
+    const float wgt[4] = {w0, w1, w2, w3};
+    float v = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        if (wgt[k] != 0.0f) {
+            const int c1y = clampi(py[k] + (int)row.oy1, 0, H - 1) + MAXR - oy, c1x = clampi(px[k] + (int)row.ox1, 0, W - 1) + MAXR - ox;
+            const int c2y = clampi(py[k] + (int)row.oy2, 0, H - 1) + MAXR - oy, c2x = clampi(px[k] + (int)row.ox2, 0, W - 1) + MAXR - ox;
+            const float diff = __fsub_rn(dense_box_mean(L, SPAN, c1y, c1x, r), dense_box_mean(L, SPAN, c2y, c2x, r));
+            v += finish_value(diff, row.thr, mode, temperature) * wgt[k];
+        }
+    }
+    return v;
+}
+
+// one keypoint whose window `Lbox` is in flight / has landed on mbarrier `bar` (phase `parity`).  NPP = pairs per thread
+// (P / 64): the pair loops are fully unrolled over exactly NPP slots so that the NPP independent tap chains overlap.
+template <bool CPA, int NPP>
 __device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long kidx, float ky, float kx, const float* Lbox,
                                                uint32_t bar, uint32_t parity, float* red, const uint4* sTap,
                                                const float4* sThr, int g, int t) {
@@ -912,98 +966,96 @@ __device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long k
     const DenseKp kp = dense_kp_pos(ky, kx, H, W);
     const int iy0 = kp.iy0, ix0 = kp.ix0;
     const float w = kp.w, e = 1.0f - w, s = kp.s, n = 1.0f - s;
-    const int ys = min(iy0 + 1, H - 1), xe = min(ix0 + 1, W - 1);
     const int oy = iy0 - LO, ox = ix0 - LO;     // integral coords of L(0,0)
     const float wgt[4] = {n * e, n * w, s * e, s * w};                  // nw, ne, sw, se
     const float* L = Lbox + (ox & 3);           // window column 0 inside the 16-byte aligned box
-    mbar_wait(bar, parity);
+    if (CPA) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");            // this thread's 16-byte copies have landed
+        group_bar(g);                                                   // ... and everyone else's
+    } else {
+        mbar_wait(bar, parity);
+    }
 
-    constexpr int MAXPP = 8;
-    float d[MAXPP];
+    float d[NPP];
+    int pidx[NPP];
     float ss = 0.0f;
     // no centre clamp for any of the four neighbours <=> their offsets in [-15,14] stay inside the image
     const bool interior = iy0 >= 15 && iy0 + 1 + 14 <= H - 1 && ix0 >= 15 && ix0 + 1 + 14 <= W - 1;
     const char* lbytes = reinterpret_cast<const char*>(L);
     auto ldl = [&](unsigned int byte_off) -> float { return *reinterpret_cast<const float*>(lbytes + byte_off); };
-    if (interior && w == 0.0f && s == 0.0f) {
-        // keypoint on the pixel grid (every detector output): the weights are exactly {1, 0, 0, 0}, one neighbour, no
+    if (a.dbg & 4) {
+#pragma unroll
+        for (int q = 0; q < NPP; ++q) { d[q] = L[t + q * TPG]; pidx[q] = t + q * TPG < a.P ? t + q * TPG : -1; }
+    } else if (interior && w == 0.0f && s == 0.0f) {
+        // keypoint whose sampling position is exactly on the pixel grid: the weights are {1, 0, 0, 0}, one neighbour, no
         // per-neighbour tests; 0 + value * 1 of the general path is value (up to the sign of a zero)
 #pragma unroll
-        for (int q = 0; q < MAXPP; ++q) {
-            const int p = t + q * TPG;
-            d[q] = 0.0f;
-            if (p < a.P) {
-                const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
-                const float4 tb = sThr[p];
-                const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(ta.x), ldl(ta.y)), ldl(ta.z)), ldl(ta.w));
-                const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(tc.x), ldl(tc.y)), ldl(tc.z)), ldl(tc.w));
-                const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));           // bad.py:99, :110
-                const float v = __fadd_rn(0.0f, finish_value(diff, tb.x, a.mode, a.temperature));
-                d[q] = v;
-                ss = fmaf(v, v, ss);
-            }
+        for (int q = 0; q < NPP; ++q) {
+            const int p = t + q * TPG;                                  // slot; sThr[p].w holds its pair index
+            d[q] = 0.0f; pidx[q] = -1;
+            if (p >= a.P) continue;                                     // only when P is not a multiple of 64
+            const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+            const float4 tb = sThr[p];
+            const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(ta.x), ldl(ta.y)), ldl(ta.z)), ldl(ta.w));
+            const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(tc.x), ldl(tc.y)), ldl(tc.z)), ldl(tc.w));
+            const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));               // bad.py:99, :110
+            d[q] = __fadd_rn(0.0f, finish_value(diff, tb.x, a.mode, a.temperature));
+            pidx[q] = __float_as_int(tb.w);
         }
     } else if (interior) {
 #pragma unroll
-        for (int q = 0; q < MAXPP; ++q) {
+        for (int q = 0; q < NPP; ++q) {
             const int p = t + q * TPG;
-            d[q] = 0.0f;
-            if (p < a.P) {
-                const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
-                const float4 tb = sThr[p];
-                float v = 0.0f;
+            d[q] = 0.0f; pidx[q] = -1;
+            if (p >= a.P) continue;
+            const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+            const float4 tb = sThr[p];
+            float v = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (wgt[k] != 0.0f) {                                   // group-uniform
-                        const unsigned int lk = ((k >> 1) * SPAN + (k & 1)) * 4;
-                        const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + ta.x), ldl(lk + ta.y)), ldl(lk + ta.z)),
-                                                   ldl(lk + ta.w));
-                        const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + tc.x), ldl(lk + tc.y)), ldl(lk + tc.z)),
-                                                   ldl(lk + tc.w));
-                        const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));   // bad.py:99, :110
-                        v += finish_value(diff, tb.x, a.mode, a.temperature) * wgt[k];
-                    }
+            for (int k = 0; k < 4; ++k) {
+                if (wgt[k] != 0.0f) {                                   // group-uniform
+                    const unsigned int lk = ((k >> 1) * SPAN + (k & 1)) * 4;
+                    const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + ta.x), ldl(lk + ta.y)), ldl(lk + ta.z)),
+                                               ldl(lk + ta.w));
+                    const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + tc.x), ldl(lk + tc.y)), ldl(lk + tc.z)),
+                                               ldl(lk + tc.w));
+                    const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));       // bad.py:99, :110
+                    v += finish_value(diff, tb.x, a.mode, a.temperature) * wgt[k];
                 }
-                d[q] = v;
-                ss = fmaf(v, v, ss);
             }
+            d[q] = v;
+            pidx[q] = __float_as_int(tb.w);
         }
     } else {
-        const int py[4] = {iy0, iy0, ys, ys}, px[4] = {ix0, xe, ix0, xe};
-        auto value_at = [&](int qy, int qx, const PairRow& row, int r) -> float {
-            const int c1y = clampi(qy + (int)row.oy1, 0, H - 1) + MAXR - oy, c1x = clampi(qx + (int)row.ox1, 0, W - 1) + MAXR - ox;
-            const int c2y = clampi(qy + (int)row.oy2, 0, H - 1) + MAXR - oy, c2x = clampi(qx + (int)row.ox2, 0, W - 1) + MAXR - ox;
-            const float diff = __fsub_rn(dense_box_mean(L, SPAN, c1y, c1x, r), dense_box_mean(L, SPAN, c2y, c2x, r));
-            return finish_value(diff, row.thr, a.mode, a.temperature);
-        };
 #pragma unroll
-        for (int q = 0; q < MAXPP; ++q) {
-            const int p = t + q * TPG;
-            d[q] = 0.0f;
-            if (p < a.P) {
-                const PairRow row = load_pair(a.table, p);
-                const int r = (int)row.r;
-                float v = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (wgt[k] != 0.0f) v += value_at(py[k], px[k], row, r) * wgt[k];
-                d[q] = v;
-                ss = fmaf(v, v, ss);
-            }
+        for (int q = 0; q < NPP; ++q) {
+            d[q] = 0.0f; pidx[q] = -1;
+            if (t + q * TPG >= a.P) continue;
+            pidx[q] = __float_as_int(sThr[t + q * TPG].w);
+            d[q] = dense_pair_border(a.table, pidx[q], L, H, W, oy, ox, iy0, ix0, wgt[0], wgt[1], wgt[2], wgt[3], a.mode,
+                                     a.temperature);
         }
     }
+#pragma unroll
+    for (int q = 0; q < NPP; ++q) ss = fmaf(d[q], d[q], ss);
     float inv = 1.0f;
     if (a.normalize) inv = 1.0f / fmaxf(sqrtf(group_sum(ss, red, g, t)), 1e-12f);
 #pragma unroll
-    for (int q = 0; q < MAXPP; ++q) {
-        const int p = t + q * TPG;
-        if (p < a.P) out[p] = d[q] * inv;
-    }
+    for (int q = 0; q < NPP; ++q)
+        if (pidx[q] >= 0) out[pidx[q]] = d[q] * inv;
+}
+
+// slot -> pair index (pair_order.inc): the built-in orders for 256 / 512 pairs, the identity otherwise
+__device__ __forceinline__ int pair_of_slot(int slot, int P) {
+    return P == 256 ? (int)OM_PAIR_ORDER_256[slot] : (P == 512 ? (int)OM_PAIR_ORDER_512[slot] : slot);
 }
 
 // Every 64-thread group walks its keypoints (grid-stride); NBUF as in sparse_win_kernel.
-template <int GROUPS, int NBUF>
-__global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __grid_constant__ CUtensorMap tmap, DenseKpArgs a) {
+// CPA: the window is fetched by the group's 64 threads as 16-byte cp.async copies instead of one TMA box (measured
+// slower: 105 us against 83 us, the address arithmetic of 10 copies per thread costs more than the TMA unit saves);
+// kept as a cross-check of the TMA path.
+template <int GROUPS, int NBUF, bool CPA, int NPP>
+__global__ void __launch_bounds__(GROUPS * TPG, 4) dense_at_kpts_kernel(const __grid_constant__ CUtensorMap tmap, DenseKpArgs a) {
     constexpr int LO = DK_LO, SPAN = DK_SPAN;   // integral rows [iy0-15, iy0+31] cover every tap of the 4 neighbours
     constexpr int WBUF = DK_ROWS * SPAN;                     // 48*52*4 bytes per window: a multiple of 128
     extern __shared__ __align__(128) float sI[];
@@ -1019,9 +1071,11 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __gri
     }
 
     for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
-        // window coordinates of the taps of neighbour (0,0): pixel q of the image is integral index q + MAXR,
+        // slot p takes pair pair_of_slot(p): 32 consecutive slots are the lanes of one tap read, ordered for few bank
+        // conflicts.  Window coordinates of the taps of neighbour (0,0): pixel q of the image is integral index q + MAXR,
         // the window starts at integral index iy0 - LO
-        const PairRow row = load_pair(a.table, p);
+        const int pair = pair_of_slot(p, a.P);
+        const PairRow row = load_pair(a.table, pair);
         const int r = (int)row.r;
         const int cy1 = LO + MAXR + (int)row.oy1, cx1 = LO + MAXR + (int)row.ox1;
         const int cy2 = LO + MAXR + (int)row.oy2, cx2 = LO + MAXR + (int)row.ox2;
@@ -1032,7 +1086,7 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __gri
         sTap[2 * p + 1] = make_uint4(off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r),
                                      off(cy2 - r, cx2 - r));
         const float side = (float)(2 * r + 1);
-        sThr[p] = make_float4(row.thr, side * side, __fdiv_rn(1.0f, side * side), 0.0f);
+        sThr[p] = make_float4(row.thr, side * side, __fdiv_rn(1.0f, side * side), __int_as_float(pair));
     }
     __syncthreads();
 
@@ -1042,8 +1096,32 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __gri
     const uint32_t bar0 = smem_u32(&bars[2 * g]);
     // thread 0 of the group launches the window load of keypoint k into buffer `buf`: one TMA box, rows/columns
     // outside the integral read as zero and are never used as taps
+    const int IP = ipitch(a.W, MAXR), IH = a.H + 2 * MAXR + 1;
     auto issue = [&](long long k, int buf) {
-        if (t == 0) {
+        if (a.dbg & 2) {
+            if (CPA) asm volatile("cp.async.commit_group;" ::: "memory");
+            else if (t == 0) mbar_arrive(bar0 + 8u * buf);
+            return;
+        }
+        if (CPA) {
+            const float ky = a.kpts[k * 2 + 0], kx = a.kpts[k * 2 + 1];
+            if (ky >= 0.0f) {
+                const DenseKp kp = dense_kp_pos(ky, kx, a.H, a.W);
+                const int wx0 = (kp.ix0 - LO) & ~3, wy0 = kp.iy0 - LO;
+                const float* img = a.I + (size_t)(k / a.K) * IH * IP;
+                const uint32_t dst0 = smem_u32(wbuf + buf * WBUF);
+                constexpr int C4 = SPAN / 4;                            // 16-byte pieces per window row
+                for (int i = t; i < DK_ROWS * C4; i += TPG) {
+                    const int row = i / C4, c4 = i - row * C4;
+                    const int gy = wy0 + row, gx = wx0 + 4 * c4;
+                    const bool ok = gy >= 0 && gy < IH && gx >= 0 && gx < IP;      // outside: zero fill, never used as a tap
+                    const float* src = ok ? img + (size_t)gy * IP + gx : a.I;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)(row * SPAN + 4 * c4) * 4u),
+                                 "l"(src), "r"(ok ? 16 : 0) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else if (t == 0) {
             const float ky = a.kpts[k * 2 + 0], kx = a.kpts[k * 2 + 1];
             if (ky >= 0.0f) {
                 const DenseKp kp = dense_kp_pos(ky, kx, a.H, a.W);
@@ -1061,7 +1139,7 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __gri
         if (NBUF == 2 && kidx + stride < total) issue(kidx + stride, buf ^ 1);   // that buffer was released by the barrier below
         const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
         if (ky >= 0.0f) {
-            dense_kp_group(a, kidx, ky, kx, wbuf + buf * WBUF, bar0 + 8u * buf, phase[buf], red, sTap, sThr, g, t);
+            dense_kp_group<CPA, NPP>(a, kidx, ky, kx, wbuf + buf * WBUF, bar0 + 8u * buf, phase[buf], red, sTap, sThr, g, t);
             phase[buf] ^= 1u;
         } else {                                                    // shi_tomasi_bad_sinkhorn.py:143,158: masked rows are zero
             float* out = a.desc + (size_t)kidx * a.P;
@@ -1072,6 +1150,9 @@ __global__ void __launch_bounds__(GROUPS * TPG) dense_at_kpts_kernel(const __gri
     }
 }
 
+int g_dense_window_tma = 1;    // om_debug_dense_window: bit 0: 1 = one TMA box per keypoint window (default, 83 us), 0 = 16-byte cp.async
+                               // copies (105 us); bits 1, 2: diagnosis (skip the fetch / skip the pair arithmetic)
+
 template <int GROUPS>
 int launch_dense_kp(const DenseKpArgs& a, cudaStream_t st) {
     CUtensorMap tmap;
@@ -1080,12 +1161,21 @@ int launch_dense_kp(const DenseKpArgs& a, cudaStream_t st) {
                         DK_ROWS));
     constexpr int NBUF = 1;
     const size_t smem = (size_t)GROUPS * NBUF * DK_ROWS * DK_SPAN * sizeof(float) + (size_t)a.P * (2 * sizeof(uint4) + sizeof(float4));
-    OM_TRY(set_smem((dense_at_kpts_kernel<GROUPS, NBUF>), smem));
     const long long total = (long long)a.B * a.K;
     const long long nblk = (total + GROUPS - 1) / GROUPS;
     const int per_sm = (int)(228 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (228 KB, 1 KB reserved per CTA)
     const long long resident = 148ll * (per_sm < 1 ? 1 : per_sm);
-    dense_at_kpts_kernel<GROUPS, NBUF><<<(unsigned)(nblk < resident ? nblk : resident), GROUPS * TPG, smem, st>>>(tmap, a);
+    const unsigned grid = (unsigned)(nblk < resident ? nblk : resident);
+    DenseKpArgs a2 = a;
+    a2.dbg = g_dense_window_tma & 6;
+    const bool cpa = !(g_dense_window_tma & 1);
+    auto go = [&](auto kernel) -> int {
+        OM_TRY(set_smem(kernel, smem));
+        kernel<<<grid, GROUPS * TPG, smem, st>>>(tmap, a2);
+        return OM_OK;
+    };
+    if (a.P <= 4 * TPG) OM_TRY(cpa ? go(dense_at_kpts_kernel<GROUPS, NBUF, true, 4>) : go(dense_at_kpts_kernel<GROUPS, NBUF, false, 4>));
+    else OM_TRY(cpa ? go(dense_at_kpts_kernel<GROUPS, NBUF, true, 8>) : go(dense_at_kpts_kernel<GROUPS, NBUF, false, 8>));
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -1239,6 +1329,8 @@ int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const floa
 }  // namespace om
 
 using namespace om;
+
+extern "C" void om_debug_dense_window(int tma) { g_dense_window_tma = tma; }
 
 extern "C" int om_angle_map_f32(const float* image, int B, int H, int W, const float* moment_kernels, int patch_size,
                                 float* angle_map, void* stream) {
