@@ -375,7 +375,8 @@ extern "C" int om_essential_matrix_f32(const float* probs, const float* pts1, co
     if (n_iter < 0 || n_iter_manifold < 0) return OM_ERR_PARAM;
     if (top_k > E_MAXK || N > 8192 || M > 8192) return OM_ERR_LIMIT;
     const size_t smem = (size_t)(3 * N + 3 * M) * sizeof(float);
-    OM_TRY(set_smem(essential_kernel, smem));
+    // the kernel also has ~11 KB of static shared memory: opt in whenever the sum may pass the 48 KB default
+    if (smem > 32 * 1024) OM_CUDA(cudaFuncSetAttribute(essential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EssArgs a{probs, pts1, pts2, valid1, valid2, N, M, top_k, n_iter, n_iter_manifold, pts_batched, E};
     essential_kernel<<<B, ET, smem, (cudaStream_t)stream>>>(a);
     OM_AFTER_LAUNCH();

@@ -703,3 +703,16 @@ def test_essential_matrix_argument_errors():
         _ops.essential_matrix(P, pts[:, :7], pts, None, None, 3, 30, 10)
     with pytest.raises(RuntimeError):
         om.EssentialMatrixEstimator(torch.eye(3), image_shape=(2, 2)).to(DEV)(P[0])   # grid smaller than N
+
+
+def test_essential_matrix_large_and_ragged():
+    """N != M beyond 2048 points: the kernel's shared-memory opt-in path; float64 oracle on the same inputs."""
+    gen = torch.Generator().manual_seed(5)
+    N, M = 2100, 1900
+    P = torch.rand(N + 1, M + 1, generator=gen) * 0.5
+    K_inv = torch.linalg.inv(torch.tensor([[40.0, 0.0, 32.0], [0.0, 40.0, 32.0], [0.0, 0.0, 1.0]]))
+    p1, p2 = O.grid_points(N, (64, 64), K_inv), O.grid_points(M, (64, 64), K_inv)
+    v1, v2 = torch.rand(N, generator=gen) > 0.1, torch.rand(M, generator=gen) > 0.1
+    E = _ops.essential_matrix(P[None].to(DEV), p1[None].to(DEV), p2[None].to(DEV), v1[None].to(DEV), v2[None].to(DEV), 3, 30, 10).cpu()[0]
+    ref = O.essential_matrix(P, p1, p2, v1, v2, dtype=torch.float64)
+    assert float((E.double() - ref).abs().max()) <= E_RTOL * float(ref.abs().max())
