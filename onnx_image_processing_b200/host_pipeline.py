@@ -48,6 +48,10 @@ class HostBatchMatcher:
 
     uint8 host images are accepted (4x less PCIe traffic): they are widened to float32 on the device,
     which is exact, so results are identical to passing the same values as float32.
+
+    Any module whose forward(image1, image2) returns a tuple of tensors with the pair batch as their first dimension
+    works: the three-output matchers, ``MatchExtractionWrapper`` (matches only: no (K+1)^2 matrix crosses PCIe) or the
+    ``WithFilters`` matcher.  The pinned result buffers are shaped after the first chunk's outputs.
     """
 
     def __init__(self, model: torch.nn.Module, chunk: int = 16, n_streams: int = 4, device=None, depth: int = 2,
@@ -63,13 +67,17 @@ class HostBatchMatcher:
         self._out = [None] * self.depth
         self._calls = 0
 
-    def _outputs(self, B: int, K: int):
-        slot = self._calls % self.depth
+    def _outputs(self, slot: int, B: int, outs, n: int):
+        """Pinned host buffers of result set `slot`, shaped (B, ...) after the device outputs of one chunk of n pairs."""
         cur = self._out[slot]
-        if cur is None or cur[0].shape[0] != B or cur[0].shape[1] != K:
-            cur = (torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
-                   torch.empty((B, K, 2), dtype=torch.float32).pin_memory(),
-                   torch.empty((B, K + 1, K + 1), dtype=torch.float32).pin_memory())
+        ok = cur is not None and len(cur) == len(outs) and all(
+            h.shape[0] == B and h.shape[1:] == o.shape[1:] and h.dtype == o.dtype for h, o in zip(cur, outs))
+        if not ok:
+            for o in outs:
+                if o.dim() == 0 or o.shape[0] != n:
+                    raise RuntimeError("HostBatchMatcher: every model output must have the pair batch as its first "
+                                       f"dimension, got {tuple(o.shape)} for a chunk of {n} pairs")
+            cur = tuple(torch.empty((B,) + tuple(o.shape[1:]), dtype=o.dtype).pin_memory() for o in outs)
             self._out[slot] = cur
         return cur
 
@@ -86,9 +94,9 @@ class HostBatchMatcher:
         if not image2.is_pinned():
             image2 = image2.pin_memory()
         B = image1.shape[0]
-        K = int(self.model.max_keypoints)
-        o1, o2, op = self._outputs(B, K)
+        slot = self._calls % self.depth
         self._calls += 1
+        host = None
         cur = torch.cuda.current_stream(self.device)
         if self.join:
             for s in self.streams:
@@ -101,11 +109,13 @@ class HostBatchMatcher:
                 d2 = image2[lo:hi].to(self.device, non_blocking=True)
                 if d1.dtype != torch.float32:
                     d1, d2 = d1.float(), d2.float()
-                k1, k2, p = self.model(d1, d2)
-                o1[lo:hi].copy_(k1, non_blocking=True)
-                o2[lo:hi].copy_(k2, non_blocking=True)
-                op[lo:hi].copy_(p, non_blocking=True)
+                outs = self.model(d1, d2)
+                outs = (outs,) if torch.is_tensor(outs) else tuple(outs)
+                if host is None:
+                    host = self._outputs(slot, B, outs, hi - lo)
+                for h, o in zip(host, outs):
+                    h[lo:hi].copy_(o, non_blocking=True)
         if self.join:
             for s in self.streams:
                 cur.wait_stream(s)
-        return o1, o2, op
+        return host

@@ -716,3 +716,34 @@ def test_essential_matrix_large_and_ragged():
     E = _ops.essential_matrix(P[None].to(DEV), p1[None].to(DEV), p2[None].to(DEV), v1[None].to(DEV), v2[None].to(DEV), 3, 30, 10).cpu()[0]
     ref = O.essential_matrix(P, p1, p2, v1, v2, dtype=torch.float64)
     assert float((E.double() - ref).abs().max()) <= E_RTOL * float(ref.abs().max())
+
+
+# ------------------------------------------------------------------------------------------
+# host pipeline
+# ------------------------------------------------------------------------------------------
+def test_host_batch_matcher_equals_direct_calls():
+    """HostBatchMatcher (pinned host images in, pinned host results out, chunks on a ring of streams) returns what the
+    module returns for the same pairs; uint8 host images give the same results as the same pixels in float32; a model with
+    other outputs (MatchExtractionWrapper: matches only) works through the same pipeline."""
+    from onnx_image_processing_b200.host_pipeline import HostBatchMatcher
+    i1, i2 = O.texture_images(10, 120, 160, seed=31)
+    model = om.ShiTomasiSparseBADSinkhornMatcher(64).to(DEV).eval()
+    with torch.no_grad():
+        ref = [t.cpu() for t in model(i1.to(DEV), i2.to(DEV))]
+    for join in (True, False):
+        hb = HostBatchMatcher(model, chunk=4, n_streams=3, depth=2, join=join)
+        for imgs in ((i1, i2), (i1.to(torch.uint8), i2.to(torch.uint8))):
+            got = hb(*imgs)
+            hb.synchronize()
+            torch.cuda.synchronize()
+            assert len(got) == 3 and all(g.is_pinned() for g in got)
+            for g, r in zip(got, ref):
+                assert torch.equal(g, r)
+    wrapped = om.MatchExtractionWrapper(model, max_matches=32, match_threshold=0.02).to(DEV).eval()
+    with torch.no_grad():
+        ref = [t.cpu() for t in wrapped(i1.to(DEV), i2.to(DEV))]
+    got = HostBatchMatcher(wrapped, chunk=3)(i1, i2)
+    torch.cuda.synchronize()
+    assert len(got) == 4 and got[3].dtype == torch.bool and int(got[3].sum()) > 0
+    for g, r in zip(got, ref):
+        assert torch.equal(g, r)
