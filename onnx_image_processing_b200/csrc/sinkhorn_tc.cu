@@ -238,14 +238,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
             // ===== fp16 split.  Stage = 32 floats of K (two K=16 MMA steps) =====
             // Tile layout (bytes): element (row, k) at (k/8)*LBO + row*16 + (k%8)*2 -- the same core-matrix
             // geometry as the TF32 tiles (8 rows x 16 bytes, LBO between K groups, SBO = 128 between row groups).
-            // Work item = (16-row block, K group of 8): a warp stores 16 rows x 16 bytes = 256 contiguous bytes per
-            // item (conflict-free 8-byte stores) and reads 16 x 32-byte sectors.  144 items per stage (128 of the d2
-            // tile, 16 of the d1 tile) are dealt round-robin to warps 0..14; warp 15 only issues the MMAs, so that
-            // staging stage c+1 and the tensor core working on stage c overlap (the tensor pipe paces at ~2.1k cycles
-            // per stage, a producer warp needs ~1.9k).
+            // Work item = 4 rows x the 32 floats (128 bytes) of the chunk: a warp-level load reads four whole 128-byte
+            // lines (lane = row, 16-byte segment) and the two 8-byte stores per lane land in the four K groups of the
+            // tile (4 shared-memory wavefronts each).  What paces the producers is L1 wavefronts, one per line touched:
+            // the earlier item (16 rows x one K group of 8 floats: 16 half-used lines per load, conflict-free stores)
+            // cost 20 wavefronts per 512 bytes staged, this one 12.  144 items per stage (128 of the d2 tile, 16 of the
+            // d1 tile) are dealt round-robin to warps 0..14; warp 15 only issues the MMAs, so that staging stage c+1 and
+            // the tensor core working on stage c overlap (the tensor pipe paces at ~2.1k cycles per stage).
             constexpr int KC2 = 32, NPW = 15, NITEM = 144, IPW = (NITEM + NPW - 1) / NPW;
             const int nchunks = D / KC2;
-            const int prow = lane >> 1, half = lane & 1;
+            const int prow = lane >> 3, seg = lane & 7;             // row within the item, 16-byte segment of its 128-byte line
+            const int kgl = seg >> 1, half = seg & 1;               // K group of 8 floats, half of it
             float mx = 0.f;
             const bool trc = a.trace != nullptr && tid == NPW * 32;
             long long y0 = 0, y1 = 0, y2 = 0, y3 = 0;
@@ -261,13 +264,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     src[t] = nullptr;
                     dst[t] = 0;
                     if (i < 128) {                                  // d2 tile (MMA "A")
-                        const int j = 16 * (i >> 2) + prow, kg = i & 3;
-                        if (j < M) src[t] = A + (size_t)j * D + 8 * kg + 4 * half;
-                        dst[t] = (uint32_t)(kg * A_LBO + j * 16 + half * 8);
+                        const int j = 4 * i + prow;
+                        if (j < M) src[t] = A + (size_t)j * D + 4 * seg;
+                        dst[t] = (uint32_t)(kgl * A_LBO + j * 16 + half * 8);
                     } else if (i < NITEM) {                         // d1 tile (MMA "B")
-                        const int r = 16 * ((i - 128) >> 2) + prow, kg = (i - 128) & 3;
-                        if (r < nreal) src[t] = Bm + (size_t)r * D + 8 * kg + 4 * half;
-                        dst[t] = (uint32_t)(2 * A_TILE + kg * B_LBO + r * 16 + half * 8);
+                        const int r = 4 * (i - 128) + prow;
+                        if (r < nreal) src[t] = Bm + (size_t)r * D + 4 * seg;
+                        dst[t] = (uint32_t)(2 * A_TILE + kgl * B_LBO + r * 16 + half * 8);
                     }
                 }
                 // items are handled in two halves: as soon as a half is staged its registers are refilled with the next
@@ -306,14 +309,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                     mbar_arrive(smem_u32(&bars[5 + s]));                            // stage s is full
                     fetch(c + 1, HALF, IPW);
                 }
-                // squared norms, sinkhorn.py:98-99: the lane pair holds one K group of a row; the 4 K groups of a row sit
-                // in different warps -> partial sums through shared memory (sCW is free now), combined in fixed order
+                // squared norms, sinkhorn.py:98-99: the 8 lanes of a row hold its 8 segments (summed over the chunks)
 #pragma unroll
                 for (int t = 0; t < IPW; ++t) {
                     const int i = warp + NPW * t;
-                    const float v = acc[t] + __shfl_xor_sync(0xffffffffu, acc[t], 1);
-                    if (half == 0 && i < 128) sCW[(i & 3) * MAXM + 16 * (i >> 2) + prow] = v;
-                    else if (half == 0 && i < NITEM) sCW[4 * MAXM + ((i - 128) & 3) * B_ROWS + 16 * ((i - 128) >> 2) + prow] = v;
+                    float v = acc[t];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    if (seg == 0 && i < 128) sN2[4 * i + prow] = v;
+                    else if (seg == 0 && i < NITEM) sN1[4 * (i - 128) + prow] = v;
                 }
             } else if (lane == 0) {
                 // ===== MMA issuer (warp 15): wait until the producers have stored chunk c, then drive the tensor core =====
@@ -348,14 +353,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                 }
             }
             __syncwarp();
-            overflow = __syncthreads_or(mx >= 60000.0f ? 1 : 0);
-            for (int r = tid; r < MAXM + B_ROWS; r += NT) {
-                if (r < MAXM) sN2[r] = (sCW[r] + sCW[MAXM + r]) + (sCW[2 * MAXM + r] + sCW[3 * MAXM + r]);
-                else {
-                    const float* q = sCW + 4 * MAXM + (r - MAXM);
-                    sN1[r - MAXM] = (q[0] + q[B_ROWS]) + (q[2 * B_ROWS] + q[3 * B_ROWS]);
-                }
-            }
+            overflow = __syncthreads_or(mx >= 60000.0f ? 1 : 0);    // (also publishes sN1 / sN2)
         } else {
         const int lrow = tid >> 2, lkq = tid & 3;                   // loader: row (+128q), 16-byte K unit
         float nb[4] = {0.f, 0.f, 0.f, 0.f}, na = 0.f;
