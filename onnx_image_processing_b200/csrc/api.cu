@@ -2,6 +2,8 @@
 // matcher that chains the stage launchers on one stream (no host synchronisation in between).
 #include <string.h>
 
+#include <mutex>
+
 #include "bad_tables.inc"
 #include "common.cuh"
 
@@ -80,12 +82,35 @@ extern "C" int om_bad_table(int num_pairs, signed char* h_boxes, float* h_thresh
 namespace {
 
 struct MatchWs {
-    void* detect;  size_t detect_bytes;
+    void* detect[2];  size_t detect_bytes;     // one set per image: the two image chains run on two streams
     float* desc1;  float* desc2;
-    void* dense;   size_t dense_bytes;
+    void* dense[2];   size_t dense_bytes;
     void* sink;    size_t sink_bytes;
     size_t total;
 };
+
+// The detector / descriptor chains of image 1 and image 2 are independent until the Sinkhorn kernel: image 2 runs on a
+// side stream (fork and join by events, capturable into a CUDA graph), so that under-filled launches (top-k: one CTA
+// per image) and kernel tails of one chain overlap with the other chain.  One side stream and event pair per device,
+// created on the first call.
+int g_match_streams = 2;                        // om_debug_match_streams: 1 = both chains on the caller's stream
+constexpr int MAX_DEVICES = 64;
+cudaStream_t g_side_stream[MAX_DEVICES] = {};
+cudaEvent_t g_fork_event[MAX_DEVICES] = {}, g_join_event[MAX_DEVICES] = {};
+std::mutex g_match_mutex;                       // the record / wait pairs on the shared events must not interleave between host threads
+
+int side_stream(cudaStream_t* side, cudaEvent_t* fork, cudaEvent_t* join) {
+    int dev = 0;
+    OM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return OM_ERR_LIMIT;
+    if (g_side_stream[dev] == nullptr) {
+        OM_CUDA(cudaStreamCreateWithFlags(&g_side_stream[dev], cudaStreamNonBlocking));
+        OM_CUDA(cudaEventCreateWithFlags(&g_fork_event[dev], cudaEventDisableTiming));
+        OM_CUDA(cudaEventCreateWithFlags(&g_join_event[dev], cudaEventDisableTiming));
+    }
+    *side = g_side_stream[dev]; *fork = g_fork_event[dev]; *join = g_join_event[dev];
+    return OM_OK;
+}
 
 int check_params(const om_match_params* p) {
     if (p == nullptr) return OM_ERR_NULL;
@@ -100,7 +125,8 @@ MatchWs plan(const om_match_params* p, void* base) {
     char* c = (char*)base;
     size_t off = 0;
     w.detect_bytes = topk_workspace_bytes(p->B, p->H, p->W, p->K);
-    w.detect = c + off; off += align_up(w.detect_bytes);
+    w.detect[0] = c + off; off += align_up(w.detect_bytes);
+    w.detect[1] = c + off; off += align_up(w.detect_bytes);
     const size_t db = align_up((size_t)p->B * p->K * p->P * sizeof(float));
     w.desc1 = (float*)(c + off); off += db;
     w.desc2 = (float*)(c + off); off += db;
@@ -108,7 +134,8 @@ MatchWs plan(const om_match_params* p, void* base) {
                         ? dense_bad_workspace_bytes(p->B, p->H, p->W)
                         : sparse_bad_workspace_bytes(p->B, p->H, p->W,
                                                      p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE);
-    w.dense = c + off; off += align_up(w.dense_bytes);
+    w.dense[0] = c + off; off += align_up(w.dense_bytes);
+    w.dense[1] = c + off; off += align_up(w.dense_bytes);
     w.sink_bytes = sinkhorn_workspace_bytes(p->B, p->K, p->K, p->P);
     w.sink = c + off; off += align_up(w.sink_bytes);
     w.total = off;
@@ -116,6 +143,8 @@ MatchWs plan(const om_match_params* p, void* base) {
 }
 
 }  // namespace
+
+extern "C" void om_debug_match_streams(int n) { g_match_streams = n == 1 ? 1 : 2; }
 
 extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
     if (check_params(p) != OM_OK) return 0;
@@ -139,18 +168,31 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
     const float* images[2] = {image1, image2};
     float* kp[2] = {kpts1, kpts2};
     float* ds[2] = {d1, d2};
+    cudaStream_t chain[2] = {st, st};
+    cudaEvent_t fork = nullptr, join = nullptr;
+    std::unique_lock<std::mutex> lock(g_match_mutex, std::defer_lock);
+    if (g_match_streams == 2) {
+        lock.lock();
+        OM_TRY(side_stream(&chain[1], &fork, &join));
+        OM_CUDA(cudaEventRecord(fork, st));                         // image 2's chain starts behind the caller's prior work
+        OM_CUDA(cudaStreamWaitEvent(chain[1], fork, 0));
+    }
     for (int s = 0; s < 2; ++s) {
         // keypoint scores are discarded by the matcher modules (`keypoints1, _ = ...`)
-        OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect, w.detect_bytes, st));
+        OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
         if (p->flavour == OM_MATCH_DENSE) {
             OM_TRY(dense_bad_at_kpts_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
-                                            p->temperature, p->normalize, ds[s], w.dense, w.dense_bytes, st));
+                                            p->temperature, p->normalize, ds[s], w.dense[s], w.dense_bytes, chain[s]));
         } else {
             const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
             OM_TRY(sparse_bad_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
                                      p->temperature, p->normalize, p->sampling_mode, theta, nullptr, moment_kernels,
-                                     p->patch_size, ds[s], w.dense, w.dense_bytes, st));
+                                     p->patch_size, ds[s], w.dense[s], w.dense_bytes, chain[s]));
         }
+    }
+    if (g_match_streams == 2) {
+        OM_CUDA(cudaEventRecord(join, chain[1]));
+        OM_CUDA(cudaStreamWaitEvent(st, join, 0));                  // Sinkhorn needs both descriptor sets
     }
     return sinkhorn_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
                            probs, w.sink, w.sink_bytes, st);
