@@ -230,8 +230,8 @@ void om_debug_force_generic_stencil(int on);
 /* NMS kernel of the split sweep form at radius 3: 1 = nms3_sweep_kernel (default), 2 = the same at 6 CTAs per SM,
  * 0 = the any-radius nms_sweep_kernel (cross-check). */
 void om_debug_nms_variant(int v);
-/* Fused matcher: 2 = the detector / descriptor chain of image 2 runs on a side stream next to image 1's (default),
- * 1 = both chains on the caller's stream. */
+/* Fused matcher: 4 (default) = image 2's detector / descriptor chain and both integral-image builds run on side streams
+ * next to image 1's chain, 2 = only image 2's chain on a side stream, 1 = everything on the caller's stream. */
 void om_debug_match_streams(int n);
 /* Keypoint windows of the dense descriptor kernel: bit 0: 1 = one TMA box per keypoint (default), 0 = 16-byte cp.async
  * copies by the keypoint's thread group (cross-check, slower); bit 1 / bit 2 (diagnosis only, wrong results): skip the

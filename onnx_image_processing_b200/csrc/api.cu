@@ -89,26 +89,28 @@ struct MatchWs {
     size_t total;
 };
 
-// The detector / descriptor chains of image 1 and image 2 are independent until the Sinkhorn kernel: image 2 runs on a
-// side stream (fork and join by events, capturable into a CUDA graph), so that under-filled launches (top-k: one CTA
-// per image) and kernel tails of one chain overlap with the other chain.  One side stream and event pair per device,
-// created on the first call.
-int g_match_streams = 2;                        // om_debug_match_streams: 1 = both chains on the caller's stream
+// The detector / descriptor chains of image 1 and image 2 are independent until the Sinkhorn kernel, and inside a chain
+// the integral image needs only the image: with 4 streams image 2's chain and both integral builds run on side streams
+// (fork and join by events, capturable into a CUDA graph), so that under-filled launches (top-k: one CTA per image),
+// kernel tails and issue-bound / bandwidth-bound kernels overlap.  Side streams and events are per device, created on
+// the first call.
+int g_match_streams = 4;                        // om_debug_match_streams: 1 = everything on the caller's stream, 2 = two chains, 4
 constexpr int MAX_DEVICES = 64;
-cudaStream_t g_side_stream[MAX_DEVICES] = {};
-cudaEvent_t g_fork_event[MAX_DEVICES] = {}, g_join_event[MAX_DEVICES] = {};
+cudaStream_t g_side_stream[MAX_DEVICES][3] = {};
+cudaEvent_t g_fork_event[MAX_DEVICES] = {}, g_join_event[MAX_DEVICES] = {}, g_pre_event[MAX_DEVICES][2] = {};
 std::mutex g_match_mutex;                       // the record / wait pairs on the shared events must not interleave between host threads
 
-int side_stream(cudaStream_t* side, cudaEvent_t* fork, cudaEvent_t* join) {
+int side_streams(int* device) {
     int dev = 0;
     OM_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_DEVICES) return OM_ERR_LIMIT;
-    if (g_side_stream[dev] == nullptr) {
-        OM_CUDA(cudaStreamCreateWithFlags(&g_side_stream[dev], cudaStreamNonBlocking));
+    if (g_side_stream[dev][0] == nullptr) {
+        for (int i = 0; i < 3; ++i) OM_CUDA(cudaStreamCreateWithFlags(&g_side_stream[dev][i], cudaStreamNonBlocking));
         OM_CUDA(cudaEventCreateWithFlags(&g_fork_event[dev], cudaEventDisableTiming));
         OM_CUDA(cudaEventCreateWithFlags(&g_join_event[dev], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) OM_CUDA(cudaEventCreateWithFlags(&g_pre_event[dev][i], cudaEventDisableTiming));
     }
-    *side = g_side_stream[dev]; *fork = g_fork_event[dev]; *join = g_join_event[dev];
+    *device = dev;
     return OM_OK;
 }
 
@@ -144,7 +146,7 @@ MatchWs plan(const om_match_params* p, void* base) {
 
 }  // namespace
 
-extern "C" void om_debug_match_streams(int n) { g_match_streams = n == 1 ? 1 : 2; }
+extern "C" void om_debug_match_streams(int n) { g_match_streams = n == 1 ? 1 : (n == 2 ? 2 : 4); }
 
 extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
     if (check_params(p) != OM_OK) return 0;
@@ -168,31 +170,47 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
     const float* images[2] = {image1, image2};
     float* kp[2] = {kpts1, kpts2};
     float* ds[2] = {d1, d2};
-    cudaStream_t chain[2] = {st, st};
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t chain[2] = {st, st};           // detector + descriptors of image 1 / image 2
+    cudaStream_t pre[2] = {st, st};             // integral image of image 1 / image 2
+    const int ns = g_match_streams;
+    int dev = 0;
     std::unique_lock<std::mutex> lock(g_match_mutex, std::defer_lock);
-    if (g_match_streams == 2) {
+    if (ns > 1) {
         lock.lock();
-        OM_TRY(side_stream(&chain[1], &fork, &join));
-        OM_CUDA(cudaEventRecord(fork, st));                         // image 2's chain starts behind the caller's prior work
-        OM_CUDA(cudaStreamWaitEvent(chain[1], fork, 0));
+        OM_TRY(side_streams(&dev));
+        chain[1] = g_side_stream[dev][0];
+        if (ns == 4) { pre[0] = g_side_stream[dev][1]; pre[1] = g_side_stream[dev][2]; }
+        OM_CUDA(cudaEventRecord(g_fork_event[dev], st));            // side work starts behind the caller's prior work
+        for (int i = 0; i < (ns == 4 ? 3 : 1); ++i) OM_CUDA(cudaStreamWaitEvent(g_side_stream[dev][i], g_fork_event[dev], 0));
+    }
+    auto descriptors = [&](int s, cudaStream_t q, int phase) -> int {
+        if (p->flavour == OM_MATCH_DENSE)
+            return dense_bad_at_kpts_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
+                                            p->temperature, p->normalize, ds[s], w.dense[s], w.dense_bytes, q, phase);
+        const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
+        return sparse_bad_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode, p->temperature,
+                                 p->normalize, p->sampling_mode, theta, nullptr, moment_kernels, p->patch_size, ds[s],
+                                 w.dense[s], w.dense_bytes, q, phase);
+    };
+    if (ns == 4) {
+        for (int s = 0; s < 2; ++s) {
+            OM_TRY(descriptors(s, pre[s], 1));                      // integral image only
+            OM_CUDA(cudaEventRecord(g_pre_event[dev][s], pre[s]));
+        }
     }
     for (int s = 0; s < 2; ++s) {
         // keypoint scores are discarded by the matcher modules (`keypoints1, _ = ...`)
         OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
-        if (p->flavour == OM_MATCH_DENSE) {
-            OM_TRY(dense_bad_at_kpts_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
-                                            p->temperature, p->normalize, ds[s], w.dense[s], w.dense_bytes, chain[s]));
+        if (ns == 4) {
+            OM_CUDA(cudaStreamWaitEvent(chain[s], g_pre_event[dev][s], 0));
+            OM_TRY(descriptors(s, chain[s], 2));
         } else {
-            const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
-            OM_TRY(sparse_bad_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
-                                     p->temperature, p->normalize, p->sampling_mode, theta, nullptr, moment_kernels,
-                                     p->patch_size, ds[s], w.dense[s], w.dense_bytes, chain[s]));
+            OM_TRY(descriptors(s, chain[s], 0));
         }
     }
-    if (g_match_streams == 2) {
-        OM_CUDA(cudaEventRecord(join, chain[1]));
-        OM_CUDA(cudaStreamWaitEvent(st, join, 0));                  // Sinkhorn needs both descriptor sets
+    if (ns > 1) {
+        OM_CUDA(cudaEventRecord(g_join_event[dev], chain[1]));
+        OM_CUDA(cudaStreamWaitEvent(st, g_join_event[dev], 0));     // Sinkhorn needs both descriptor sets
     }
     return sinkhorn_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
                            probs, w.sink, w.sink_bytes, st);

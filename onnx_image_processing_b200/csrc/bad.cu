@@ -1267,7 +1267,8 @@ size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode) {
 int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
                       const float* orientation, const float* moment_kernels, int patch_size, float* desc,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
+                      void* ws, size_t ws_bytes, cudaStream_t st, int phase) {
+    // phase 0: everything; 1: only the integral image (needs no keypoints); 2: only the descriptors (integral built)
     if (image == nullptr || kpts == nullptr || desc == nullptr) return OM_ERR_NULL;
     if (B <= 0 || H <= 1 || W <= 1 || K <= 0) return OM_ERR_SHAPE;
     OM_TRY(check_table(pair_table, P));
@@ -1283,8 +1284,11 @@ int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts
     const bool oriented = theta_mode != OM_THETA_NONE;
     const int pad = oriented ? PAD_ORI : PAD_PLAIN;
     const SparseWs w = carve_sparse(ws, B, H, W, pad);
-    OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)(B + 1) * sizeof(unsigned int), st));
-    OM_TRY(build_prefix<true>(image, B, H, W, pad, w.T, w.I, w.flags, st));
+    if (phase != 2) {
+        OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)(B + 1) * sizeof(unsigned int), st));
+        OM_TRY(build_prefix<true>(image, B, H, W, pad, w.T, w.I, w.flags, st));
+    }
+    if (phase == 1) return OM_OK;
     SparseArgs a{};
     a.image = image; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P;
     a.mode = desc_mode; a.temperature = temperature; a.normalize = normalize;
@@ -1312,14 +1316,15 @@ size_t dense_bad_workspace_bytes(int B, int H, int W) {
 
 int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const float* kpts, int K,
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
-                             float* desc, void* ws, size_t ws_bytes, cudaStream_t st) {
+                             float* desc, void* ws, size_t ws_bytes, cudaStream_t st, int phase) {
     if (image == nullptr || kpts == nullptr || desc == nullptr) return OM_ERR_NULL;
     if (B <= 0 || H <= 1 || W <= 1 || K <= 0) return OM_ERR_SHAPE;
     OM_TRY(check_table(pair_table, P));
     if (desc_mode < OM_DESC_RAW || desc_mode > OM_DESC_HARD) return OM_ERR_PARAM;
     if (ws == nullptr || ws_bytes < dense_bad_workspace_bytes(B, H, W)) return OM_ERR_WORKSPACE;
     const DenseWs d = carve_dense(ws, B, H, W);
-    OM_TRY(build_integral(image, B, H, W, d, st));
+    if (phase != 2) OM_TRY(build_integral(image, B, H, W, d, st));
+    if (phase == 1) return OM_OK;
     DenseKpArgs a{};
     a.I = d.I; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P; a.mode = desc_mode;
     a.temperature = temperature; a.normalize = normalize; a.desc = desc;

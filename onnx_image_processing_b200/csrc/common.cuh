@@ -107,12 +107,12 @@ size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode);
 int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
                       const float* orientation, const float* moment_kernels, int patch_size, float* desc,
-                      void* ws, size_t ws_bytes, cudaStream_t st);
+                      void* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);   // phase 1: integral only, 2: descriptors only
 
 size_t dense_bad_workspace_bytes(int B, int H, int W);
 int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const float* kpts, int K,
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
-                             float* desc, void* ws, size_t ws_bytes, cudaStream_t st);
+                             float* desc, void* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);
 
 extern int g_tc_allow_scaling, g_tc_allow_f16;   // sinkhorn_tc.cu; test hooks
 // tcgen05 / TMEM cluster kernel (sinkhorn_tc.cu); limits: L2 cost, N <= 512, M <= 512, D % 16 == 0

@@ -29,7 +29,7 @@ for rep in range(2):
         print(f"{wl} B={B} stencil routing {mode}: {run(20) * 1000:.1f} us/step")
 lib.om_debug_force_generic_stencil(0)
 for rep in range(3):
-    for n in (1, 2):
+    for n in (1, 2, 4):
         lib.om_debug_match_streams(n)
         print(f"{wl} B={B} image chains on {n} stream(s): {run(30) * 1000:.1f} us/step")
-lib.om_debug_match_streams(2)
+lib.om_debug_match_streams(4)
