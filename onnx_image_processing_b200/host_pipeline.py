@@ -119,3 +119,41 @@ class HostBatchMatcher:
             for s in self.streams:
                 cur.wait_stream(s)
         return host
+
+
+class GraphedMatcher:
+    """One matcher step captured into a CUDA graph and replayed (every C-ABI call is capturable: no allocation, no
+    synchronisation, the side streams of the fused matcher fork and join by events).  Worth it at small batches, where
+    the ~13 launches and 6 event operations of a step are a visible part of its ~0.15 ms: batch 1 drops to ~0.12 ms.
+
+    ``graphed = GraphedMatcher(model, image1, image2)`` captures for the shapes of the two example tensors;
+    ``graphed(image1, image2)`` copies new images into the static input buffers, replays and returns the static output
+    tensors (overwritten by the next call).  ``graphed.inputs`` are the static buffers: filling them directly (for example
+    as the destination of a host-to-device copy) and calling ``graphed.replay()`` saves the device-to-device copies."""
+
+    def __init__(self, model: torch.nn.Module, image1: torch.Tensor, image2: torch.Tensor, warmup: int = 2):
+        if not (image1.is_cuda and image2.is_cuda):
+            raise RuntimeError("GraphedMatcher captures device work: the example images must be CUDA tensors")
+        self.model = model
+        self.inputs = (image1.clone(), image2.clone())
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(image1.device)
+        side.wait_stream(torch.cuda.current_stream(image1.device))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # creates the library's side streams and warms the allocator
+                model(*self.inputs)
+            with torch.cuda.graph(self.graph, stream=side):
+                outs = model(*self.inputs)
+        torch.cuda.current_stream(image1.device).wait_stream(side)
+        self.outputs = (outs,) if torch.is_tensor(outs) else tuple(outs)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    def __call__(self, image1: torch.Tensor, image2: torch.Tensor):
+        for dst, src in zip(self.inputs, (image1, image2)):
+            if src.shape != dst.shape:
+                raise RuntimeError(f"GraphedMatcher was captured for images of shape {tuple(dst.shape)}, got {tuple(src.shape)}")
+            dst.copy_(src, non_blocking=True)
+        return self.replay()

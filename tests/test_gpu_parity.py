@@ -747,3 +747,22 @@ def test_host_batch_matcher_equals_direct_calls():
     assert len(got) == 4 and got[3].dtype == torch.bool and int(got[3].sum()) > 0
     for g, r in zip(got, ref):
         assert torch.equal(g, r)
+
+
+def test_matcher_step_is_graph_capturable():
+    """The whole fused matcher (its side streams included) captures into a CUDA graph; replays on new images give what
+    eager calls give."""
+    from onnx_image_processing_b200.host_pipeline import GraphedMatcher
+    model = om.ShiTomasiBADSinkhornMatcher(96).to(DEV).eval()
+    a1, a2 = (t.to(DEV) for t in O.texture_images(2, 120, 160, seed=41))
+    b1, b2 = (t.to(DEV) for t in O.texture_images(2, 120, 160, seed=42))
+    graphed = GraphedMatcher(model, a1, a2)
+    with torch.no_grad():
+        for x1, x2 in ((b1, b2), (a1, a2), (b1, b2)):
+            want = [t.clone() for t in model(x1, x2)]
+            got = graphed(x1, x2)
+            torch.cuda.synchronize()
+            for g, w in zip(got, want):
+                assert torch.equal(g, w)
+    with pytest.raises(RuntimeError):
+        graphed(a1[:1], a2[:1])
