@@ -410,10 +410,9 @@ struct SparseKpCtx {
     int H, W;
 };
 
-// One pair at one keypoint through the full sampling pipeline (bad.py:504-557).  Kept out of line: inlined into the
-// unrolled pair loop it made the kernel several hundred KB of code, and the kernels stalled on instruction fetch.
+// One pair at one keypoint through the full sampling pipeline (bad.py:504-557).
 template <int HS, bool ORIENTED, bool BILINEAR>
-__device__ __noinline__ float sparse_pair_general(const SparseKpCtx& c, const float* table, int p, int mode, float temperature) {
+__device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx& c, const float* table, int p, int mode, float temperature) {
     using G = WinGeom<HS>;
     constexpr int S = G::S, WP = G::WP;
     const int H = c.H, W = c.W;
@@ -455,6 +454,14 @@ __device__ __noinline__ float sparse_pair_general(const SparseKpCtx& c, const fl
     const float inv_area = __fdiv_rn(1.0f, side * side);
     const float diff = __fsub_rn(sample(row.oy1, row.ox1, r, inv_area), sample(row.oy2, row.ox2, r, inv_area));
     return finish_value(diff, row.thr, mode, temperature);
+}
+// Out-of-line form for the kernels that have the tap-table fast path (nearest, not oriented): there this is the rare
+// border path, and inlined into the unrolled pair loop next to the fast path it made the kernel several hundred KB of
+// code (stalls on instruction fetch).  The oriented / bilinear kernels have only this path and inline it, so that the
+// pairs of a thread overlap.
+template <int HS, bool ORIENTED, bool BILINEAR>
+__device__ __noinline__ float sparse_pair_general(const SparseKpCtx& c, const float* table, int p, int mode, float temperature) {
+    return sparse_pair_general_impl<HS, ORIENTED, BILINEAR>(c, table, p, mode, temperature);
 }
 
 // one keypoint whose window `win` is in flight / has landed on mbarrier `bar` (phase `parity`).  NPP = pairs per
@@ -535,7 +542,8 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                d[q] = sparse_pair_general<HS, ORIENTED, BILINEAR>(c, a.table, p, a.mode, a.temperature);
+                d[q] = FAST ? sparse_pair_general<HS, ORIENTED, BILINEAR>(c, a.table, p, a.mode, a.temperature)
+                            : sparse_pair_general_impl<HS, ORIENTED, BILINEAR>(c, a.table, p, a.mode, a.temperature);
                 ss = fmaf(d[q], d[q], ss);
             }
         }
