@@ -210,8 +210,8 @@ def per_kernel_times(model, workload, i1, i2, steps, warmup):
         nat.check(lib.om_debug_detect_stage(ptr(i1), B, H, W, bs, r, margin, thr, K, ptr(kp), ptr(ks), ptr(ws),
                                             ws.numel(), sp, stage), "om_debug_detect_stage")
     # x2: the step runs every per-image kernel once per image of the pair
-    if bs == 3 and r == 3:      # split sweep form: score kernel, then NMS kernel through a score map in the workspace
-        out["score3_sweep_kernel"] = dict(ms=event_time_ms(lambda: det(2), steps, warmup, st), per_step=2,
+    if bs in (3, 5) and r == 3:  # split sweep form: score kernel, then NMS kernel through a score map in the workspace
+        out["score3_sweep_kernel" if bs == 3 else "score5_sweep_kernel"] = dict(ms=event_time_ms(lambda: det(2), steps, warmup, st), per_step=2,
                                          bytes=B * (2 * H * W * 4))
         out["nms3_sweep_kernel"] = dict(ms=event_time_ms(lambda: det(3), steps, warmup, st), per_step=2,
                                        bytes=B * (H * W * 4))

@@ -222,8 +222,8 @@ int om_match_pairs_f32(const om_match_params* p, const float* image1, const floa
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 
-/* Stencil kernel selection: 0 = default routing (block 3 / radius 3: split register-sweep kernels, i.e. a score
- * kernel and an NMS kernel; other block 3/5, radius 3/5: tiled shared-memory kernel), 1 = generic (runtime block
+/* Stencil kernel selection: 0 = default routing (block 3 or 5 with radius 3: split register-sweep kernels, i.e. a
+ * score kernel and an NMS kernel; block 3 or 5 with radius 5: tiled shared-memory kernel), 1 = generic (runtime block
  * size / radius) kernel, 2 = tiled kernel, 3 = fused sweep kernel, 4 = split sweep kernels; lets the tests check
  * them against each other. */
 void om_debug_force_generic_stencil(int on);
@@ -237,8 +237,8 @@ void om_debug_match_streams(int n);
  * copies by the keypoint's thread group (cross-check, slower); bit 1 / bit 2 (diagnosis only, wrong results): skip the
  * window fetch / skip the pair arithmetic. */
 void om_debug_dense_window(int tma);
-/* Score kernel of the split sweep form at block size 3: 1 = score3_sweep_kernel (default), 2 = the same at 6 CTAs
- * per SM, 0 = stencil_sweep_kernel<.., NMS = false> (cross-check). */
+/* Score kernel of the split sweep form: 1 = score3_sweep_kernel / score5_sweep_kernel (default), 2 = the same at
+ * another occupancy (6 / 3 CTAs per SM instead of 5 / 4), 0 = stencil_sweep_kernel<.., NMS = false> (cross-check). */
 void om_debug_score_variant(int v);
 /* Sweep-kernel tuning.  min_blocks 3 or 4: fused sweep kernel, output rows per tile (0 = default 40) and resident
  * CTAs per SM.  min_blocks 99: split kernels, strip_rows for both; 100 + n: strip_rows for the score kernel, n rows
