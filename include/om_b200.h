@@ -183,7 +183,8 @@ int om_mutual_matches_f32(const float* probs, const float* kpts1, const float* k
  * pts_batched = 1).  probs (B,N+1,M+1); pts1 (B|1,N,2), pts2 (B|1,M,2): normalised (x, y) = K^-1 [x, y, 1];
  * valid1 (B,N), valid2 (B,M): bytes 0/1, both or neither; E (B,3,3).  Bidirectional top_k mask AND P > 0.01, Hartley
  * normalisation, 9x9 normal equations, n_iter shifted power iterations, denormalisation, projection onto singular
- * values (s, s, 0) with n_iter_manifold power iterations.  Limits: top_k <= 8, N, M <= 8192; top_k > N or M is
+ * values (s, s, 0) with n_iter_manifold power iterations.  One 8-CTA thread-block cluster per pair (row slices, column
+ * statistics combined over distributed shared memory).  Limits: top_k <= 8, N, M <= 8192; top_k > N or M is
  * OM_ERR_SHAPE (torch.topk raises). */
 int om_essential_matrix_f32(const float* probs, const float* pts1, const float* pts2, const unsigned char* valid1,
                             const unsigned char* valid2, int B, int N, int M, int pts_batched, int top_k, int n_iter,
@@ -230,6 +231,9 @@ void om_debug_force_generic_stencil(int on);
 /* NMS kernel of the split sweep form at radius 3: 1 = nms3_sweep_kernel (default), 2 = the same at 6 CTAs per SM,
  * 0 = the any-radius nms_sweep_kernel (cross-check). */
 void om_debug_nms_variant(int v);
+/* Essential-matrix head: 1 = an 8-CTA cluster per pair (default; falls back to one CTA when the per-column scratch does
+ * not fit shared memory), 0 = one CTA per pair. */
+void om_debug_essential_variant(int clustered);
 /* Fused matcher: 4 (default) = image 2's detector / descriptor chain and both integral-image builds run on side streams
  * next to image 1's chain, 2 = only image 2's chain on a side stream, 1 = everything on the caller's stream. */
 void om_debug_match_streams(int n);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "om_debug_force_generic_stencil": (None, [c_int]),
     "om_debug_sweep_tuning": (None, [c_int, c_int]),
     "om_debug_nms_variant": (None, [c_int]),
+    "om_debug_essential_variant": (None, [c_int]),
     "om_debug_match_streams": (None, [c_int]),
     "om_debug_dense_window": (None, [c_int]),
     "om_debug_score_variant": (None, [c_int]),

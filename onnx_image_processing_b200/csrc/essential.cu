@@ -15,9 +15,12 @@
 // The long sums (marginals, centroids, the 81 entries of M_flat) are accumulated in double in a fixed order and rounded
 // to float once; the reference accumulates them in float inside ATen's sum / matmul (order unspecified), so the two
 // agree to float rounding of those sums.  Phase E repeats the reference's float operations in index order.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace om {
 
@@ -187,10 +190,17 @@ __device__ M3 project_onto_manifold(const M3& E, int iters) {
     return mul3(mul3(U, S), transpose3(V));
 }
 
+// CLS = CTAs per pair.  CLS = 8: a thread-block cluster shares one pair; CTA r owns the rows [r * RS, (r + 1) * RS) of P for
+// every pass (row statistics are complete per CTA, column statistics are partial per CTA and combined through
+// distributed shared memory after a cluster barrier), rank 0 finishes the algebra.  CLS = 1: one CTA does everything
+// (used when the per-column scratch does not fit shared memory).  One pair on one SM took 0.65 ms (2.7 M warp
+// instructions on 16 warps); eight SMs per pair bring a single pair to ~0.1 ms.
+template <int CLS>
 __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double scratch[EW];
     __shared__ double mpart[EW][81];
+    __shared__ double mcta[81];
     __shared__ float wf2[EW][6];
     __shared__ float m9[81];
     const int N = a.N, M = a.M, k = a.top_k;
@@ -200,11 +210,22 @@ __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
     float* w2 = w1 + N;
     float* mul1 = w2 + M;                            // validity factors (1 or 0)
     float* mul2 = mul1 + N;
-    const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    double* w2part = reinterpret_cast<double*>(mul2 + M + ((3 * N + 3 * M) & 1));   // CLS > 1: column sums over the own rows
+    float* colk = reinterpret_cast<float*>(w2part + M);                             // CLS > 1: k largest of each column over the own rows
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    int rank = 0;
+    if constexpr (CLS > 1) rank = (int)cg::this_cluster().block_rank();
+    const int z = blockIdx.x / CLS;
+    const int RS = (N + CLS - 1) / CLS;              // rows per CTA
+    const int i_lo = min(rank * RS, N), i_hi = min(i_lo + RS, N);
     const float* P = a.P + (size_t)z * (N + 1) * (M + 1);
     const float* pts1 = a.pts1 + (a.pts_batched ? (size_t)z * N * 2 : 0);
     const float* pts2 = a.pts2 + (a.pts_batched ? (size_t)z * M * 2 : 0);
     const unsigned full = 0xffffffffu;
+    auto csync = [&]() {
+        if constexpr (CLS > 1) cg::this_cluster().sync();
+        else __syncthreads();
+    };
 
     for (int i = tid; i < N; i += ET) mul1[i] = (a.valid1 == nullptr || a.valid1[(size_t)z * N + i]) ? 1.0f : 0.0f;
     for (int j = tid; j < M; j += ET) mul2[j] = (a.valid2 == nullptr || a.valid2[(size_t)z * M + j]) ? 1.0f : 0.0f;
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
     };
 
     // ---- A: k-th largest of every row and column ------------------------------------------------------------------
-    for (int i = wrp; i < N; i += EW) {
+    for (int i = i_lo + wrp; i < i_hi; i += EW) {
         float t[E_MAXK];
 #pragma unroll
         for (int q = 0; q < E_MAXK; ++q) t[q] = -CUDART_INF_F;
@@ -238,21 +259,44 @@ __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
         float t[E_MAXK];
 #pragma unroll
         for (int q = 0; q < E_MAXK; ++q) t[q] = -CUDART_INF_F;
-        for (int i = 0; i < N; ++i) topk_insert(t, k, masked(i, j));
-        float kth = t[0];
+        for (int i = i_lo; i < i_hi; ++i) topk_insert(t, k, masked(i, j));
+        if constexpr (CLS > 1) {
 #pragma unroll
-        for (int q = 1; q < E_MAXK; ++q)
-            if (q < k) kth = t[q];
-        thr_col[j] = kth;
+            for (int q = 0; q < E_MAXK; ++q)
+                if (q < k) colk[(size_t)j * k + q] = t[q];
+        } else {
+            float kth = t[0];
+#pragma unroll
+            for (int q = 1; q < E_MAXK; ++q)
+                if (q < k) kth = t[q];
+            thr_col[j] = kth;
+        }
     }
-    __syncthreads();
+    csync();
+    if constexpr (CLS > 1) {                         // merge the CLS partial lists of every column (each CTA, all columns)
+        for (int j = tid; j < M; j += ET) {
+            float t[E_MAXK];
+#pragma unroll
+            for (int q = 0; q < E_MAXK; ++q) t[q] = -CUDART_INF_F;
+            for (int rr = 0; rr < CLS; ++rr) {
+                const float* rk = cg::this_cluster().map_shared_rank(colk, rr);
+                for (int q = 0; q < k; ++q) topk_insert(t, k, rk[(size_t)j * k + q]);
+            }
+            float kth = t[0];
+#pragma unroll
+            for (int q = 1; q < E_MAXK; ++q)
+                if (q < k) kth = t[q];
+            thr_col[j] = kth;
+        }
+        __syncthreads();
+    }
     auto weight = [&](int i, int j) -> float {       // :221-237
         const float v = masked(i, j);
         return (v >= thr_row[i] && v >= thr_col[j] && v > 0.01f) ? v : 0.0f;
     };
 
     // ---- B: marginals ----------------------------------------------------------------------------------------------
-    for (int i = wrp; i < N; i += EW) {
+    for (int i = i_lo + wrp; i < i_hi; i += EW) {
         double s = 0.0;
         for (int j = lane; j < M; j += 32) s += (double)weight(i, j);
         s = warp_sum_d(s);
@@ -260,18 +304,29 @@ __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
     }
     for (int j = tid; j < M; j += ET) {
         double s = 0.0;
-        for (int i = 0; i < N; ++i) s += (double)weight(i, j);
-        w2[j] = (float)s;
+        for (int i = i_lo; i < i_hi; ++i) s += (double)weight(i, j);
+        if constexpr (CLS > 1) w2part[j] = s;
+        else w2[j] = (float)s;
     }
-    __syncthreads();
+    csync();
+    if constexpr (CLS > 1) {                         // column sums over all rows; the other CTAs' slices of the row sums
+        for (int j = tid; j < M; j += ET) {
+            double s = 0.0;
+            for (int rr = 0; rr < CLS; ++rr) s += cg::this_cluster().map_shared_rank(w2part, rr)[j];
+            w2[j] = (float)s;
+        }
+        for (int i = tid; i < N; i += ET)
+            if (i < i_lo || i >= i_hi) w1[i] = cg::this_cluster().map_shared_rank(w1, i / RS)[i];
+        __syncthreads();
+    }
 
-    // ---- C: Hartley normalisation of both point sets ---------------------------------------------------------------
+    // ---- C: Hartley normalisation of both point sets (every CTA, from the complete marginals) --------------------
     const Hartley h1 = hartley_from(pts1, w1, N, scratch);
     const Hartley h2 = hartley_from(pts2, w2, M, scratch);
 
     // ---- D: M_flat = F1^T (W F2), one warp per row of W ------------------------------------------------------------
     double acc[3] = {0.0, 0.0, 0.0};                 // entries lane, lane + 32, lane + 64 of the 9x9 (pr, qs)
-    for (int i = wrp; i < N; i += EW) {
+    for (int i = i_lo + wrp; i < i_hi; i += EW) {
         if (w1[i] == 0.0f) continue;                 // every weight of the row is zero (weights are >= 0)
         double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // sum_j w f2 f2^T: xx, xy, x, yy, y, 1
         for (int j = lane; j < M; j += 32) {
@@ -315,12 +370,23 @@ __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < EW; ++w) s += mpart[w][tid];
+        mcta[tid] = s;
+    }
+    csync();
+    if (rank == 0 && tid < 81) {
+        double s = 0.0;
+        if constexpr (CLS > 1) {
+            for (int rr = 0; rr < CLS; ++rr) s += cg::this_cluster().map_shared_rank(mcta, rr)[tid];
+        } else {
+            s = mcta[tid];
+        }
         // (pr, qs) -> (pq, rs): M_mat[3p+q][3r+s] = M_flat[3p+r][3q+s]   (:263)
         const int pr = tid / 9, qs = tid - 9 * pr;
         const int p = pr / 3, r = pr - 3 * p, q = qs / 3, sidx = qs - 3 * q;
         m9[(3 * p + q) * 9 + (3 * r + sidx)] = (float)s;
     }
-    __syncthreads();
+    csync();                                         // rank 0 has read every CTA's partial sums: the others may leave
+    if (rank != 0) return;
 
     // ---- E: eigenvector, denormalisation, manifold projection (warp 0) --------------------------------------------
     if (wrp != 0) return;
@@ -359,11 +425,15 @@ __global__ void __launch_bounds__(ET) essential_kernel(EssArgs a) {
         for (int j = 0; j < 3; ++j) out[i * 3 + j] = Eo.a[i][j];
 }
 
+int g_essential_cluster = 1;   // om_debug_essential_variant: 0 = one CTA per pair, 1 = an 8-CTA cluster per pair (default)
+
 }  // namespace
 
 }  // namespace om
 
 using namespace om;
+
+extern "C" void om_debug_essential_variant(int clustered) { g_essential_cluster = clustered ? 1 : 0; }
 
 extern "C" int om_essential_matrix_f32(const float* probs, const float* pts1, const float* pts2, const unsigned char* valid1,
                                        const unsigned char* valid2, int B, int N, int M, int pts_batched, int top_k,
@@ -374,11 +444,32 @@ extern "C" int om_essential_matrix_f32(const float* probs, const float* pts1, co
     if (top_k < 1 || top_k > N || top_k > M) return OM_ERR_SHAPE;         // torch.topk raises for k > dim
     if (n_iter < 0 || n_iter_manifold < 0) return OM_ERR_PARAM;
     if (top_k > E_MAXK || N > 8192 || M > 8192) return OM_ERR_LIMIT;
-    const size_t smem = (size_t)(3 * N + 3 * M) * sizeof(float);
-    // the kernel also has ~11 KB of static shared memory: opt in whenever the sum may pass the 48 KB default
-    if (smem > 32 * 1024) OM_CUDA(cudaFuncSetAttribute(essential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EssArgs a{probs, pts1, pts2, valid1, valid2, N, M, top_k, n_iter, n_iter_manifold, pts_batched, E};
-    essential_kernel<<<B, ET, smem, (cudaStream_t)stream>>>(a);
+    // floats: thresholds, marginals, validity factors (3N + 3M); cluster form: + one double and top_k floats per column
+    const size_t base = (size_t)(3 * N + 3 * M + ((3 * N + 3 * M) & 1)) * sizeof(float);
+    const size_t clustered = base + (size_t)M * sizeof(double) + (size_t)M * top_k * sizeof(float);
+    constexpr int CLS = 8;
+    // many small pairs already fill the GPU with one CTA each (measured: 64 pairs of 128 points 98 us vs 154 us clustered)
+    const bool small_and_many = B >= 48 && (long long)N * M <= 256ll * 256ll;
+    if (g_essential_cluster && !small_and_many && clustered + 16 * 1024 <= 200 * 1024 && (long long)B * CLS < (1ll << 31)) {
+        if (clustered > 32 * 1024)
+            OM_CUDA(cudaFuncSetAttribute(essential_kernel<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clustered));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * CLS), 1, 1);
+        cfg.blockDim = dim3(ET, 1, 1);
+        cfg.dynamicSmemBytes = clustered;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CLS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        OM_CUDA(cudaLaunchKernelEx(&cfg, essential_kernel<CLS>, a));
+    } else {
+        // the kernel also has ~12 KB of static shared memory: opt in whenever the sum may pass the 48 KB default
+        if (base > 32 * 1024) OM_CUDA(cudaFuncSetAttribute(essential_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+        essential_kernel<1><<<B, ET, base, (cudaStream_t)stream>>>(a);
+    }
     OM_AFTER_LAUNCH();
     return OM_OK;
 }

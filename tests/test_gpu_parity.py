@@ -766,3 +766,26 @@ def test_matcher_step_is_graph_capturable():
                 assert torch.equal(g, w)
     with pytest.raises(RuntimeError):
         graphed(a1[:1], a2[:1])
+
+
+@pytest.mark.parametrize("name", G.names("essential_module") + G.names("essential_grid")[:2])
+def test_essential_cluster_and_single_cta_forms_agree(name):
+    """The 8-CTA cluster form (row slices, column statistics over distributed shared memory) and the one-CTA form compute
+    the same weights and sums (partial sums are combined in double before the single rounding)."""
+    g = G.load(name)
+    P, p1, p2, v1, v2, kw = _essential_case(g)
+    args = dict(top_k=3, n_iter=30, n_iter_manifold=10)
+    args.update(kw)
+    vb = (None, None) if v1 is None else (v1[None].to(DEV), v2[None].to(DEV))
+    lib = _native.lib()
+    outs = []
+    for clustered in (1, 0):
+        lib.om_debug_essential_variant(clustered)
+        try:
+            outs.append(_ops.essential_matrix(P[None].to(DEV), p1[None].to(DEV), p2[None].to(DEV), vb[0], vb[1], args["top_k"],
+                                              args["n_iter"], args["n_iter_manifold"]).cpu()[0])
+        finally:
+            lib.om_debug_essential_variant(1)
+    scale = float(g["E"].abs().max())
+    assert float((outs[0] - outs[1]).abs().max()) <= 2e-6 * scale
+    assert float((outs[0] - g["E"]).abs().max()) <= E_RTOL * scale
