@@ -55,6 +55,11 @@ __device__ __forceinline__ float sample_coord(float pos, float scale, float half
     return fminf(fmaxf(u, 0.0f), max_val);
 }
 
+// slot -> pair index (pair_order.inc): the built-in orders for 256 / 512 pairs, the identity otherwise
+__device__ __forceinline__ int pair_of_slot(int slot, int P) {
+    return P == 256 ? (int)OM_PAIR_ORDER_256[slot] : (P == 512 ? (int)OM_PAIR_ORDER_512[slot] : slot);
+}
+
 __device__ __forceinline__ float finish_value(float diff, float thr, int mode, float temperature) {
     const float centered = __fsub_rn(diff, thr);                       // bad.py:212 / :559
     if (mode == OM_DESC_RAW) return centered;
@@ -469,7 +474,8 @@ __device__ __noinline__ float sparse_pair_general(const SparseKpCtx& c, const fl
 template <int HS, bool ORIENTED, bool BILINEAR, int NPP>
 __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long kidx, int z, float ky, float kx,
                                                  const unsigned int* win, uint32_t bar, uint32_t parity, float* red,
-                                                 float* sTheta, const uint4* sTap, const float2* sThr, int g, int t) {
+                                                 float* sTheta, const uint4* sTap, const float2* sThr,
+                                                 const unsigned short* sIdx, int g, int t) {
     constexpr bool FAST = !ORIENTED && !BILINEAR;
     const int H = a.H, W = a.W;
     float* out = a.desc + (size_t)kidx * a.P;
@@ -556,7 +562,7 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
 #pragma unroll
     for (int q = 0; q < NPP; ++q) {
         const int p = t + q * TPG;
-        if (p < a.P) out[p] = d[q] * inv;
+        if (p < a.P) out[fast ? (int)sIdx[p] : p] = d[q] * inv;     // fast path: slot p holds pair sIdx[p]
     }
 }
 
@@ -575,6 +581,7 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
     unsigned int* sWin = reinterpret_cast<unsigned int*>(smem_raw);             // GROUPS x NBUF x GSTRIDE
     uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * NBUF * G::GSTRIDE);  // fast path: 2 x 4 window byte offsets per pair
     float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? 2 * a.P : 0));      //            {threshold, 1/area}
+    unsigned short* sIdx = reinterpret_cast<unsigned short*>(sThr + (FAST ? a.P : 0));   //     slot -> pair (pair_order.inc)
 
     const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
     if (threadIdx.x == 0) {
@@ -584,7 +591,11 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
     }
     if (FAST) {
         for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
-            const PairRow row = load_pair(a.table, p);
+            // slot p takes pair pair_of_slot(p): the 32 lanes of a tap read are 32 consecutive slots, ordered for few bank
+            // conflicts (the window geometry differs from the dense kernel's by a constant offset: same order)
+            const int pair = pair_of_slot(p, a.P);
+            sIdx[p] = (unsigned short)pair;
+            const PairRow row = load_pair(a.table, pair);
             const int r = (int)row.r;
             const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
             auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * G::WP + x) * 4u; };
@@ -623,7 +634,7 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
         int z;
         if (win_needed(a, kidx, ky, kx, z)) {
             sparse_win_group<HS, ORIENTED, BILINEAR, NPP>(a, kidx, z, ky, kx, wbuf + buf * G::GSTRIDE, bar0 + 8u * buf, phase[buf],
-                                                     red, sTheta, sTap, sThr, g, t);
+                                                     red, sTheta, sTap, sThr, sIdx, g, t);
             phase[buf] ^= 1u;
         } else if (!(ky >= 0.0f)) {                                 // bad.py:461, :570 -> the row is all zeros
             float* out = a.desc + (size_t)kidx * a.P;
@@ -642,7 +653,7 @@ int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t s
     OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, G::WP, G::WR));
     constexpr int NBUF = 1;
     const size_t smem = (size_t)GROUPS * NBUF * G::GSTRIDE * 4 +
-                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (2 * sizeof(uint4) + sizeof(float2)) : 0);
+                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (2 * sizeof(uint4) + sizeof(float2) + sizeof(unsigned short)) : 0);
     const long long total = (long long)a.B * a.K;
     const long long nblk = (total + GROUPS - 1) / GROUPS;
     const int per_sm = (int)(228 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (228 KB, 1 KB reserved per CTA)
@@ -1051,11 +1062,6 @@ __device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long k
 #pragma unroll
     for (int q = 0; q < NPP; ++q)
         if (pidx[q] >= 0) out[pidx[q]] = d[q] * inv;
-}
-
-// slot -> pair index (pair_order.inc): the built-in orders for 256 / 512 pairs, the identity otherwise
-__device__ __forceinline__ int pair_of_slot(int slot, int P) {
-    return P == 256 ? (int)OM_PAIR_ORDER_256[slot] : (P == 512 ? (int)OM_PAIR_ORDER_512[slot] : slot);
 }
 
 // Every 64-thread group walks its keypoints (grid-stride); NBUF as in sparse_win_kernel.
