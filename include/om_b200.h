@@ -255,7 +255,8 @@ void om_debug_force_generic_sinkhorn(int on);
 /* 0: tcgen05/TMEM cluster kernel (default; scaling-form loop when exp(-unused/eps) is safe),
  * 1: FP32-FFMA cluster kernel, 2: generic kernels, 3: tcgen05 kernel with the log-domain loop forced,
  * 4: tcgen05 kernel with the 3xTF32 similarity GEMM forced (default: two-term fp16 split),
- * 5: generic kernels with the log-domain loop forced (2: scaling form when safe). */
+ * 5: generic kernels with the log-domain loop forced (2: scaling form when safe),
+ * 7: generic kernels with the FP32 FFMA cost GEMM (2 and 5 run the cost GEMM on tcgen05 when D % 32 == 0). */
 void om_debug_sinkhorn_variant(int variant);
 /* Device buffer of (B*8 CTAs) x 12 int64: the tcgen05 kernel stores clock64 stamps of its phases there
  * (NULL switches tracing off).  Used by tools/sinkhorn_trace.py only. */

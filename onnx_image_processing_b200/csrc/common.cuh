@@ -120,6 +120,9 @@ int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, i
                         float unused, float* P, cudaStream_t st);
 
 size_t sinkhorn_workspace_bytes(int B, int N, int M, int D);
+// cost matrix of the generic Sinkhorn path on tcgen05 (sinkhorn_tc.cu); D % 32 == 0; *ovf != 0: does nothing
+int cost_tc_launch(const float* d1, const float* d2, const float* n1, const float* n2, int B, int N, int M, int D, float eps,
+                   float dustbin, int as_exp, float* S, const unsigned int* ovf, cudaStream_t st);
 int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
                     float unused_score, int distance_l1, float* P, void* ws, size_t ws_bytes, cudaStream_t st);
 

@@ -38,14 +38,19 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // generic path
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sqnorm_kernel(const float* d, long long rows, int D, float* out) {
+// squared norms of the rows; ovf (nullable): set when some |x| >= 60000 (out of range for the fp16 terms of cost_tc_kernel)
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* d, long long rows, int D, float* out, unsigned int* ovf) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const float* p = d + row * D;
-    float acc = 0.0f;
-    for (int k = threadIdx.x & 31; k < D; k += 32) acc = fmaf(p[k], p[k], acc);
+    float acc = 0.0f, mx = 0.0f;
+    for (int k = threadIdx.x & 31; k < D; k += 32) {
+        acc = fmaf(p[k], p[k], acc);
+        mx = fmaxf(mx, fabsf(p[k]));
+    }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) out[row] = acc;
+    if (ovf != nullptr && !(mx < 60000.0f)) atomicOr(ovf, 1u);
 }
 
 // S[b][i][j] = -clamp(n1_i + n2_j - 2 a_i.b_j, 0) / eps for i<N, j<M; dustbin elsewhere (sinkhorn.py:98-103, :178-187)
@@ -55,8 +60,10 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* d, long long r
 // index order (one fmaf each), as the 64 x 64 / 4 x 4 kernel it replaces did: 26 -> ~50 TFLOP/s.
 constexpr int CT = 128, CK = 16, CPITCH = CT + 4;
 __global__ void __launch_bounds__(256, 2) cost_l2_kernel(const float* d1, const float* d2, const float* n1, const float* n2,
-                                                      int N, int M, int D, float eps, float dustbin, int as_exp, float* S) {
+                                                      int N, int M, int D, float eps, float dustbin, int as_exp, float* S,
+                                                      const unsigned int* only_if) {
     __shared__ __align__(16) float As[2][CK][CPITCH];
+    if (only_if != nullptr && *only_if == 0u) return;                 // the tensor-core kernel did this launch's work
     __shared__ __align__(16) float Bs[2][CK][CPITCH];
     const int z = blockIdx.z, i0 = blockIdx.y * CT, j0 = blockIdx.x * CT;
     const float* A = d1 + (size_t)z * N * D;
@@ -294,6 +301,7 @@ SkWs carve_sk(void* ws, int B, int N, int M) {
 }
 
 int g_generic_allow_scaling = 1;   // test hook: 0 forces the log-domain generic kernels
+int g_generic_tc = 1;              // test hook: 0 forces the FP32 FFMA cost kernel on the generic path
 
 int sinkhorn_generic(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                      float dustbin, int l1, float* P, void* ws, cudaStream_t st) {
@@ -304,11 +312,17 @@ int sinkhorn_generic(const float* d1, const float* d2, int B, int N, int M, int 
         cost_l1_kernel<<<dim3((M + 32) / 32, (N + 8) / 8, B), 256, 0, st>>>(d1, d2, N, M, D, eps, dustbin, scaling, P);
         OM_AFTER_LAUNCH();
     } else {
-        sqnorm_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, st>>>(d1, (long long)B * N, D, w.n1);
+        // similarity GEMM on tcgen05 (two-term fp16 split) when D allows; the FP32 FFMA kernel runs behind it and only
+        // does work when some |x| >= 60000 was seen (flag in the first word of w.u, which the iterations overwrite later)
+        const bool tc = g_generic_tc && D % 32 == 0;
+        unsigned int* ovf = tc ? reinterpret_cast<unsigned int*>(w.u) : nullptr;
+        if (tc) OM_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned int), st));
+        sqnorm_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, st>>>(d1, (long long)B * N, D, w.n1, ovf);
         OM_AFTER_LAUNCH();
-        sqnorm_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(d2, (long long)B * M, D, w.n2);
+        sqnorm_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(d2, (long long)B * M, D, w.n2, ovf);
         OM_AFTER_LAUNCH();
-        cost_l2_kernel<<<dim3((M + CT) / CT, (N + CT) / CT, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, scaling, P);
+        if (tc) OM_TRY(cost_tc_launch(d1, d2, w.n1, w.n2, B, N, M, D, eps, dustbin, scaling, P, ovf, st));
+        cost_l2_kernel<<<dim3((M + CT) / CT, (N + CT) / CT, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, scaling, P, ovf);
         OM_AFTER_LAUNCH();
     }
     if (scaling) {
@@ -618,7 +632,8 @@ int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int 
 
 // 0: tcgen05 cluster kernel (scaling-form loop when safe), 1: FFMA cluster kernel, 2: generic kernels,
 // 3: tcgen05 cluster kernel with the log-domain loop forced, 4: tcgen05 cluster kernel with the 3xTF32 GEMM forced,
-// 5: generic kernels with the log-domain loop forced (2 = generic kernels, scaling form when safe)
+// 5: generic kernels with the log-domain loop forced (2 = generic kernels, scaling form when safe),
+// 7: generic kernels with the FP32 FFMA cost GEMM (2 / 5: cost GEMM on tcgen05 when D % 32 == 0)
 int g_sinkhorn_variant = 0;
 
 }  // namespace
@@ -638,8 +653,9 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
     if (iterations <= 0 || !(epsilon > 0.0f)) return OM_ERR_PARAM;        // sinkhorn.py:66-69
     if (B > 65535) return OM_ERR_LIMIT;
     const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && g_sinkhorn_variant != 2 &&
-                      g_sinkhorn_variant != 5 && (long long)B * CL < (1ll << 31);
+                      g_sinkhorn_variant != 5 && g_sinkhorn_variant != 7 && (long long)B * CL < (1ll << 31);
     g_generic_allow_scaling = g_sinkhorn_variant != 5;
+    g_generic_tc = g_sinkhorn_variant != 7;
     if (fast && (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 3 || g_sinkhorn_variant == 4)) {
         g_tc_allow_scaling = g_sinkhorn_variant != 3;
         g_tc_allow_f16 = g_sinkhorn_variant != 4;

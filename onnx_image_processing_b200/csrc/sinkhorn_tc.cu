@@ -827,11 +827,174 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
     }   // !XD
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Cost matrix of the generic path (more than 512 keypoints) on tcgen05: S[z][i][j] for one 64 (i) x 128 (j) tile per CTA,
+// same two-term fp16 split, tile layout, producer items and MMA stream as the cluster kernel above (one 128-row block
+// of d2 as "A", 64 rows of d1 as "B").  Warps 0..3 stage the operands and read TMEM lanes 32w..32w+31 in the epilogue
+// (lane = column j: coalesced rows of S), warp 4 issues the MMAs.  When some |x| >= 60000 was seen (*ovf != 0) the CTA
+// exits at once and the FP32 FFMA kernel, launched behind it, does the work instead (and exits at once otherwise).
+// ------------------------------------------------------------------------------------------
+constexpr int GA_ROWS = 128, GB_ROWS = 64;
+constexpr int GA_LBO = GA_ROWS * 16, GB_LBO = GB_ROWS * 16;
+constexpr int GA_TERM = 4 * GA_LBO, GB_TERM = 4 * GB_LBO;          // 32 floats of K = 4 K groups of 8 halves
+constexpr int G_STAGE = 2 * GA_TERM + 2 * GB_TERM;                 // 24 KB
+constexpr int G_THREADS = 160;
+
+__global__ void __launch_bounds__(G_THREADS) cost_tc_kernel(const float* d1, const float* d2, const float* n1, const float* n2,
+                                                            int N, int M, int D, float eps, int as_exp, float* S,
+                                                            const unsigned int* ovf) {
+    extern __shared__ __align__(128) unsigned char gsm[];
+    __shared__ __align__(8) uint64_t bars[5];                       // [0,1] stage free, [2] GEMM done, [3,4] stage full
+    __shared__ uint32_t tmem_slot;
+    if (*ovf != 0u) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int z = blockIdx.z, j0 = blockIdx.x * GA_ROWS, i0 = blockIdx.y * GB_ROWS;
+    const float* A = d2 + (size_t)z * M * D;
+    const float* Bm = d1 + (size_t)z * N * D;
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        mbar_init(smem_u32(&bars[2]), 1);
+        mbar_init(smem_u32(&bars[3]), 128);
+        mbar_init(smem_u32(&bars[4]), 128);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t stage0 = smem_u32(gsm);
+    constexpr int KC2 = 32, NITEM = 48, IPW = NITEM / 4, HALF = IPW / 2;
+    const int nchunks = D / KC2;
+    if (warp < 4) {
+        const int prow = lane >> 3, seg = lane & 7, kgl = seg >> 1, half = seg & 1;
+        float4 cur[IPW];
+        const float* src[IPW];
+        uint32_t dst[IPW];
+#pragma unroll
+        for (int t = 0; t < IPW; ++t) {
+            const int i = warp + 4 * t;
+            src[t] = nullptr;
+            if (i < 32) {                                           // d2 rows: MMA "A"
+                const int rl = 4 * i + prow, j = j0 + rl;
+                if (j < M) src[t] = A + (size_t)j * D + 4 * seg;
+                dst[t] = (uint32_t)(kgl * GA_LBO + rl * 16 + half * 8);
+            } else {                                                // d1 rows: MMA "B"
+                const int rl = 4 * (i - 32) + prow, r = i0 + rl;
+                if (r < N) src[t] = Bm + (size_t)r * D + 4 * seg;
+                dst[t] = (uint32_t)(2 * GA_TERM + kgl * GB_LBO + rl * 16 + half * 8);
+            }
+        }
+        auto fetch = [&](int c, int t0, int t1) {
+#pragma unroll
+            for (int t = 0; t < IPW; ++t)
+                if (t >= t0 && t < t1)
+                    cur[t] = (src[t] != nullptr && c < nchunks) ? __ldg(reinterpret_cast<const float4*>(src[t] + c * KC2))
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto stage = [&](unsigned char* st, int t0, int t1) {
+#pragma unroll
+            for (int t = 0; t < IPW; ++t) {
+                if (t >= t0 && t < t1) {
+                    uint2 hi, lo;
+                    split_f16(cur[t], hi, lo);
+                    *reinterpret_cast<uint2*>(st + dst[t]) = hi;
+                    *reinterpret_cast<uint2*>(st + dst[t] + ((warp + 4 * t) < 32 ? GA_TERM : GB_TERM)) = lo;
+                }
+            }
+        };
+        fetch(0, 0, IPW);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1;
+            if (c >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((c >> 1) - 1) & 1));      // MMAs of chunk c-2 done
+            unsigned char* st = gsm + s * G_STAGE;
+            stage(st, 0, HALF);
+            fetch(c + 1, 0, HALF);
+            stage(st, HALF, IPW);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&bars[3 + s]));
+            fetch(c + 1, HALF, IPW);
+        }
+    } else if (lane == 0) {
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1;
+            mbar_wait(smem_u32(&bars[3 + s]), (uint32_t)((c >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = stage0 + s * G_STAGE;
+#pragma unroll
+            for (int ks = 0; ks < KC2 / 16; ++ks) {
+                const uint64_t ahi = umma_desc(sa + 2 * ks * GA_LBO, GA_LBO, SBO);
+                const uint64_t alo = umma_desc(sa + GA_TERM + 2 * ks * GA_LBO, GA_LBO, SBO);
+                const uint64_t bhi = umma_desc(sa + 2 * GA_TERM + 2 * ks * GB_LBO, GB_LBO, SBO);
+                const uint64_t blo = umma_desc(sa + 2 * GA_TERM + GB_TERM + 2 * ks * GB_LBO, GB_LBO, SBO);
+                umma_f16(tmem_base, ahi, bhi, (c | ks) != 0);
+                umma_f16(tmem_base, ahi, blo, 1u);
+                umma_f16(tmem_base, alo, bhi, 1u);
+            }
+            umma_commit(smem_u32(&bars[s]));
+            if (c == nchunks - 1) umma_commit(smem_u32(&bars[2]));
+        }
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[2]), 0u);                              // every MMA has completed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+        const int j = j0 + 32 * warp + lane;
+        const float n2j = j < M ? n2[(size_t)z * M + j] : 0.0f;
+        float* Sz = S + (size_t)z * (N + 1) * (M + 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * h), r);
+#pragma unroll
+            for (int ii = 0; ii < 32; ++ii) {
+                const int i = i0 + 32 * h + ii;
+                if (i < N && j < M) {
+                    const float dot = __uint_as_float(r[ii]);
+                    const float cost = fmaxf(__fsub_rn(__fadd_rn(n1[(size_t)z * N + i], n2j), __fmul_rn(2.0f, dot)), 0.0f);   // sinkhorn.py:98-103
+                    const float v = __fdiv_rn(-cost, eps);
+                    Sz[(size_t)i * (M + 1) + j] = as_exp ? expf(v) : v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(64) : "memory");
+}
+
+// dustbin row and column of S (sinkhorn.py:182-187) for the tensor-core cost kernel
+__global__ void __launch_bounds__(256) dustbin_fill_kernel(float* S, int N, int M, float value) {
+    float* Sz = S + (size_t)blockIdx.y * (N + 1) * (M + 1);
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e <= M) Sz[(size_t)N * (M + 1) + e] = value;
+    if (e < N) Sz[(size_t)e * (M + 1) + M] = value;
+}
+
 }  // namespace
 
 int g_tc_allow_scaling = 1;         // test hook: 0 forces the log-domain loop of the tcgen05 kernel
 int g_tc_allow_f16 = 1;             // test hook: 0 forces the 3xTF32 similarity GEMM
 long long* g_tc_trace = nullptr;   // debug: device buffer of B*8 CTAs x 8 stamps, set through om_debug_sinkhorn_trace
+
+// tensor-core cost matrix of the generic path; D % 32 == 0.  `ovf` (device): non-zero = out of fp16 range, nothing is done
+int cost_tc_launch(const float* d1, const float* d2, const float* n1, const float* n2, int B, int N, int M, int D, float eps,
+                   float dustbin, int as_exp, float* S, const unsigned int* ovf, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)G_STAGE;     // exactly 48 KB, plus the static barriers: needs the opt-in
+    OM_CUDA(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cost_tc_kernel<<<dim3((M + GA_ROWS - 1) / GA_ROWS, (N + GB_ROWS - 1) / GB_ROWS, B), G_THREADS, smem, st>>>(d1, d2, n1, n2, N, M, D, eps,
+                                                                                                               as_exp, S, ovf);
+    OM_AFTER_LAUNCH();
+    const int len = (N > M ? N : M) + 1;
+    dustbin_fill_kernel<<<dim3((len + 255) / 256, B), 256, 0, st>>>(S, N, M, as_exp ? expf(dustbin) : dustbin);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
 
 int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                         float unused, float* P, cudaStream_t st) {

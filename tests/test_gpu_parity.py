@@ -206,7 +206,7 @@ def test_gather_functions():
 # ------------------------------------------------------------------------------------------
 # Sinkhorn
 # ------------------------------------------------------------------------------------------
-VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32", 5: "generic-log"}
+VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32", 5: "generic-log", 7: "generic-ffma-cost"}
 
 
 def _with_variant(variant, fn):
@@ -255,7 +255,7 @@ def test_sinkhorn_variants_agree_on_matched_descriptors():
     d1 = torch.nn.functional.normalize(torch.randn(3, 512, 256, generator=g), dim=-1)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(512, generator=g)] + 0.02 * torch.randn(3, 512, 256, generator=g), dim=-1)
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.05, 1.0).float()
-    for variant in (0, 1, 2, 3, 4, 5):
+    for variant in (0, 1, 2, 3, 4, 5, 7):
         got = _with_variant(variant, lambda: om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2)))
         m = PR.prob_metrics(got, ref)
         assert PR.probs_ok(m), (VARIANTS[variant], m)
@@ -273,7 +273,7 @@ def test_sinkhorn_descriptors_beyond_fp16_range():
     assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
 
 
-@pytest.mark.parametrize("variant", [0, 5], ids=lambda v: {0: "scaling", 5: "log-domain"}[v])
+@pytest.mark.parametrize("variant", [0, 5, 7], ids=lambda v: {0: "scaling", 5: "log-domain", 7: "ffma-cost"}[v])
 @pytest.mark.parametrize("N,M,eps,dist", [(700, 700, 0.05, "l2"), (1024, 1024, 0.05, "l2"), (600, 901, 1.0, "l2"), (530, 520, 0.2, "l1")])
 def test_sinkhorn_large_k_generic_path(N, M, eps, dist, variant):
     """Beyond the cluster kernel's 512 x 512 (the export default K = 1024 and config 5's K = 2048 live here): the
@@ -789,3 +789,21 @@ def test_essential_cluster_and_single_cta_forms_agree(name):
     scale = float(g["E"].abs().max())
     assert float((outs[0] - outs[1]).abs().max()) <= 2e-6 * scale
     assert float((outs[0] - g["E"]).abs().max()) <= E_RTOL * scale
+
+
+def test_generic_sinkhorn_beyond_fp16_range_and_odd_descriptor_length():
+    """Generic path (more than 512 keypoints): descriptors beyond the fp16 range must take the FP32 cost kernel (the
+    tensor-core kernel steps aside through its overflow flag); a descriptor length that is not a multiple of 32 never
+    uses the tensor-core kernel."""
+    g = torch.Generator().manual_seed(9)
+    d1 = torch.nn.functional.normalize(torch.randn(1, 600, 256, generator=g), dim=-1)
+    d2 = torch.nn.functional.normalize(d1[:, torch.randperm(600, generator=g)] + 0.2 * torch.randn(1, 600, 256, generator=g), dim=-1)
+    scale = 3.0e6
+    ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.5, 1.0).float()
+    got = om.SinkhornMatcher(20, 0.5 * scale * scale, scale * scale).to(DEV)(*_cuda(d1 * scale, d2 * scale))
+    assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
+    e1 = torch.nn.functional.normalize(torch.randn(1, 560, 100, generator=g), dim=-1)
+    e2 = torch.nn.functional.normalize(e1[:, torch.randperm(560, generator=g)] + 0.2 * torch.randn(1, 560, 100, generator=g), dim=-1)
+    ref = O.sinkhorn(e1, e2, 20, 0.3, 1.0)
+    got = om.SinkhornMatcher(20, 0.3, 1.0).to(DEV)(*_cuda(e1, e2))
+    assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
