@@ -946,6 +946,7 @@ __global__ void __launch_bounds__(G_THREADS) cost_tc_kernel(const float* d1, con
     if (warp < 4) {
         const int j = j0 + 32 * warp + lane;
         const float n2j = j < M ? n2[(size_t)z * M + j] : 0.0f;
+        const float scale2 = (float)(1.4426950408889634 / (double)eps);
         float* Sz = S + (size_t)z * (N + 1) * (M + 1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -957,8 +958,8 @@ __global__ void __launch_bounds__(G_THREADS) cost_tc_kernel(const float* d1, con
                 if (i < N && j < M) {
                     const float dot = __uint_as_float(r[ii]);
                     const float cost = fmaxf(__fsub_rn(__fadd_rn(n1[(size_t)z * N + i], n2j), __fmul_rn(2.0f, dot)), 0.0f);   // sinkhorn.py:98-103
-                    const float v = __fdiv_rn(-cost, eps);
-                    Sz[(size_t)i * (M + 1) + j] = as_exp ? expf(v) : v;
+                    // scaling form: K = exp(-cost / eps) as 2^(-cost * log2(e) / eps), the cluster kernel's arithmetic
+                    Sz[(size_t)i * (M + 1) + j] = as_exp ? ex2(__fmul_rn(-cost, scale2)) : __fdiv_rn(-cost, eps);
                 }
             }
         }
