@@ -161,6 +161,10 @@ int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M,
 int om_sinkhorn_filter_rows_f32(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin,
                                 unsigned char* valid, void* stream);
 
+/* SinkhornMatcherWithScores, matching/sinkhorn.py:211-259: scores0 (B,N) = max over the core columns of every row,
+ * scores1 (B,M) = max over the core rows of every column of probs (B,N+1,M+1). */
+int om_sinkhorn_scores_f32(const float* probs, int B, int N, int M, float* scores0, float* scores1, void* stream);
+
 /* ---- match extraction -------------------------------------------------------------------- */
 
 size_t om_mutual_matches_workspace_bytes(int B, int N, int M);

@@ -14,7 +14,6 @@ from . import build as _build
 
 _lock = threading.Lock()
 _lib = None
-_tls = threading.local()
 
 
 class MatchParams(Structure):
@@ -58,6 +57,7 @@ SIGNATURES = {
     "om_sinkhorn_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "om_sinkhorn_filter_rows_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "om_sinkhorn_scores_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "om_essential_matrix_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_void_p, c_void_p]),
     "om_mutual_matches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -90,9 +90,15 @@ def lib() -> ctypes.CDLL:
         return _lib
     with _lock:
         if _lib is None:
-            path = _build.LIB_PATH
-            if not os.path.exists(path):
+            # build() returns at once when the binary is newer than every source and the header; a stale binary (edited
+            # kernels, changed struct layout) is rebuilt instead of being loaded silently.  Without nvcc an existing
+            # binary is used as it is (the GPU box gets the binary built in the authoring container).
+            try:
                 path = _build.build()      # raises if nvcc is missing: no CPU fallback exists
+            except RuntimeError:
+                path = _build.LIB_PATH
+                if not os.path.exists(path):
+                    raise
             handle = ctypes.CDLL(path)
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(handle, name)   # AttributeError if the library lacks a declared symbol
@@ -109,10 +115,9 @@ def check(status: int, what: str) -> None:
 
 
 def use_device(index: int) -> None:
-    """Point the library's CUDA runtime at `index` (cached per thread)."""
-    if getattr(_tls, "device", None) != index:
-        check(lib().om_set_device(int(index)), "om_set_device")
-        _tls.device = index
+    """Kept for callers that drive the C ABI by hand: every compute entry point already runs on the device that owns its
+    first pointer argument and restores the caller's current device (DeviceScope in csrc/common.cuh)."""
+    check(lib().om_set_device(int(index)), "om_set_device")
 
 
 def launch_count() -> int:

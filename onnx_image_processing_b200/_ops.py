@@ -7,6 +7,7 @@ there is no CPU implementation behind them.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -38,12 +39,16 @@ def _f32(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 def _begin(t: torch.Tensor):
-    nat.use_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    """(library, stream): the current torch stream of the tensor's device.  The C entry points switch to the device that
+    owns their first pointer and restore the caller's, so nothing here touches the current device."""
     return nat.lib(), ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
 def _ws(nbytes: int, like: torch.Tensor) -> torch.Tensor:
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+    ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+    if os.environ.get("OM_POISON_WS"):       # tests: no kernel may depend on what a workspace held before
+        ws.fill_(0xFF)
+    return ws
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -265,7 +270,7 @@ def _(desc1, desc2, iterations, epsilon, unused_score, distance_l1):
 @torch.library.custom_op("b200match::filter_rows", mutates_args=(), device_types="cuda")
 def filter_rows(probs: torch.Tensor, ratio_threshold: float, dustbin_margin: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """(filtered copy of P, valid mask): the outlier filters of SinkhornMatcherWithFilters."""
-    p = _f32(probs, "P").clone()
+    p = _f32(probs, "P").clone()            # the op must not mutate its argument; matchers that own P use filter_rows_
     B, N, M = int(p.shape[0]), int(p.shape[1]) - 1, int(p.shape[2]) - 1
     lib, st = _begin(p)
     valid = torch.empty((B, N), dtype=torch.uint8, device=p.device)
@@ -277,6 +282,41 @@ def filter_rows(probs: torch.Tensor, ratio_threshold: float, dustbin_margin: flo
 @filter_rows.register_fake
 def _(probs, ratio_threshold, dustbin_margin):
     return probs.new_empty(tuple(probs.shape)), probs.new_empty((probs.shape[0], probs.shape[1] - 1), dtype=torch.bool)
+
+
+@torch.library.custom_op("b200match::filter_rows_", mutates_args=("probs",), device_types="cuda")
+def filter_rows_(probs: torch.Tensor, ratio_threshold: float, dustbin_margin: float) -> torch.Tensor:
+    """In-place form for the matchers that own P (no copy of the (K+1)^2 matrix): filters `probs`, returns the mask."""
+    if not (probs.is_cuda and probs.dtype == torch.float32 and probs.is_contiguous()):
+        raise RuntimeError("filter_rows_ needs a contiguous float32 CUDA tensor")
+    B, N, M = int(probs.shape[0]), int(probs.shape[1]) - 1, int(probs.shape[2]) - 1
+    lib, st = _begin(probs)
+    valid = torch.empty((B, N), dtype=torch.uint8, device=probs.device)
+    nat.check(lib.om_sinkhorn_filter_rows_f32(_p(probs), B, N, M, float(ratio_threshold), float(dustbin_margin), _p(valid), st),
+              "om_sinkhorn_filter_rows_f32")
+    return valid.to(torch.bool)
+
+
+@filter_rows_.register_fake
+def _(probs, ratio_threshold, dustbin_margin):
+    return probs.new_empty((probs.shape[0], probs.shape[1] - 1), dtype=torch.bool)
+
+
+@torch.library.custom_op("b200match::sinkhorn_scores", mutates_args=(), device_types="cuda")
+def sinkhorn_scores(probs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores0 (B,N), scores1 (B,M)) of SinkhornMatcherWithScores: row / column maxima of the core block."""
+    p = _f32(probs, "P")
+    B, N, M = int(p.shape[0]), int(p.shape[1]) - 1, int(p.shape[2]) - 1
+    lib, st = _begin(p)
+    s0 = torch.empty((B, N), dtype=torch.float32, device=p.device)
+    s1 = torch.empty((B, M), dtype=torch.float32, device=p.device)
+    nat.check(lib.om_sinkhorn_scores_f32(_p(p), B, N, M, _p(s0), _p(s1), st), "om_sinkhorn_scores_f32")
+    return s0, s1
+
+
+@sinkhorn_scores.register_fake
+def _(probs):
+    return (probs.new_empty((probs.shape[0], probs.shape[1] - 1)), probs.new_empty((probs.shape[0], probs.shape[2] - 1)))
 
 
 @torch.library.custom_op("b200match::mutual_matches", mutates_args=(), device_types="cuda")
@@ -321,6 +361,8 @@ def essential_matrix(probs: torch.Tensor, pts1: torch.Tensor, pts2: torch.Tensor
     if top_k > min(N, M):
         raise RuntimeError("selected index k out of range")              # torch.topk's message
     v1 = v2 = None
+    if (valid1 is None) != (valid2 is None):
+        raise RuntimeError("valid1 and valid2 must be given together (both masks or neither)")
     if valid1 is not None:
         v1 = valid1.to(device=p.device, dtype=torch.uint8).contiguous()
         v2 = valid2.to(device=p.device, dtype=torch.uint8).contiguous()

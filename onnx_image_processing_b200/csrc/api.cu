@@ -92,33 +92,70 @@ struct MatchWs {
 // The detector / descriptor chains of image 1 and image 2 are independent until the Sinkhorn kernel, and inside a chain
 // the integral image needs only the image: with 4 streams image 2's chain and both integral builds run on side streams
 // (fork and join by events, capturable into a CUDA graph), so that under-filled launches (top-k: one CTA per image),
-// kernel tails and issue-bound / bandwidth-bound kernels overlap.  Side streams and events are per device, created on
-// the first call.
+// kernel tails and issue-bound / bandwidth-bound kernels overlap.
+// Side streams and events belong to ONE caller stream: a small per-(device, caller stream) pool, so that calls on
+// different caller streams (HostBatchMatcher's chunk streams, two caller threads) share nothing and overlap freely.
 int g_match_streams = 4;                        // om_debug_match_streams: 1 = everything on the caller's stream, 2 = two chains, 4
-constexpr int MAX_DEVICES = 64;
-cudaStream_t g_side_stream[MAX_DEVICES][3] = {};
-cudaEvent_t g_fork_event[MAX_DEVICES] = {}, g_join_event[MAX_DEVICES] = {}, g_pre_event[MAX_DEVICES][2] = {};
-std::mutex g_match_mutex;                       // the record / wait pairs on the shared events must not interleave between host threads
 
-int side_streams(int* device) {
-    int dev = 0;
-    OM_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= MAX_DEVICES) return OM_ERR_LIMIT;
-    if (g_side_stream[dev][0] == nullptr) {
-        for (int i = 0; i < 3; ++i) OM_CUDA(cudaStreamCreateWithFlags(&g_side_stream[dev][i], cudaStreamNonBlocking));
-        OM_CUDA(cudaEventCreateWithFlags(&g_fork_event[dev], cudaEventDisableTiming));
-        OM_CUDA(cudaEventCreateWithFlags(&g_join_event[dev], cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) OM_CUDA(cudaEventCreateWithFlags(&g_pre_event[dev][i], cudaEventDisableTiming));
+struct SideSet {
+    int device = -1;
+    cudaStream_t owner = nullptr;               // the caller stream this set serves
+    cudaStream_t side[3] = {};
+    cudaEvent_t fork = nullptr, pre[2] = {}, join[3] = {};
+    unsigned long long last_use = 0;
+    std::mutex busy;                            // two host threads on the SAME caller stream: record / wait pairs must not interleave
+};
+constexpr int MAX_SIDE_SETS = 64;
+SideSet g_sets[MAX_SIDE_SETS];
+int g_num_sets = 0;
+unsigned long long g_use_clock = 0;
+std::mutex g_pool_mutex;                        // guards the table only, never held while work is enqueued
+
+// the set serving (device, caller stream); created on first use, the least recently used one is re-assigned when the
+// table is full (its streams are idle-or-ordered: a later caller simply queues behind whatever they still hold)
+int side_set_for(int device, cudaStream_t owner, SideSet** out) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    SideSet* lru = nullptr;
+    for (int i = 0; i < g_num_sets; ++i) {
+        SideSet& s = g_sets[i];
+        if (s.device == device && s.owner == owner) { s.last_use = ++g_use_clock; *out = &s; return OM_OK; }
+        if (s.device == device && (lru == nullptr || s.last_use < lru->last_use)) lru = &s;
     }
-    *device = dev;
+    SideSet* s = nullptr;
+    if (g_num_sets < MAX_SIDE_SETS) {
+        s = &g_sets[g_num_sets];
+        for (int i = 0; i < 3; ++i) OM_CUDA(cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking));
+        OM_CUDA(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) OM_CUDA(cudaEventCreateWithFlags(&s->pre[i], cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) OM_CUDA(cudaEventCreateWithFlags(&s->join[i], cudaEventDisableTiming));
+        s->device = device;
+        ++g_num_sets;
+    } else if (lru != nullptr) {
+        s = lru;
+    } else {
+        return OM_ERR_LIMIT;
+    }
+    s->owner = owner;
+    s->last_use = ++g_use_clock;
+    *out = s;
     return OM_OK;
 }
 
+// Everything a stage launcher would reject is rejected HERE, before any work is forked onto side streams
 int check_params(const om_match_params* p) {
     if (p == nullptr) return OM_ERR_NULL;
     if (p->flavour < OM_MATCH_SPARSE || p->flavour > OM_MATCH_DENSE) return OM_ERR_PARAM;
     if (p->B <= 0 || p->H <= 1 || p->W <= 1 || p->K <= 0) return OM_ERR_SHAPE;
+    if ((long long)p->K > (long long)p->H * p->W) return OM_ERR_SHAPE;   // torch.topk raises too
+    if ((long long)p->H * p->W >= (1ll << 31) || p->B > 65535 || p->K > OM_MAX_K) return OM_ERR_LIMIT;
     if (p->P != 256 && p->P != 512) return OM_ERR_PARAM;                 // descriptor/bad.py:385-388
+    if (p->block_size < 1 || p->block_size % 2 == 0 || p->block_size / 2 > OM_MAX_BLOCK_HALF) return OM_ERR_PARAM;
+    if (p->nms_radius < 0 || p->nms_radius > OM_MAX_NMS_RADIUS) return OM_ERR_PARAM;
+    if (p->desc_mode < OM_DESC_RAW || p->desc_mode > OM_DESC_HARD) return OM_ERR_PARAM;
+    if (p->flavour != OM_MATCH_DENSE && p->sampling_mode != OM_SAMPLE_NEAREST && p->sampling_mode != OM_SAMPLE_BILINEAR)
+        return OM_ERR_PARAM;
+    if (p->flavour == OM_MATCH_ANGLE && (p->patch_size < 1 || p->patch_size % 2 == 0 || p->patch_size > 31)) return OM_ERR_PARAM;
+    if (p->iterations <= 0 || !(p->epsilon > 0.0f)) return OM_ERR_PARAM;  // matching/sinkhorn.py:66-69
     return OM_OK;
 }
 
@@ -146,6 +183,17 @@ MatchWs plan(const om_match_params* p, void* base) {
 
 }  // namespace
 
+namespace om {
+int device_count_cached() {
+    static int n = -1;
+    if (n < 0) {
+        int c = 0;
+        n = cudaGetDeviceCount(&c) == cudaSuccess ? c : 0;
+    }
+    return n;
+}
+}  // namespace om
+
 extern "C" void om_debug_match_streams(int n) { g_match_streams = n == 1 ? 1 : (n == 2 ? 2 : 4); }
 
 extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
@@ -156,6 +204,7 @@ extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
 extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1, const float* image2,
                                   const float* pair_table, const float* moment_kernels, float* kpts1, float* kpts2,
                                   float* probs, float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(image1);
     OM_TRY(check_params(p));
     if (image1 == nullptr || image2 == nullptr || pair_table == nullptr || kpts1 == nullptr || kpts2 == nullptr ||
         probs == nullptr)
@@ -173,15 +222,20 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
     cudaStream_t chain[2] = {st, st};           // detector + descriptors of image 1 / image 2
     cudaStream_t pre[2] = {st, st};             // integral image of image 1 / image 2
     const int ns = g_match_streams;
-    int dev = 0;
-    std::unique_lock<std::mutex> lock(g_match_mutex, std::defer_lock);
+    SideSet* set = nullptr;
+    std::unique_lock<std::mutex> busy;
+    int nside = 0;                              // side streams that were forked and must be joined, on every path
     if (ns > 1) {
-        lock.lock();
-        OM_TRY(side_streams(&dev));
-        chain[1] = g_side_stream[dev][0];
-        if (ns == 4) { pre[0] = g_side_stream[dev][1]; pre[1] = g_side_stream[dev][2]; }
-        OM_CUDA(cudaEventRecord(g_fork_event[dev], st));            // side work starts behind the caller's prior work
-        for (int i = 0; i < (ns == 4 ? 3 : 1); ++i) OM_CUDA(cudaStreamWaitEvent(g_side_stream[dev][i], g_fork_event[dev], 0));
+        OM_TRY(side_set_for(dev_scope__.dev, st, &set));
+        busy = std::unique_lock<std::mutex>(set->busy);
+        chain[1] = set->side[0];
+        if (ns == 4) { pre[0] = set->side[1]; pre[1] = set->side[2]; }
+        OM_CUDA(cudaEventRecord(set->fork, st));                    // side work starts behind the caller's prior work
+        nside = ns == 4 ? 3 : 1;
+        for (int i = 0; i < nside; ++i) {
+            const cudaError_t e = cudaStreamWaitEvent(set->side[i], set->fork, 0);
+            if (e != cudaSuccess) { nside = i; break; }
+        }
     }
     auto descriptors = [&](int s, cudaStream_t q, int phase) -> int {
         if (p->flavour == OM_MATCH_DENSE)
@@ -192,26 +246,35 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
                                  p->normalize, p->sampling_mode, theta, nullptr, moment_kernels, p->patch_size, ds[s],
                                  w.dense[s], w.dense_bytes, q, phase);
     };
-    if (ns == 4) {
-        for (int s = 0; s < 2; ++s) {
-            OM_TRY(descriptors(s, pre[s], 1));                      // integral image only
-            OM_CUDA(cudaEventRecord(g_pre_event[dev][s], pre[s]));
-        }
-    }
-    for (int s = 0; s < 2; ++s) {
-        // keypoint scores are discarded by the matcher modules (`keypoints1, _ = ...`)
-        OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
+    // the forked part: whatever it returns, the side streams are joined back below (an unjoined fork would leave side work
+    // running on a workspace the caller may free, and would invalidate a stream capture)
+    auto forked = [&]() -> int {
+        if (ns > 1 && nside != (ns == 4 ? 3 : 1)) return OM_ERR_CUDA_BASE + (int)cudaErrorUnknown;
         if (ns == 4) {
-            OM_CUDA(cudaStreamWaitEvent(chain[s], g_pre_event[dev][s], 0));
-            OM_TRY(descriptors(s, chain[s], 2));
-        } else {
-            OM_TRY(descriptors(s, chain[s], 0));
+            for (int s = 0; s < 2; ++s) {
+                OM_TRY(descriptors(s, pre[s], 1));                  // integral image only
+                OM_CUDA(cudaEventRecord(set->pre[s], pre[s]));
+            }
         }
+        for (int s = 0; s < 2; ++s) {
+            // keypoint scores are discarded by the matcher modules (`keypoints1, _ = ...`)
+            OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
+            if (ns == 4) {
+                OM_CUDA(cudaStreamWaitEvent(chain[s], set->pre[s], 0));
+                OM_TRY(descriptors(s, chain[s], 2));
+            } else {
+                OM_TRY(descriptors(s, chain[s], 0));
+            }
+        }
+        return OM_OK;
+    };
+    int rc = forked();
+    for (int i = 0; i < nside; ++i) {                               // join: always, also on the error paths
+        const cudaError_t e1 = cudaEventRecord(set->join[i], set->side[i]);
+        const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(st, set->join[i], 0) : e1;
+        if (e2 != cudaSuccess && rc == OM_OK) rc = OM_ERR_CUDA_BASE + (int)e2;
     }
-    if (ns > 1) {
-        OM_CUDA(cudaEventRecord(g_join_event[dev], chain[1]));
-        OM_CUDA(cudaStreamWaitEvent(st, g_join_event[dev], 0));     // Sinkhorn needs both descriptor sets
-    }
+    if (rc != OM_OK) return rc;
     return sinkhorn_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
-                           probs, w.sink, w.sink_bytes, st);
+                           probs, w.sink, w.sink_bytes, st);                     // needs both descriptor sets
 }

@@ -1353,6 +1353,7 @@ extern "C" void om_debug_dense_window(int tma) { g_dense_window_tma = tma; }
 
 extern "C" int om_angle_map_f32(const float* image, int B, int H, int W, const float* moment_kernels, int patch_size,
                                 float* angle_map, void* stream) {
+    OM_ON_DEVICE_OF(image);
     if (image == nullptr || moment_kernels == nullptr || angle_map == nullptr) return OM_ERR_NULL;
     if (B <= 0 || H <= 0 || W <= 0) return OM_ERR_SHAPE;
     if (patch_size < 1 || patch_size % 2 == 0 || patch_size > 31) return OM_ERR_PARAM;
@@ -1370,6 +1371,7 @@ extern "C" int om_sparse_bad_f32(const float* image, int B, int H, int W, const 
                                  int sampling_mode, int theta_mode, const float* orientation,
                                  const float* moment_kernels, int patch_size, float* desc, void* ws, size_t ws_bytes,
                                  void* stream) {
+    OM_ON_DEVICE_OF(image);
     return sparse_bad_launch(image, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, sampling_mode,
                              theta_mode, orientation, moment_kernels, patch_size, desc, ws, ws_bytes,
                              (cudaStream_t)stream);
@@ -1383,6 +1385,7 @@ extern "C" size_t om_dense_bad_workspace_bytes(int B, int H, int W) { return den
 
 extern "C" int om_dense_bad_f32(const float* image, int B, int H, int W, const float* pair_table, int P, int desc_mode,
                                 float temperature, float* desc_map, void* ws, size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(image);
     if (image == nullptr || desc_map == nullptr) return OM_ERR_NULL;
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || H > 65535) return OM_ERR_SHAPE;
     OM_TRY(check_table(pair_table, P));
@@ -1402,12 +1405,14 @@ extern "C" int om_dense_bad_f32(const float* image, int B, int H, int W, const f
 extern "C" int om_dense_bad_at_kpts_f32(const float* image, int B, int H, int W, const float* kpts, int K,
                                         const float* pair_table, int P, int desc_mode, float temperature,
                                         int normalize, float* desc, void* ws, size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(image);
     return dense_bad_at_kpts_launch(image, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, desc, ws,
                                     ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int om_gather_descriptors_f32(const float* desc_map, int B, int D, int H, int W, const float* kpts, int K,
                                          int subpixel, float* desc, void* stream) {
+    OM_ON_DEVICE_OF(desc_map);
     if (desc_map == nullptr || kpts == nullptr || desc == nullptr) return OM_ERR_NULL;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0) return OM_ERR_SHAPE;
     const long long n = (long long)B * K * D;
@@ -1421,6 +1426,7 @@ extern "C" int om_gather_descriptors_f32(const float* desc_map, int B, int D, in
 extern "C" int om_debug_dense_stage(const float* image, int B, int H, int W, const float* kpts, int K,
                                     const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                                     float* desc, void* ws, size_t ws_bytes, void* stream, int stage) {
+    OM_ON_DEVICE_OF(image);
     if (image == nullptr || kpts == nullptr || desc == nullptr) return OM_ERR_NULL;
     if (B <= 0 || H <= 1 || W <= 1 || K <= 0) return OM_ERR_SHAPE;
     OM_TRY(check_table(pair_table, P));

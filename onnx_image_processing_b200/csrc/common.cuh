@@ -34,6 +34,40 @@ inline void count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELA
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// implementation limits shared by the stage launchers and the fused matcher's up-front validation
+constexpr int OM_MAX_BLOCK_HALF = 4;     // block_size <= 9
+constexpr int OM_MAX_NMS_RADIUS = 8;
+constexpr int OM_MAX_K = 16384;          // top-k kernel: keypoints per image
+
+// Every compute entry point runs on the device that owns its first device pointer and restores the caller's current
+// device before returning (the library links its own static CUDA runtime; a changed current device must not leak into
+// the caller's).  One-GPU processes skip the pointer query.
+int device_count_cached();
+struct DeviceScope {
+    int prev = -1, dev = 0, status = OM_OK;
+    explicit DeviceScope(const void* device_ptr) {
+        if (device_count_cached() <= 1 || device_ptr == nullptr) { cudaGetDevice(&dev); return; }
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, device_ptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            cudaGetDevice(&dev);
+            return;
+        }
+        dev = at.device;
+        int cur = 0;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) {
+            if (cudaSetDevice(dev) == cudaSuccess) prev = cur;
+            else status = OM_ERR_CUDA_BASE + (int)cudaGetLastError();
+        }
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define OM_ON_DEVICE_OF(ptr)                       \
+    om::DeviceScope dev_scope__(ptr);              \
+    if (dev_scope__.status != OM_OK) return dev_scope__.status
+
 template <typename K>
 inline int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {

@@ -438,6 +438,7 @@ extern "C" void om_debug_essential_variant(int clustered) { g_essential_cluster 
 extern "C" int om_essential_matrix_f32(const float* probs, const float* pts1, const float* pts2, const unsigned char* valid1,
                                        const unsigned char* valid2, int B, int N, int M, int pts_batched, int top_k,
                                        int n_iter, int n_iter_manifold, float* E, void* stream) {
+    OM_ON_DEVICE_OF(probs);
     if (probs == nullptr || pts1 == nullptr || pts2 == nullptr || E == nullptr) return OM_ERR_NULL;
     if ((valid1 == nullptr) != (valid2 == nullptr)) return OM_ERR_NULL;
     if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;

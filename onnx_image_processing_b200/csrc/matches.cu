@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(MT) match_rows_kernel(const float* P, int N, i
     }
     if (lane == 0) {
         row_max[(size_t)z * N + i] = best;
-        row_arg[(size_t)z * N + i] = arg;
+        if (row_arg != nullptr) row_arg[(size_t)z * N + i] = arg;
     }
 }
 
@@ -160,6 +160,18 @@ int next_pow2(int v) {
     return p;
 }
 
+// SinkhornMatcherWithScores, matching/sinkhorn.py:251-257: column maxima of the core block (the row maxima come from
+// match_rows_kernel).  One thread per column, consecutive threads read consecutive addresses of a row.
+__global__ void __launch_bounds__(256) col_max_kernel(const float* P, int N, int M, float* col_max) {
+    const int z = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= M) return;
+    const float* col = P + (size_t)z * (N + 1) * (M + 1) + j;
+    float best = col[0];
+    for (int i = 1; i < N; ++i) best = fmaxf(best, col[(size_t)i * (M + 1)]);
+    col_max[(size_t)z * M + j] = best;
+}
+
 }  // namespace
 
 }  // namespace om
@@ -168,11 +180,25 @@ using namespace om;
 
 extern "C" int om_sinkhorn_filter_rows_f32(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin,
                                            unsigned char* valid, void* stream) {
+    OM_ON_DEVICE_OF(probs);
     if (probs == nullptr || valid == nullptr) return OM_ERR_NULL;
     if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
     if (B > 65535) return OM_ERR_LIMIT;
     filter_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, (cudaStream_t)stream>>>(probs, N, M, ratio_threshold,
                                                                                                dustbin_margin, valid);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+extern "C" int om_sinkhorn_scores_f32(const float* probs, int B, int N, int M, float* scores0, float* scores1, void* stream) {
+    OM_ON_DEVICE_OF(probs);
+    if (probs == nullptr || scores0 == nullptr || scores1 == nullptr) return OM_ERR_NULL;
+    if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
+    if (B > 65535) return OM_ERR_LIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    match_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, st>>>(probs, N, M, scores0, nullptr);
+    OM_AFTER_LAUNCH();
+    col_max_kernel<<<dim3((M + 255) / 256, B), 256, 0, st>>>(probs, N, M, scores1);
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -185,6 +211,7 @@ extern "C" size_t om_mutual_matches_workspace_bytes(int B, int N, int M) {
 extern "C" int om_mutual_matches_f32(const float* probs, const float* kpts1, const float* kpts2, int B, int N, int M,
                                      int max_matches, float threshold, float* matched_kpts1, float* matched_kpts2,
                                      float* scores, unsigned char* valid, void* ws, size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(probs);
     if (probs == nullptr || kpts1 == nullptr || kpts2 == nullptr || matched_kpts1 == nullptr || matched_kpts2 == nullptr ||
         scores == nullptr || valid == nullptr)
         return OM_ERR_NULL;

@@ -680,6 +680,7 @@ extern "C" size_t om_sinkhorn_workspace_bytes(int B, int N, int M, int D) { retu
 extern "C" int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M, int D, int iterations,
                                float epsilon, float unused_score, int distance_l1, float* P, void* ws,
                                size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(desc1);
     return sinkhorn_launch(desc1, desc2, B, N, M, D, iterations, epsilon, unused_score, distance_l1, P, ws, ws_bytes,
                            (cudaStream_t)stream);
 }

@@ -31,15 +31,32 @@ def _register_bank(mod: nn.Module, num_pairs: int) -> None:
     mod.register_buffer("box_kernel_bank", (masks / ((2.0 * rv + 1.0) ** 2).clamp_min(1.0)).unsqueeze(1))
 
 
-def _register_pair_table(mod: nn.Module) -> None:
-    """(P,6) rows {ox1, ox2, oy1, oy2, radius, threshold}: what the C ABI consumes.  Non-persistent,
-    so state_dict keys stay exactly the reference's."""
-    t = torch.stack([mod.offset_x1, mod.offset_x2, mod.offset_y1, mod.offset_y2, mod.radii.float(), mod.thresholds],
-                    dim=1).contiguous()
-    mod.register_buffer("_pair_table", t, persistent=False)
+class _PairTable:
+    """``_pair_table``: (P,6) rows {ox1, ox2, oy1, oy2, radius, threshold}, what the C ABI consumes.  It is DERIVED from
+    the module's buffers -- the ones the reference's forward reads (bad.py:33-38 for the dense module, the ``*_v`` views
+    and ``radius_select`` of bad.py:413-423 for SparseBAD) -- and rebuilt whenever one of them changed (load_state_dict,
+    in-place edits, .to(device)), so a loaded state_dict is what the kernels use.  Not a buffer: state_dict keys stay
+    exactly the reference's."""
+
+    def _pair_sources(self):
+        return (self.offset_x1, self.offset_x2, self.offset_y1, self.offset_y2, self.radii, self.thresholds)
+
+    def _pair_columns(self):
+        return [self.offset_x1, self.offset_x2, self.offset_y1, self.offset_y2, self.radii.float(), self.thresholds]
+
+    @property
+    def _pair_table(self) -> torch.Tensor:
+        key = tuple((b.data_ptr(), b._version, str(b.device)) for b in self._pair_sources())
+        cache = self.__dict__.get("_pair_cache")
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                t = torch.stack([c.reshape(-1).float() for c in self._pair_columns()], dim=1).contiguous()
+            cache = (key, t)
+            self.__dict__["_pair_cache"] = cache
+        return cache[1]
 
 
-class BADDescriptor(nn.Module):
+class BADDescriptor(_PairTable, nn.Module):
     """Dense BAD map (B,1,H,W) -> (B,num_pairs,H,W) (bad.py:14-218, non-oriented path)."""
 
     def __init__(self, num_pairs: int = 256, binarize: bool = False, soft_binarize: bool = True,
@@ -52,7 +69,6 @@ class BADDescriptor(nn.Module):
         _register_tables(self, num_pairs)
         self.register_buffer("area", ((2.0 * self.radii.float() + 1.0) ** 2).view(-1, 1, 1))
         _register_bank(self, num_pairs)
-        _register_pair_table(self)
 
     def forward(self, x: torch.Tensor, orientation: torch.Tensor | None = None) -> torch.Tensor:
         if orientation is not None:
@@ -73,7 +89,7 @@ def extract_descriptors_at_keypoints_subpixel(descriptor_map: torch.Tensor, keyp
     return _ops.gather_descriptors(descriptor_map, keypoints, True)
 
 
-class SparseBAD(nn.Module):
+class SparseBAD(_PairTable, nn.Module):
     """BAD descriptors at keypoints only, optionally rotated by a per-pixel orientation map
     (bad.py:336-576)."""
 
@@ -94,7 +110,13 @@ class SparseBAD(nn.Module):
         for name in ("offset_y1", "offset_x1", "offset_y2", "offset_x2", "thresholds"):   # bad.py:413-417
             self.register_buffer(name + "_v", getattr(self, name).view(1, 1, -1))
         _register_bank(self, num_pairs)
-        _register_pair_table(self)
+
+    def _pair_sources(self):                 # what SparseBAD.forward of the reference reads (bad.py:520-525, :554-559)
+        return (self.offset_x1_v, self.offset_x2_v, self.offset_y1_v, self.offset_y2_v, self.radius_select, self.thresholds_v)
+
+    def _pair_columns(self):
+        return [self.offset_x1_v, self.offset_x2_v, self.offset_y1_v, self.offset_y2_v,
+                self.radius_select.argmax(dim=0).float(), self.thresholds_v]
 
     def _mode(self) -> int:
         return _ops.desc_mode(self.binarize, self.soft_binarize)

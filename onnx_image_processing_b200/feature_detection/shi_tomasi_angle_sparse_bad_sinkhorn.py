@@ -65,5 +65,5 @@ class ShiTomasiAngleSparseBADSinkhornMatcherWithFilters(ShiTomasiAngleSparseBADS
 
     def forward(self, image1: torch.Tensor, image2: torch.Tensor):
         k1, k2, probs, _, _ = self.match(image1, image2)
-        probs, valid = _ops.filter_rows(probs, float(self.matcher.ratio_threshold), float(self.matcher.dustbin_margin))
+        valid = _ops.filter_rows_(probs, float(self.matcher.ratio_threshold), float(self.matcher.dustbin_margin))   # P is ours: in place
         return k1, k2, probs, valid

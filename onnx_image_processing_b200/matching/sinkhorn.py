@@ -32,8 +32,8 @@ class SinkhornMatcherWithScores(SinkhornMatcher):
 
     def forward(self, desc1: torch.Tensor, desc2: torch.Tensor):
         P = super().forward(desc1, desc2)
-        core = P[:, :desc1.shape[1], :desc2.shape[1]]
-        return P, core.max(dim=-1).values, core.max(dim=-2).values
+        scores0, scores1 = _ops.sinkhorn_scores(P)
+        return P, scores0, scores1
 
 
 class SinkhornMatcherWithFilters(SinkhornMatcher):
@@ -47,5 +47,6 @@ class SinkhornMatcherWithFilters(SinkhornMatcher):
         self.dustbin_margin = dustbin_margin if dustbin_margin is not None else -1.0
 
     def forward(self, desc1: torch.Tensor, desc2: torch.Tensor):
-        P = super().forward(desc1, desc2)
-        return _ops.filter_rows(P, float(self.ratio_threshold), float(self.dustbin_margin))
+        P = super().forward(desc1, desc2)                # fresh tensor owned here: filtered in place, no copy
+        valid = _ops.filter_rows_(P, float(self.ratio_threshold), float(self.dustbin_margin))
+        return P, valid

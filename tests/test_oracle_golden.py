@@ -158,3 +158,76 @@ def test_table_facts():
             assert o.min() >= -15 and o.max() <= 14
     with pytest.raises(ValueError):
         O.bad_tables(128)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size goldens (tests/golden/make_golden_full.py): the sizes the benchmark runs
+# ------------------------------------------------------------------------------------------
+def check_p_summary(p, g, tol, argmax_min=1.0):
+    """(1, N+1, M+1) matrix against the row-sample form stored for the large cases."""
+    N = p.shape[1] - 1
+    rows = g["P_rows"].long()
+    assert float((p[0, rows][:, :N + 1] - g["P_sample"]).abs()[:, :N].max()) <= tol          # sampled rows, core + dustbin column
+    assert float((p[0, N, :N] - g["P_dust_row"][:N]).abs().max()) <= tol
+    assert float((p[0, :N, N] - g["P_dust_col"][:N]).abs().max()) <= tol
+    assert abs(float(p[0, N, N]) - float(g["P_dust_row"][N])) <= max(tol, 1e-4 * float(g["P_dust_row"][N]))
+    core = p[0, :N, :N]
+    assert float((core.max(dim=-1).values - g["P_row_max"]).abs().max()) <= tol
+    assert float((core.argmax(dim=-1) == g["P_row_argmax"]).float().mean()) >= argmax_min
+    assert float((core.argmax(dim=-2) == g["P_col_argmax"]).float().mean()) >= argmax_min
+    assert abs(float(p.double().sum()) - g["P_sum64"]) <= 1e-6 * abs(g["P_sum64"]) + tol * N
+
+
+def test_dense_full_default():
+    """BASELINE configs[1] at its real size: the oracle against the reference's own outputs."""
+    g = G.load("dense_full_default")
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = O.dense_matcher(g["image1"], g["image2"], 512, return_descriptors=True)
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    assert (d1 - g["desc1"]).abs().max() <= 2e-6 and (d2 - g["desc2"]).abs().max() <= 2e-6
+    assert (p - g["P"])[:, :512, :].abs().max() <= 2e-6
+    m = G.load("matches_dense_full")
+    mk1, mk2, sc, valid = O.mutual_matches(p, k1, k2, m["max_matches"], m["threshold"])
+    assert torch.equal(valid, m["valid"].bool()) and int(valid.sum()) > 50
+    assert (sc - m["scores"]).abs().max() <= 2e-6
+    v = valid
+    assert torch.equal(mk1[v], m["mk1"][v]) and torch.equal(mk2[v], m["mk2"][v])
+
+
+def full_descriptor_bits(g, which):
+    """hard-binarised descriptors stored as packed bits + the row norm factor -> float descriptors"""
+    import numpy as np
+    bits = torch.from_numpy(np.unpackbits(g[f"desc{which}_bits"].numpy(), axis=-1)).float()
+    return bits * g[f"desc{which}_norm"].unsqueeze(-1)
+
+
+def test_sparse_full_export():
+    """The configuration the reference's export script ships, at full size (K = 1024: generic Sinkhorn path)."""
+    g = G.load("sparse_full_export")
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = O.sparse_matcher(g["image1"], g["image2"], 1024, return_descriptors=True, **g["kwargs"])
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    assert (d1 - full_descriptor_bits(g, 1)).abs().max() <= 2e-6 and (d2 - full_descriptor_bits(g, 2)).abs().max() <= 2e-6
+    check_p_summary(p, g, 2e-6)
+
+
+def test_sparse_1080p_k2048():
+    """BASELINE configs[4]: 1080x1920, K = 2048, both images, descriptors and P."""
+    g = G.load("sparse_1080p_k2048")
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = O.sparse_matcher(g["image1"], g["image2"], 2048, return_descriptors=True)
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    rows = g["desc_rows"].long()
+    assert (d1[0, rows] - g["desc1_sample"]).abs().max() <= 2e-6 and (d2[0, rows] - g["desc2_sample"]).abs().max() <= 2e-6
+    assert (d1[0].double().sum(dim=-1).float() - g["desc1_rowsum"]).abs().max() <= 1e-4
+    assert (d2[0].double().sum(dim=-1).float() - g["desc2_rowsum"]).abs().max() <= 1e-4
+    check_p_summary(p, g, 2e-6)
+
+
+def test_sinkhorn_with_scores():
+    g = G.load("sinkhorn_with_scores")
+    with torch.no_grad():
+        p = O.sinkhorn(g["desc1"], g["desc2"], **g["kwargs"])
+    N, M = g["desc1"].shape[1], g["desc2"].shape[1]
+    assert torch.equal(p, g["P"])
+    assert torch.equal(p[:, :N, :M].max(dim=-1).values, g["scores0"]) and torch.equal(p[:, :N, :M].max(dim=-2).values, g["scores1"])
