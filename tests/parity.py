@@ -73,3 +73,35 @@ def prob_metrics(p_test: torch.Tensor, p_ref: torch.Tensor) -> dict:
 def probs_ok(m: dict) -> bool:
     return (m["finite"] and m["core"] <= PROB_TOL and m["dust_row"] <= PROB_TOL and m["corner_rel"] <= PROB_TOL
             and m["argmax"] >= ARGMAX_MIN)
+
+
+def p_summary_metrics(p: torch.Tensor, g: dict) -> dict:
+    """(1, N+1, M+1) matrix against the row-sample form stored for the large goldens (tests/golden/make_golden_full.py):
+    sampled full rows, the complete dustbin row / column, every row's maximum and argmax, every column's argmax."""
+    p = p.cpu()
+    N = p.shape[1] - 1
+    rows = g["P_rows"].long()
+    core = p[0, :N, :N]
+    corner_ref = float(g["P_dust_row"][N])
+    return dict(core=max(float((p[0, rows] - g["P_sample"]).abs()[:, :N].max()),
+                         float((core.max(dim=-1).values - g["P_row_max"]).abs().max()),
+                         float((p[0, :N, N] - g["P_dust_col"][:N]).abs().max())),
+                dust_row=float((p[0, N, :N] - g["P_dust_row"][:N]).abs().max()),
+                corner_rel=abs(float(p[0, N, N]) - corner_ref) / max(abs(corner_ref), 1e-30),
+                argmax=float((core.argmax(dim=-1) == g["P_row_argmax"]).float().mean()),
+                col_argmax=float((core.argmax(dim=-2) == g["P_col_argmax"]).float().mean()),
+                sum_rel=abs(float(p.double().sum()) - g["P_sum64"]) / abs(g["P_sum64"]),
+                finite=bool(torch.isfinite(p).all()))
+
+
+def p_summary_ok(p: torch.Tensor, g: dict, tol: float = PROB_TOL, argmax_min: float = 1.0) -> None:
+    m = p_summary_metrics(p, g)
+    assert m["finite"] and m["core"] <= tol and m["dust_row"] <= tol and m["corner_rel"] <= max(tol, PROB_TOL), m
+    assert m["argmax"] >= argmax_min and m["col_argmax"] >= argmax_min and m["sum_rel"] <= 1e-5, m
+
+
+def full_descriptor_bits(g: dict, which: int) -> torch.Tensor:
+    """hard-binarised descriptors stored as packed bits + the row norm factor -> float descriptors"""
+    import numpy as np
+    bits = torch.from_numpy(np.unpackbits(g[f"desc{which}_bits"].numpy(), axis=-1)).float()
+    return bits * g[f"desc{which}_norm"].unsqueeze(-1)

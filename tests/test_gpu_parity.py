@@ -14,6 +14,10 @@ from tests import parity as PR
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
+# measured on B200 (tools/measure_parity.py -> profiles/r2_parity_measured.json); thresholds = measured + a small margin
+EXPORT_MAX_FLIPPED_BITS = 0          # measured 0 of 1 048 576 hard bits (same integer arithmetic on every B200)
+ORIENTED_ROWS_MIN = 1.0              # oriented descriptor rows within 1e-5 of the reference
+
 
 def _cuda(*ts):
     return [t.to(DEV) for t in ts]
@@ -158,12 +162,12 @@ def test_oriented_sparse_bad(sampling_mode):
     sb = om.SparseBAD(sampling_mode=sampling_mode).to(DEV)
     got_map = sb(img.to(DEV), k.to(DEV), ang.to(DEV))
     m1 = PR.desc_metrics(got_map, ref)
-    assert m1["rows_within"] >= 0.99, m1
+    assert m1["rows_within"] >= ORIENTED_ROWS_MIN, m1
     mk = om.AngleEstimator().to(DEV).moment_kernels
     got_mom = _ops.sparse_bad(img.to(DEV), k.to(DEV), sb._pair_table, 0, 10.0, True, _ops.sampling_code(sampling_mode),
                               _ops.THETA_MOMENTS, None, mk)
     m2 = PR.desc_metrics(got_mom, ref)
-    assert m2["rows_within"] >= 0.97, m2
+    assert m2["rows_within"] >= ORIENTED_ROWS_MIN, m2
 
 
 def test_angle_map_matches_oracle():
@@ -315,10 +319,12 @@ def test_sparse_matcher_golden(name):
     kw = g["kwargs"]
     hard = kw.get("binarize") and not kw.get("soft_binarize", True)
     soft = kw.get("binarize") and kw.get("soft_binarize", True)
-    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=0.98 if hard else 1.0,
-                       desc_tol=PR.DESC_TOL_SOFT if soft else PR.DESC_TOL)
+    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=1.0, desc_tol=PR.DESC_TOL_SOFT if soft else PR.DESC_TOL)
     if hard:
-        assert m["core"] <= 5e-3 and m["argmax"] >= 0.99, m       # a flipped bit moves one row of P
+        # a hard bit can flip only where |box difference - threshold| is at rounding level; measured on B200
+        # (profiles/r2_parity_measured.json): 0 flipped bits on every hard-binarised golden -> the plain north-star bar
+        assert int(((d1.cpu() > 0) != (g["desc1"] > 0)).sum()) == 0
+        assert PR.probs_ok(m), m
     elif not kw.get("normalize_descriptors", True):
         # raw descriptors (norm up to ~1000) make -cost/eps reach -2.6e6: one fp32 ulp of the log-score is
         # 0.25, and the reference's own fp32 P differs from its fp64 P by 1e-2 on this case (measured);
@@ -500,15 +506,16 @@ def test_angle_matcher_golden(name):
     g = G.load(name)
     model = om.ShiTomasiAngleSparseBADSinkhornMatcher(g["K"], **g["kwargs"]).to(DEV).eval()
     k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
-    # orientation rounding flips touch ~0.1 % of rows (SURVEY.md section 0 trap 5); report, bound loosely
-    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=0.97)
-    assert m["finite"] and m["argmax"] >= 0.99 and m["core"] <= 2e-2, m
+    # SURVEY.md section 0 trap 5 expects ~0.1 % of rows to differ through orientation rounding flips; measured on B200
+    # (profiles/r2_parity_measured.json): 0 of 1280 rows beyond 1e-5 on the goldens, max 4e-7 -> the plain north-star bar
+    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=1.0)
+    assert PR.probs_ok(m), m
     det = om.ShiTomasiAngleSparseBADDetector(g["K"], **{k: v for k, v in g["kwargs"].items()
                                                         if k not in ("epsilon", "sinkhorn_iterations")}).to(DEV)
     dk, dsc, dd = det(g["image1"].to(DEV))
     assert PR.keypoint_mismatches(dk, g["det_kpts"], g["det_scores"]) == 0
     assert PR.scores_close(dsc, g["det_scores"])
-    assert PR.desc_metrics(dd, g["det_desc"])["rows_within"] >= 0.97
+    assert PR.desc_metrics(dd, g["det_desc"])["rows_within"] == 1.0
 
 
 @pytest.mark.parametrize("name", G.names("dense"))
@@ -807,3 +814,209 @@ def test_generic_sinkhorn_beyond_fp16_range_and_odd_descriptor_length():
     ref = O.sinkhorn(e1, e2, 20, 0.3, 1.0)
     got = om.SinkhornMatcher(20, 0.3, 1.0).to(DEV)(*_cuda(e1, e2))
     assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size goldens minted from the live reference (tests/golden/make_golden_full.py): the sizes the benchmark runs,
+# at the north star's tolerances (keypoints identical, descriptors 1e-5, probabilities 1e-4, argmax 99.9 %)
+# ------------------------------------------------------------------------------------------
+def test_dense_full_golden():
+    """BASELINE configs[1] (the headline bench): ShiTomasiBADSinkhornMatcher(512) at 480x640 against the reference's run."""
+    g = G.load("dense_full_default")
+    model = om.ShiTomasiBADSinkhornMatcher(512).to(DEV).eval()
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
+    assert PR.keypoint_mismatches(k1, g["kpts1"]) == 0 and PR.keypoint_mismatches(k2, g["kpts2"]) == 0
+    for d, ref in ((d1, g["desc1"]), (d2, g["desc2"])):
+        m = PR.desc_metrics(d, ref)
+        assert m["rows_within"] == 1.0 and m["max_abs"] <= PR.DESC_TOL, m
+    m = PR.prob_metrics(p, g["P"])
+    assert PR.probs_ok(m), m
+    # matches-only form of the same model (MatchExtractionWrapper) against the reference's wrapper
+    mg = G.load("matches_dense_full")
+    wrapped = om.MatchExtractionWrapper(model, max_matches=mg["max_matches"], match_threshold=mg["threshold"]).to(DEV).eval()
+    with torch.no_grad():
+        got = wrapped(*_cuda(g["image1"], g["image2"]))
+    gv, rv = got[3].cpu(), mg["valid"].bool()
+    assert float((gv == rv).float().mean()) >= 0.98                      # P differs by <= 1e-4: a threshold case may flip
+    both = gv & rv
+    assert int(both.sum()) > 50 and float((got[2].cpu() - mg["scores"])[both].abs().max()) <= PR.PROB_TOL
+    same = (got[0].cpu()[both] == mg["mk1"][both]).all(-1) & (got[1].cpu()[both] == mg["mk2"][both]).all(-1)
+    assert float(same.float().mean()) >= 0.98                            # equal-score ties may swap slots
+
+
+def test_sparse_full_export_golden():
+    """The configuration the reference's export script ships (K=1024, 512 pairs, hard binarisation, epsilon 0.05, NMS
+    radius 5) at 480x640: radius-5 detector routing, 512-pair tables and the K > 512 Sinkhorn path end to end."""
+    g = G.load("sparse_full_export")
+    model = om.ShiTomasiSparseBADSinkhornMatcher(1024, **g["kwargs"]).to(DEV).eval()
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
+    assert PR.keypoint_mismatches(k1, g["kpts1"]) == 0 and PR.keypoint_mismatches(k2, g["kpts2"]) == 0
+    flipped = 0
+    for d, which in ((d1, 1), (d2, 2)):
+        ref = PR.full_descriptor_bits(g, which)
+        fl = (d.cpu() > 0) != (ref > 0)
+        flipped += int(fl.sum())
+        ok = ~fl.any(dim=-1)
+        assert float((d.cpu() - ref)[ok].abs().max()) <= PR.DESC_TOL       # rows without a flipped bit: the 1e-5 bar
+    # a hard bit flips only when |box difference - threshold| is at rounding level: measured 0 of 1 048 576 bits
+    assert flipped <= EXPORT_MAX_FLIPPED_BITS, flipped
+    m = PR.p_summary_metrics(p, g)
+    if flipped == 0:
+        PR.p_summary_ok(p, g, PR.PROB_TOL, PR.ARGMAX_MIN)
+    else:
+        assert m["finite"] and m["argmax"] >= 0.995, m
+
+
+def test_sparse_1080p_k2048_golden():
+    """BASELINE configs[4]: 1080x1920, K=2048 -- both images, descriptors and P against the reference's run."""
+    g = G.load("sparse_1080p_k2048")
+    model = om.ShiTomasiSparseBADSinkhornMatcher(2048).to(DEV).eval()
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = model.match(*_cuda(g["image1"], g["image2"]))
+    assert PR.keypoint_mismatches(k1, g["kpts1"]) == 0 and PR.keypoint_mismatches(k2, g["kpts2"]) == 0
+    rows = g["desc_rows"].long()
+    for d, which in ((d1, 1), (d2, 2)):
+        m = PR.desc_metrics(d[0, rows], g[f"desc{which}_sample"])
+        assert m["rows_within"] == 1.0, m
+        assert float((d[0].double().sum(-1).float().cpu() - g[f"desc{which}_rowsum"]).abs().max()) <= 1e-4   # every row, not only the sample
+    PR.p_summary_ok(p, g, PR.PROB_TOL, PR.ARGMAX_MIN)
+
+
+def test_sinkhorn_with_scores_golden():
+    """SinkhornMatcherWithScores (matching/sinkhorn.py:211-259) against the reference's outputs."""
+    g = G.load("sinkhorn_with_scores")
+    p, s0, s1 = om.SinkhornMatcherWithScores(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"]))
+    assert PR.probs_ok(PR.prob_metrics(p, g["P"]))
+    N, M = g["desc1"].shape[1], g["desc2"].shape[1]
+    assert s0.shape == (2, N) and s1.shape == (2, M)
+    assert float((s0.cpu() - g["scores0"]).abs().max()) <= PR.PROB_TOL and float((s1.cpu() - g["scores1"]).abs().max()) <= PR.PROB_TOL
+    # and exactly the maxima of the P that was returned
+    assert torch.equal(s0, p[:, :N, :M].max(dim=-1).values) and torch.equal(s1, p[:, :N, :M].max(dim=-2).values)
+
+
+# ------------------------------------------------------------------------------------------
+# robustness: workspace contents, allocation history, errors after a fork, state_dict, devices
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flavour", ["dense", "sparse", "angle", "export"])
+def test_results_do_not_depend_on_workspace_contents_or_allocation_history(flavour, monkeypatch):
+    """Every workspace is filled with 0xFF bytes (NaN floats, huge counters) before the call, and the allocator history
+    differs between the runs: keypoints, descriptors and P must be bit-identical to the plain run."""
+    i1, i2 = O.texture_images(3, 240, 320, seed=55)
+    if flavour == "export":
+        model = om.ShiTomasiSparseBADSinkhornMatcher(600, num_pairs=512, binarize=True, soft_binarize=False, epsilon=0.05, nms_radius=5)
+    else:
+        cls = dict(sparse=om.ShiTomasiSparseBADSinkhornMatcher, dense=om.ShiTomasiBADSinkhornMatcher,
+                   angle=om.ShiTomasiAngleSparseBADSinkhornMatcher)[flavour]
+        model = cls(256)
+    model = model.to(DEV).eval()
+    a1, a2 = _cuda(i1, i2)
+    with torch.no_grad():
+        want = [t.clone() for t in model.match(a1, a2)]
+        monkeypatch.setenv("OM_POISON_WS", "1")
+        junk = []
+        for rep in range(3):
+            junk.append(torch.full((rep + 1, 1 << 20), float("nan"), device=DEV))      # shifts what the allocator hands out
+            got = model.match(a1, a2)
+            for w, x in zip(want, got):
+                assert torch.equal(w, x), (flavour, rep)
+            if rep == 1:
+                junk.clear()
+                torch.cuda.empty_cache()
+
+
+def test_bad_parameters_fail_before_any_work_is_forked():
+    """A parameter only a stage launcher used to reject (NMS radius beyond the limit) now fails in the up-front validation;
+    the next call on the same stream works and the step still captures into a CUDA graph (no dangling fork)."""
+    from onnx_image_processing_b200.host_pipeline import GraphedMatcher
+    i1, i2 = (t.to(DEV) for t in O.texture_images(2, 120, 160, seed=61))
+    bad = om.ShiTomasiSparseBADSinkhornMatcher(64, nms_radius=40).to(DEV).eval()
+    good = om.ShiTomasiSparseBADSinkhornMatcher(64).to(DEV).eval()
+    with torch.no_grad():
+        want = [t.clone() for t in good(i1, i2)]
+        with pytest.raises(RuntimeError):
+            bad(i1, i2)
+        got = good(i1, i2)
+        torch.cuda.synchronize()
+        for w, x in zip(want, got):
+            assert torch.equal(w, x)
+        graphed = GraphedMatcher(good, i1, i2)
+        for w, x in zip(want, graphed(i1, i2)):
+            assert torch.equal(w, x)
+
+
+def test_caller_streams_do_not_share_side_streams():
+    """Two caller streams issuing matcher steps concurrently (what HostBatchMatcher's chunk streams do): each gets its own
+    side streams and events; results equal the single-stream ones."""
+    i1, i2 = (t.to(DEV) for t in O.texture_images(4, 240, 320, seed=62))
+    j1, j2 = (t.to(DEV) for t in O.texture_images(4, 240, 320, seed=63))
+    model = om.ShiTomasiBADSinkhornMatcher(256).to(DEV).eval()
+    with torch.no_grad():
+        wa = [t.clone() for t in model(i1, i2)]
+        wb = [t.clone() for t in model(j1, j2)]
+        torch.cuda.synchronize()
+        sa, sb = torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)
+        for _ in range(10):
+            with torch.cuda.stream(sa):
+                ga = model(i1, i2)
+            with torch.cuda.stream(sb):
+                gb = model(j1, j2)
+        torch.cuda.synchronize()
+    for w, x in zip(wa + wb, list(ga) + list(gb)):
+        assert torch.equal(w, x)
+
+
+def test_pair_table_follows_the_buffers():
+    """load_state_dict / buffer edits reach the kernels: the table the C ABI consumes is derived from the buffers the
+    reference's forward reads, at call time."""
+    img, _ = O.texture_images(1, 96, 128, seed=71)
+    k, _ = O.detect(img, 50, 3, 3, 0.0, 16)
+    sb = om.SparseBAD(normalize_descriptors=False).to(DEV)
+    d0 = sb(img.to(DEV), k.to(DEV))
+    state = {n: t.clone() for n, t in sb.state_dict().items()}
+    state["thresholds_v"] = state["thresholds_v"] + 2.0
+    sb.load_state_dict(state, strict=True)
+    d1 = sb(img.to(DEV), k.to(DEV))
+    assert float(((d0 - 2.0) - d1).abs().max()) <= 1e-4                  # centered = diff - threshold (bad.py:559)
+    dn = om.BADDescriptor().to(DEV)
+    m0 = dn(img.to(DEV))
+    with torch.no_grad():
+        dn.thresholds.add_(1.5)
+    m1 = dn(img.to(DEV))
+    assert float(((m0 - 1.5) - m1).abs().max()) <= 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_interleaved_in_one_process():
+    """Calls alternate between cuda:0 and cuda:1 tensors without any torch.cuda.set_device in between: every entry point
+    runs on the device that owns its pointers and leaves the caller's current device alone."""
+    i1, i2 = O.texture_images(2, 120, 160, seed=81)
+    m0 = om.ShiTomasiSparseBADSinkhornMatcher(64).to("cuda:0").eval()
+    m1 = om.ShiTomasiSparseBADSinkhornMatcher(64).to("cuda:1").eval()
+    with torch.no_grad():
+        want = [t.cpu() for t in m0(i1.to("cuda:0"), i2.to("cuda:0"))]
+        for _ in range(3):
+            for m, dev in ((m1, "cuda:1"), (m0, "cuda:0"), (m1, "cuda:1")):
+                cur = torch.cuda.current_device()
+                got = m(i1.to(dev), i2.to(dev))
+                assert torch.cuda.current_device() == cur
+                for w, x in zip(want, got):
+                    assert str(x.device) == dev and torch.equal(w, x.cpu())
+
+
+def test_same_pairs_alone_or_inside_a_larger_batch_are_byte_identical():
+    """What sharding over ranks relies on (1-GPU and N-GPU outputs bit-identical): the result of a pair does
+    not depend on which other pairs are in the launch, on the batch size, or on the pair's position in it."""
+    import hashlib
+    i1, i2 = O.texture_images(8, 480, 640, seed=1000)
+    model = om.ShiTomasiBADSinkhornMatcher(512).to(DEV).eval()
+
+    def sha(t):
+        return hashlib.sha256(t.cpu().contiguous().numpy().tobytes()).hexdigest()
+    with torch.no_grad():
+        whole = model(*_cuda(i1, i2))
+        for lo, hi in ((0, 1), (0, 4), (4, 8), (3, 5)):
+            part = model(*_cuda(i1[lo:hi], i2[lo:hi]))
+            for w, x in zip(whole, part):
+                assert sha(w[lo:hi]) == sha(x)

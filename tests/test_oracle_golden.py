@@ -10,6 +10,7 @@ import torch
 
 from oracle import oracle as O
 from tests import golden_util as G
+from tests import parity as PR
 
 
 def _sha(t):
@@ -163,21 +164,6 @@ def test_table_facts():
 # ------------------------------------------------------------------------------------------
 # full-size goldens (tests/golden/make_golden_full.py): the sizes the benchmark runs
 # ------------------------------------------------------------------------------------------
-def check_p_summary(p, g, tol, argmax_min=1.0):
-    """(1, N+1, M+1) matrix against the row-sample form stored for the large cases."""
-    N = p.shape[1] - 1
-    rows = g["P_rows"].long()
-    assert float((p[0, rows][:, :N + 1] - g["P_sample"]).abs()[:, :N].max()) <= tol          # sampled rows, core + dustbin column
-    assert float((p[0, N, :N] - g["P_dust_row"][:N]).abs().max()) <= tol
-    assert float((p[0, :N, N] - g["P_dust_col"][:N]).abs().max()) <= tol
-    assert abs(float(p[0, N, N]) - float(g["P_dust_row"][N])) <= max(tol, 1e-4 * float(g["P_dust_row"][N]))
-    core = p[0, :N, :N]
-    assert float((core.max(dim=-1).values - g["P_row_max"]).abs().max()) <= tol
-    assert float((core.argmax(dim=-1) == g["P_row_argmax"]).float().mean()) >= argmax_min
-    assert float((core.argmax(dim=-2) == g["P_col_argmax"]).float().mean()) >= argmax_min
-    assert abs(float(p.double().sum()) - g["P_sum64"]) <= 1e-6 * abs(g["P_sum64"]) + tol * N
-
-
 def test_dense_full_default():
     """BASELINE configs[1] at its real size: the oracle against the reference's own outputs."""
     g = G.load("dense_full_default")
@@ -194,21 +180,14 @@ def test_dense_full_default():
     assert torch.equal(mk1[v], m["mk1"][v]) and torch.equal(mk2[v], m["mk2"][v])
 
 
-def full_descriptor_bits(g, which):
-    """hard-binarised descriptors stored as packed bits + the row norm factor -> float descriptors"""
-    import numpy as np
-    bits = torch.from_numpy(np.unpackbits(g[f"desc{which}_bits"].numpy(), axis=-1)).float()
-    return bits * g[f"desc{which}_norm"].unsqueeze(-1)
-
-
 def test_sparse_full_export():
     """The configuration the reference's export script ships, at full size (K = 1024: generic Sinkhorn path)."""
     g = G.load("sparse_full_export")
     with torch.no_grad():
         k1, k2, p, d1, d2 = O.sparse_matcher(g["image1"], g["image2"], 1024, return_descriptors=True, **g["kwargs"])
     assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
-    assert (d1 - full_descriptor_bits(g, 1)).abs().max() <= 2e-6 and (d2 - full_descriptor_bits(g, 2)).abs().max() <= 2e-6
-    check_p_summary(p, g, 2e-6)
+    assert (d1 - PR.full_descriptor_bits(g, 1)).abs().max() <= 2e-6 and (d2 - PR.full_descriptor_bits(g, 2)).abs().max() <= 2e-6
+    PR.p_summary_ok(p, g, 2e-6)
 
 
 def test_sparse_1080p_k2048():
@@ -221,7 +200,7 @@ def test_sparse_1080p_k2048():
     assert (d1[0, rows] - g["desc1_sample"]).abs().max() <= 2e-6 and (d2[0, rows] - g["desc2_sample"]).abs().max() <= 2e-6
     assert (d1[0].double().sum(dim=-1).float() - g["desc1_rowsum"]).abs().max() <= 1e-4
     assert (d2[0].double().sum(dim=-1).float() - g["desc2_rowsum"]).abs().max() <= 1e-4
-    check_p_summary(p, g, 2e-6)
+    PR.p_summary_ok(p, g, 2e-6)
 
 
 def test_sinkhorn_with_scores():
