@@ -588,6 +588,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e2e["achieved_h2d_gbs_per_gpu"] = h2d_gbs
         e2e["achieved_d2h_gbs_per_gpu"] = d2h_gbs
         e2e["frac_of_link"] = max(h2d_gbs / link["h2d_gbs_per_gpu"], d2h_gbs / link["d2h_gbs_per_gpu"])
+        e2e["frac_of_duplex_link"] = (h2d_gbs + d2h_gbs) / (2.0 * link["duplex_gbs_per_gpu_each_way"])
         e2e["link_ceiling_pairs_per_s"] = world * B / max(e2e["h2d_bytes_per_step"] / (link["h2d_gbs_per_gpu"] * 1e9),
                                                           e2e["d2h_bytes_per_step"] / (link["d2h_gbs_per_gpu"] * 1e9))
 

@@ -51,6 +51,12 @@ extern "C" {
 #define OM_THETA_MAP 1       /* nearest sample of a (B,H,W) orientation map, descriptor/bad.py:487-499 */
 #define OM_THETA_MOMENTS 2   /* evaluate orientation/angle_estimation.py:161-170 at the keypoints only */
 
+/* pixel type of the images handed to om_match_pairs / om_detect_u8.  uint8 is an extension for the real callers'
+ * preprocessing (sample/visual_odometry.py:65-92, sample/image_matching.py:28-47 produce 8-bit grey images and only then
+ * widen them): the kernels read the bytes natively and results are bit-identical to the same pixels passed as float32. */
+#define OM_IMAGE_F32 0
+#define OM_IMAGE_U8 1
+
 /* matcher flavours of om_match_pairs_f32 */
 #define OM_MATCH_SPARSE 0    /* feature_detection/shi_tomasi_sparse_bad_sinkhorn.py:134-182 */
 #define OM_MATCH_ANGLE 1     /* feature_detection/shi_tomasi_angle_sparse_bad_sinkhorn.py:132-180 */
@@ -213,6 +219,7 @@ typedef struct om_match_params {
     float epsilon;
     float unused_score;
     int distance_l1;
+    int image_dtype;        /* OM_IMAGE_F32 or OM_IMAGE_U8 */
 } om_match_params;
 
 size_t om_match_workspace_bytes(const om_match_params* p);
@@ -224,6 +231,19 @@ int om_match_pairs_f32(const om_match_params* p, const float* image1, const floa
                        float* kpts1, float* kpts2, float* probs /* B,K+1,K+1 */,
                        float* desc1, float* desc2,
                        void* ws, size_t ws_bytes, void* stream);
+
+/* The same with the images in either pixel type (p->image_dtype): image1 / image2 point to float32 or uint8 (B,H,W). */
+int om_match_pairs(const om_match_params* p, const void* image1, const void* image2,
+                   const float* pair_table, const float* moment_kernels,
+                   float* kpts1, float* kpts2, float* probs /* B,K+1,K+1 */,
+                   float* desc1, float* desc2,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* om_detect_f32 on uint8 images (block 3 / 5 with NMS radius 3 read the bytes natively, other routings widen first). */
+int om_detect_u8(const unsigned char* image, int B, int H, int W, int block_size, int nms_radius,
+                 int border_margin, float score_threshold, int K,
+                 float* score_map, float* kpts, float* kpt_scores,
+                 void* ws, size_t ws_bytes, void* stream);
 
 /* ---- test hooks ---------------------------------------------------------------------------- */
 
@@ -245,6 +265,8 @@ void om_debug_match_streams(int n);
  * copies by the keypoint's thread group (cross-check, slower); bit 1 / bit 2 (diagnosis only, wrong results): skip the
  * window fetch / skip the pair arithmetic. */
 void om_debug_dense_window(int tma);
+/* Banded integral-image build: padded-image rows per band (even, 8..256; default 32). */
+void om_debug_band_rows(int rows);
 /* Score kernel of the split sweep form: 1 = score3_sweep_kernel / score5_sweep_kernel (default), 2 = the same at
  * another occupancy (6 / 3 CTAs per SM instead of 5 / 4), 0 = stencil_sweep_kernel<.., NMS = false> (cross-check). */
 void om_debug_score_variant(int v);

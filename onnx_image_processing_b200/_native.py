@@ -23,7 +23,7 @@ class MatchParams(Structure):
         ("block_size", c_int), ("nms_radius", c_int), ("border_margin", c_int), ("score_threshold", c_float),
         ("P", c_int), ("desc_mode", c_int), ("temperature", c_float), ("normalize", c_int),
         ("sampling_mode", c_int), ("patch_size", c_int), ("iterations", c_int), ("epsilon", c_float),
-        ("unused_score", c_float), ("distance_l1", c_int),
+        ("unused_score", c_float), ("distance_l1", c_int), ("image_dtype", c_int),
     ]
 
 
@@ -66,6 +66,10 @@ SIGNATURES = {
     "om_match_workspace_bytes": (c_size_t, [POINTER(MatchParams)]),
     "om_match_pairs_f32": (c_int, [POINTER(MatchParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "om_match_pairs": (c_int, [POINTER(MatchParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "om_detect_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_size_t, c_void_p]),
     "om_debug_detect_stage": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "om_debug_dense_stage": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float,
@@ -76,6 +80,7 @@ SIGNATURES = {
     "om_debug_essential_variant": (None, [c_int]),
     "om_debug_match_streams": (None, [c_int]),
     "om_debug_dense_window": (None, [c_int]),
+    "om_debug_band_rows": (None, [c_int]),
     "om_debug_score_variant": (None, [c_int]),
     "om_debug_force_generic_sinkhorn": (None, [c_int]),
     "om_debug_sinkhorn_variant": (None, [c_int]),

@@ -67,6 +67,19 @@ def _images(image: torch.Tensor, what: str) -> Tuple[torch.Tensor, int, int, int
     return _f32(image, what), B, H, W
 
 
+def _images_native(image: torch.Tensor, what: str) -> Tuple[torch.Tensor, int, int, int, int]:
+    """(tensor, B, H, W, image_dtype code): uint8 images stay uint8 (read natively by the fused kernels: an extension for
+    8-bit camera frames, exact), everything else is float32 as in the reference (`img.float()`, shi_tomasi.py:78)."""
+    if image.is_cuda and image.dtype == torch.uint8:
+        if image.dim() == 4 and image.shape[1] != 1:
+            raise RuntimeError(f"{what}: expected (B,1,H,W), got {tuple(image.shape)}")
+        if image.dim() not in (3, 4):
+            raise RuntimeError(f"{what}: expected (B,1,H,W) or (B,H,W), got {tuple(image.shape)}")
+        return image.contiguous(), image.shape[0], image.shape[-2], image.shape[-1], 1
+    img, B, H, W = _images(image, what)
+    return img, B, H, W, 0
+
+
 # ---------------------------------------------------------------------------------------------
 @torch.library.custom_op("b200match::shi_tomasi_score", mutates_args=(), device_types="cuda")
 def shi_tomasi_score(image: torch.Tensor, block_size: int) -> torch.Tensor:
@@ -126,7 +139,7 @@ def _(scores, mask, max_keypoints, score_threshold, border_margin):
 @torch.library.custom_op("b200match::detect", mutates_args=(), device_types="cuda")
 def detect(image: torch.Tensor, max_keypoints: int, block_size: int, nms_radius: int, score_threshold: float,
            border_margin: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    img, B, H, W = _images(image, "image")
+    img, B, H, W, u8 = _images_native(image, "image")
     if max_keypoints > H * W:
         raise RuntimeError("selected index k out of range")
     lib, st = _begin(img)
@@ -134,8 +147,9 @@ def detect(image: torch.Tensor, max_keypoints: int, block_size: int, nms_radius:
     kpts = torch.empty((B, K, 2), dtype=torch.float32, device=img.device)
     ks = torch.empty((B, K), dtype=torch.float32, device=img.device)
     ws = _ws(lib.om_topk_workspace_bytes(B, H, W, K), img)
-    nat.check(lib.om_detect_f32(_p(img), B, H, W, block_size, nms_radius, int(border_margin), float(score_threshold),
-                                K, _p(None), _p(kpts), _p(ks), _p(ws), ws.numel(), st), "om_detect_f32")
+    fn = lib.om_detect_u8 if u8 else lib.om_detect_f32
+    nat.check(fn(_p(img), B, H, W, block_size, nms_radius, int(border_margin), float(score_threshold),
+                 K, _p(None), _p(kpts), _p(ks), _p(ws), ws.numel(), st), "om_detect")
     return kpts, ks
 
 
@@ -383,10 +397,10 @@ def _(probs, pts1, pts2, valid1, valid2, top_k, n_iter, n_iter_manifold):
 def make_match_params(flavour: int, B: int, H: int, W: int, K: int, block_size: int, nms_radius: int,
                       border_margin: int, score_threshold: float, P: int, mode: int, temperature: float,
                       normalize: bool, sampling: int, patch_size: int, iterations: int, epsilon: float,
-                      unused_score: float, distance_l1: bool) -> nat.MatchParams:
+                      unused_score: float, distance_l1: bool, image_dtype: int = 0) -> nat.MatchParams:
     return nat.MatchParams(flavour, B, H, W, K, block_size, nms_radius, border_margin, score_threshold, P, mode,
                            temperature, int(normalize), sampling, patch_size, iterations, epsilon, unused_score,
-                           int(distance_l1))
+                           int(distance_l1), int(image_dtype))
 
 
 @torch.library.custom_op("b200match::match_pairs", mutates_args=(), device_types="cuda")
@@ -396,10 +410,12 @@ def match_pairs(image1: torch.Tensor, image2: torch.Tensor, pair_table: torch.Te
                 normalize: bool, sampling: int, iterations: int, epsilon: float, unused_score: float,
                 distance_l1: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Whole matcher forward in one C call: (kpts1, kpts2, probs, desc1, desc2)."""
-    i1, B, H, W = _images(image1, "image1")
-    i2, B2, H2, W2 = _images(image2, "image2")
+    i1, B, H, W, u8 = _images_native(image1, "image1")
+    i2, B2, H2, W2, u8b = _images_native(image2, "image2")
     if (B, H, W) != (B2, H2, W2):
         raise RuntimeError("image1 and image2 must have the same shape")
+    if u8 != u8b:                                  # mixed pixel types: widen the uint8 one
+        i1, i2, u8 = i1.float(), i2.float(), 0
     K = max_keypoints
     if K > H * W:
         raise RuntimeError("selected index k out of range")
@@ -409,7 +425,7 @@ def match_pairs(image1: torch.Tensor, image2: torch.Tensor, pair_table: torch.Te
     ps = int(mk.shape[-1]) if mk is not None else 0
     lib, st = _begin(i1)
     prm = make_match_params(flavour, B, H, W, K, block_size, nms_radius, border_margin, score_threshold, P, mode,
-                            temperature, normalize, sampling, ps, iterations, epsilon, unused_score, distance_l1)
+                            temperature, normalize, sampling, ps, iterations, epsilon, unused_score, distance_l1, u8)
     dev = i1.device
     k1 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
     k2 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
@@ -420,8 +436,8 @@ def match_pairs(image1: torch.Tensor, image2: torch.Tensor, pair_table: torch.Te
     if nbytes == 0:
         raise RuntimeError("om_match_workspace_bytes rejected the parameters")
     ws = _ws(nbytes, i1)
-    nat.check(lib.om_match_pairs_f32(ctypes.byref(prm), _p(i1), _p(i2), _p(tb), _p(mk), _p(k1), _p(k2), _p(probs),
-                                     _p(d1), _p(d2), _p(ws), ws.numel(), st), "om_match_pairs_f32")
+    nat.check(lib.om_match_pairs(ctypes.byref(prm), _p(i1), _p(i2), _p(tb), _p(mk), _p(k1), _p(k2), _p(probs),
+                                 _p(d1), _p(d2), _p(ws), ws.numel(), st), "om_match_pairs")
     return k1, k2, probs, d1, d2
 
 

@@ -156,6 +156,7 @@ int check_params(const om_match_params* p) {
         return OM_ERR_PARAM;
     if (p->flavour == OM_MATCH_ANGLE && (p->patch_size < 1 || p->patch_size % 2 == 0 || p->patch_size > 31)) return OM_ERR_PARAM;
     if (p->iterations <= 0 || !(p->epsilon > 0.0f)) return OM_ERR_PARAM;  // matching/sinkhorn.py:66-69
+    if (p->image_dtype != OM_IMAGE_F32 && p->image_dtype != OM_IMAGE_U8) return OM_ERR_PARAM;
     return OM_OK;
 }
 
@@ -204,6 +205,13 @@ extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
 extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1, const float* image2,
                                   const float* pair_table, const float* moment_kernels, float* kpts1, float* kpts2,
                                   float* probs, float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream) {
+    if (p != nullptr && p->image_dtype != OM_IMAGE_F32) return OM_ERR_PARAM;
+    return om_match_pairs(p, image1, image2, pair_table, moment_kernels, kpts1, kpts2, probs, desc1, desc2, ws, ws_bytes, stream);
+}
+
+extern "C" int om_match_pairs(const om_match_params* p, const void* image1, const void* image2,
+                              const float* pair_table, const float* moment_kernels, float* kpts1, float* kpts2,
+                              float* probs, float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream) {
     OM_ON_DEVICE_OF(image1);
     OM_TRY(check_params(p));
     if (image1 == nullptr || image2 == nullptr || pair_table == nullptr || kpts1 == nullptr || kpts2 == nullptr ||
@@ -215,8 +223,9 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
     cudaStream_t st = (cudaStream_t)stream;
     float* d1 = desc1 ? desc1 : w.desc1;
     float* d2 = desc2 ? desc2 : w.desc2;
-    const DetectCfg dc{p->B, p->H, p->W, p->block_size, p->nms_radius, p->border_margin, p->score_threshold, p->K};
-    const float* images[2] = {image1, image2};
+    const int u8 = p->image_dtype == OM_IMAGE_U8;
+    const DetectCfg dc{p->B, p->H, p->W, p->block_size, p->nms_radius, p->border_margin, p->score_threshold, p->K, u8};
+    const void* images[2] = {image1, image2};
     float* kp[2] = {kpts1, kpts2};
     float* ds[2] = {d1, d2};
     cudaStream_t chain[2] = {st, st};           // detector + descriptors of image 1 / image 2
@@ -239,10 +248,10 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
     }
     auto descriptors = [&](int s, cudaStream_t q, int phase) -> int {
         if (p->flavour == OM_MATCH_DENSE)
-            return dense_bad_at_kpts_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
+            return dense_bad_at_kpts_launch(images[s], u8, p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
                                             p->temperature, p->normalize, ds[s], w.dense[s], w.dense_bytes, q, phase);
         const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
-        return sparse_bad_launch(images[s], p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode, p->temperature,
+        return sparse_bad_launch(images[s], u8, p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode, p->temperature,
                                  p->normalize, p->sampling_mode, theta, nullptr, moment_kernels, p->patch_size, ds[s],
                                  w.dense[s], w.dense_bytes, q, phase);
     };

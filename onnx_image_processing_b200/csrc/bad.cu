@@ -71,7 +71,8 @@ __device__ __forceinline__ float finish_value(float diff, float thr, int mode, f
 }
 
 struct SparseArgs {
-    const float* image;
+    const void* image;         // float32, or uint8 when image_u8 (uint8 images are never flagged)
+    int image_u8;
     int B, H, W;
     const float* kpts;
     int K;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void sparse_bad_group(const SparseArgs& a, long long 
     const int z = (int)(kidx / a.K);
     if (a.flags != nullptr && a.flags[z] == 0u) return;   // integer-valued image: sparse_win_kernel did this keypoint
     const int H = a.H, W = a.W;
-    const float* img = a.image + (size_t)z * H * W;
+    const float* img = reinterpret_cast<const float*>(a.image) + (size_t)z * H * W;   // flagged images are float32
     float* out = a.desc + (size_t)kidx * a.P;
 
     const float ky = a.kpts[kidx * 2 + 0], kx = a.kpts[kidx * 2 + 1];
@@ -495,14 +496,17 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
             theta = __ldg(a.orientation + (size_t)z * H * W + (size_t)ny * W + nx);
         } else {
             // angle_estimation.py:161-170 at (ny,nx) only: zero-padded cross-correlation, then atan2
-            const float* img = a.image + (size_t)z * H * W;
+            const size_t ibase = (size_t)z * H * W;
+            const float* imgf = reinterpret_cast<const float*>(a.image);
+            const unsigned char* imgb = reinterpret_cast<const unsigned char*>(a.image);
             const int ps = a.patch_size, half = ps / 2;
             float m10 = 0.0f, m01 = 0.0f;
             for (int tap = t; tap < ps * ps; tap += TPG) {
                 const int j = tap / ps, i = tap - j * ps;
                 const int gy = ny + j - half, gx = nx + i - half;
                 if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                    const float v = __ldg(img + (size_t)gy * W + gx);
+                    const size_t idx = ibase + (size_t)gy * W + gx;
+                    const float v = a.image_u8 ? (float)__ldg(imgb + idx) : __ldg(imgf + idx);
                     m10 = fmaf(__ldg(a.moments + tap), v, m10);
                     m01 = fmaf(__ldg(a.moments + ps * ps + tap), v, m01);
                 }
@@ -731,7 +735,8 @@ constexpr int PC_COLS = 32, PC_SEG = 32;
 
 template <bool EXACT, int LMAX>   // LMAX > 0: a segment (<= LMAX rows) is kept in registers between the two walks
 __global__ void __launch_bounds__(PC_COLS * PC_SEG) prefix_cols_kernel(const float* image, int H, int W, int pad, void* Tout,
-                                                                       unsigned int* flags) {
+                                                                       unsigned int* flags, const unsigned int* gate) {
+    if (gate != nullptr && *gate == 0u) return;              // fallback build: only when the banded build flagged an image
     using Acc = typename std::conditional<EXACT, unsigned int, double>::type;
     using Out = typename std::conditional<EXACT, unsigned int, float>::type;
     __shared__ Acc seg_total[PC_SEG][PC_COLS];
@@ -807,7 +812,9 @@ __global__ void __launch_bounds__(PC_COLS * PC_SEG) prefix_cols_kernel(const flo
 constexpr int IR_ROWS = 8;
 
 template <bool EXACT>
-__global__ void __launch_bounds__(IR_ROWS * 32) prefix_rows_kernel(const void* Tin, int H, int W, int pad, int SL, void* Iout) {
+__global__ void __launch_bounds__(IR_ROWS * 32) prefix_rows_kernel(const void* Tin, int H, int W, int pad, int SL, void* Iout,
+                                                                   const unsigned int* gate) {
+    if (gate != nullptr && *gate == 0u) return;
     using Acc = typename std::conditional<EXACT, unsigned int, double>::type;
     using Val = typename std::conditional<EXACT, unsigned int, float>::type;
     extern __shared__ __align__(16) unsigned char sRowRaw[];
@@ -847,20 +854,334 @@ __global__ void __launch_bounds__(IR_ROWS * 32) prefix_rows_kernel(const void* T
 }
 
 template <bool EXACT>
-int build_prefix(const float* image, int B, int H, int W, int pad, void* T, void* I, unsigned int* flags, cudaStream_t st) {
+int build_prefix(const float* image, int B, int H, int W, int pad, void* T, void* I, unsigned int* flags, cudaStream_t st,
+                 const unsigned int* gate = nullptr) {
     const int Wp = W + 2 * pad, Hp = H + 2 * pad;
     const dim3 cgrid((Wp + PC_COLS - 1) / PC_COLS, B);
     const int L = (Hp + PC_SEG - 1) / PC_SEG;
-    if (EXACT && L <= 20) prefix_cols_kernel<EXACT, 20><<<cgrid, PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags);
-    else prefix_cols_kernel<EXACT, 0><<<cgrid, PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags);
+    if (EXACT && L <= 20) prefix_cols_kernel<EXACT, 20><<<cgrid, PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags, gate);
+    else prefix_cols_kernel<EXACT, 0><<<cgrid, PC_COLS * PC_SEG, 0, st>>>(image, H, W, pad, T, flags, gate);
     OM_AFTER_LAUNCH();
     const int SL = ((Wp + 31) / 32) | 1;
     const size_t smem = (size_t)IR_ROWS * 32 * SL * 4;
     if (smem > 200 * 1024) return OM_ERR_LIMIT;              // W <= ~6300
     OM_TRY(set_smem(prefix_rows_kernel<EXACT>, smem));
-    prefix_rows_kernel<EXACT><<<dim3((Hp + 1 + IR_ROWS - 1) / IR_ROWS, B), IR_ROWS * 32, smem, st>>>(T, H, W, pad, SL, I);
+    prefix_rows_kernel<EXACT><<<dim3((Hp + 1 + IR_ROWS - 1) / IR_ROWS, B), IR_ROWS * 32, smem, st>>>(T, H, W, pad, SL, I, gate);
     OM_AFTER_LAUNCH();
     return OM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// banded integral image (the default build; the two prefix passes above remain for float-valued images on the dense
+// path and for very wide images)
+// ------------------------------------------------------------------------------------------
+// The image is read in its own type (float32 or uint8) and the integral is exact uint32 arithmetic, stored as uint32
+// (sparse path: box sums are wrap-around differences) or as float32 = RN(exact) (dense path: exactly what the
+// reference's double-accumulated float32 cumsums produce for integer-valued pixels, bad.py:70-72).
+//   pass A  band_colsum_kernel: the padded image is cut into bands of IB_ROWS rows; one CTA per (band, image) sums every
+//           column of its band (tiny output: bands x pitch words per image) and raises the per-image flag when a pixel
+//           is not an integer in [0, maxv] (float input only).
+//   pass B  integral_band_kernel: one CTA per (band, image) owns ALL columns of its band: thread t holds output columns
+//           8t..8t+7.  It starts from the integral row above the band (column sums of the bands above, scanned across
+//           the CTA once), then walks its rows in groups of IB_G: row prefix = 8-element local prefix + warp scan
+//           (shuffles) + warp totals through shared memory (ONE block barrier per group, double buffered), vertical
+//           accumulation in registers (one 3-input add per pixel), two 16-byte stores per row.  Two groups of rows are in
+//           flight while a third is scanned.  The image is read twice (pass A, pass B) and the integral written once: no
+//           intermediate integral-sized array exists (the two-pass build wrote and re-read one), and every (band, image)
+//           is independent (no look-back chain).
+// float -> integer conversions use the 2^23 trick (v + 2^23 holds the integer v in its low mantissa bits for
+// 0 <= v < 2^23; (v + 2^23) - 2^23 == v exactly when v is such an integer): no conversion instructions, no branches.
+int g_band_rows = 32;              // padded-image rows per band (om_debug_band_rows)
+constexpr int IB_G = 2;            // rows per group
+constexpr int IB_PX = 8;           // output columns per thread
+constexpr float IB_MAGIC = 8388608.0f;
+
+// which pixels thread t's output columns c = 8t + j read: padded pixel column c - 1 (column 0 of the integral and the
+// columns beyond the padded width hold zero), replicate-clamped to the image
+// ALIGNED images (W % 8 == 0, 8-pixel aligned base; (1 + pad) % 8 == 0 for every pad in use): a thread's eight pixels are
+// either eight consecutive aligned pixels of the image (vector loads) or all the same replicated border pixel (one load)
+// -- no thread straddles a border.  Other images take clamped scalar loads (separate instantiation).
+struct BandCols {
+    unsigned int in;    // bit j: output column 8t + j is a pixel column
+    bool vec;           // the eight pixels are consecutive, unclamped and aligned: vector loads
+    int x0;             // image column of j = 0 (before clamping)
+    int wmax;           // W - 1
+};
+__device__ __forceinline__ BandCols band_cols(int t, int W, int pad, bool aligned_rows) {
+    BandCols b;
+    const int Wp = W + 2 * pad;
+    b.in = 0u;
+#pragma unroll
+    for (int j = 0; j < IB_PX; ++j) {
+        const int c = IB_PX * t + j;
+        if (c >= 1 && c <= Wp) b.in |= 1u << j;
+    }
+    b.x0 = IB_PX * t - 1 - pad;
+    b.wmax = W - 1;
+    b.vec = aligned_rows && b.x0 >= 0 && b.x0 + IB_PX - 1 <= W - 1 && (b.x0 & (IB_PX - 1)) == 0;
+    return b;
+}
+// raw pixels of one row (loads only: nothing here waits for the data)
+template <typename TIn, bool ALIGNED>
+__device__ __forceinline__ void band_fetch(const TIn* rowp, const BandCols& b, TIn (&raw)[IB_PX]) {
+    if (ALIGNED && !b.vec) {                                    // wholly inside the left or the right padding
+        const TIn v = __ldg(rowp + clampi(b.x0, 0, b.wmax));
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j) raw[j] = v;
+        return;
+    }
+    if (ALIGNED) {
+        if constexpr (sizeof(TIn) == 4) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(rowp + b.x0)), q1 = __ldg(reinterpret_cast<const float4*>(rowp + b.x0 + 4));
+            raw[0] = q0.x; raw[1] = q0.y; raw[2] = q0.z; raw[3] = q0.w; raw[4] = q1.x; raw[5] = q1.y; raw[6] = q1.z; raw[7] = q1.w;
+        } else {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(rowp + b.x0));
+            raw[0] = (TIn)(q.x & 0xFFu); raw[1] = (TIn)((q.x >> 8) & 0xFFu); raw[2] = (TIn)((q.x >> 16) & 0xFFu); raw[3] = (TIn)(q.x >> 24);
+            raw[4] = (TIn)(q.y & 0xFFu); raw[5] = (TIn)((q.y >> 8) & 0xFFu); raw[6] = (TIn)((q.y >> 16) & 0xFFu); raw[7] = (TIn)(q.y >> 24);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j) raw[j] = __ldg(rowp + clampi(b.x0 + j, 0, b.wmax));   // clamped: always a valid address
+    }
+}
+template <typename TIn>
+__device__ __forceinline__ unsigned int band_uint(TIn v) {
+    if constexpr (sizeof(TIn) == 4) return __float_as_uint(__fadd_rn(v, IB_MAGIC)) & 0x007FFFFFu;
+    else return (unsigned int)v;
+}
+
+template <typename TIn, int NT, bool ALIGNED>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 8 : (NT <= 256 ? 4 : 1)))
+band_colsum_kernel(const TIn* image, int H, int W, int pad, int nb, int IB_ROWS, int CP, float maxv, unsigned int* colsum,
+                   unsigned int* flags) {
+    const int z = blockIdx.y, k = blockIdx.x, t = threadIdx.x;
+    const int Hp = H + 2 * pad;
+    const bool live = IB_PX * t < CP;
+    const BandCols bc = band_cols(t, W, pad, ALIGNED);
+    const TIn* img = image + (size_t)z * H * W;
+    const int y0 = k * IB_ROWS, y1 = min(y0 + IB_ROWS, Hp);
+    unsigned int s[IB_PX];
+#pragma unroll
+    for (int j = 0; j < IB_PX; ++j) s[j] = 0u;
+    bool odd = false;
+    float mn = 0.0f, mx = 0.0f;
+    if (live) {
+        constexpr int RA = 4;                                   // rows in flight per thread
+        for (int y = y0; y < y1; y += RA) {
+            TIn raw[RA][IB_PX];
+#pragma unroll
+            for (int g = 0; g < RA; ++g) band_fetch<TIn, ALIGNED>(img + (size_t)clampi(min(y + g, y1 - 1) - pad, 0, H - 1) * W, bc, raw[g]);
+#pragma unroll
+            for (int g = 0; g < RA; ++g) {
+                if (y + g < y1) {                               // block-uniform
+#pragma unroll
+                    for (int j = 0; j < IB_PX; ++j) {
+                        if constexpr (sizeof(TIn) == 4) {
+                            const float v = raw[g][j];
+                            const float tt = __fadd_rn(v, IB_MAGIC);
+                            odd |= __fsub_rn(tt, IB_MAGIC) != v;                  // not an integer (or NaN, or beyond 2^23)
+                            mn = fminf(mn, v);
+                            mx = fmaxf(mx, v);
+                            s[j] += __float_as_uint(tt) & 0x007FFFFFu;
+                        } else {
+                            s[j] += (unsigned int)raw[g][j];
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j)
+            if (!((bc.in >> j) & 1u)) s[j] = 0u;
+        unsigned int* dst = colsum + ((size_t)z * nb + k) * CP + IB_PX * t;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    if (sizeof(TIn) == 4) {
+        odd = odd || mn < 0.0f || mx > maxv;
+        const int any_odd = __syncthreads_or(odd ? 1 : 0);
+        if (any_odd && t == 0) {
+            atomicOr(&flags[z], 1u);
+            atomicOr(&flags[gridDim.y], 1u);                 // "some image of the batch is flagged"
+        }
+    }
+}
+
+template <typename TIn, typename TOut, int NT, bool ALIGNED>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 7 : (NT <= 256 ? 3 : 1)))
+integral_band_kernel(const TIn* image, int H, int W, int pad, int nb, int IB_ROWS, int IP, int CP, const unsigned int* colsum,
+                     TOut* Iout) {
+    constexpr int NWARP = NT / 32;
+    __shared__ __align__(16) unsigned int wtot[2][NWARP][4];    // [buffer][warp][row of the group (padded to 4)]
+    const int z = blockIdx.y, k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const bool live = IB_PX * t < IP;
+    const bool live_hi = IB_PX * t + 4 < IP;                    // ipitch is a multiple of 4, not of 8
+    const BandCols bc = band_cols(t, W, pad, ALIGNED);
+    // beyond the padded width the integral holds zero (never a tap); column 0 is zero by construction (prefix of nothing)
+    const unsigned int first_zero = (unsigned int)max(0, min(IB_PX, Wp + 1 - IB_PX * t));   // columns j >= first_zero are stored as 0
+    const TIn* img = image + (size_t)z * H * W;
+    TOut* Iz = Iout + (size_t)z * (Hp + 1) * IP;
+    const int y0 = k * IB_ROWS, y1 = min(y0 + IB_ROWS, Hp);
+    const unsigned full = 0xffffffffu;
+    auto put = [&](int irow, const unsigned int (&a)[IB_PX]) {  // integral row irow, this thread's eight columns
+        if (!live) return;
+        unsigned int o[IB_PX];
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j) o[j] = a[j];
+        if (first_zero < (unsigned int)IB_PX) {                  // the thread(s) at the right end of the padded width only
+#pragma unroll
+            for (int j = 0; j < IB_PX; ++j) o[j] = (unsigned int)j < first_zero ? a[j] : 0u;
+        }
+        TOut* dst = Iz + (size_t)irow * IP + IB_PX * t;
+        if constexpr (std::is_same<TOut, float>::value) {
+            *reinterpret_cast<float4*>(dst) = make_float4(__uint2float_rn(o[0]), __uint2float_rn(o[1]), __uint2float_rn(o[2]), __uint2float_rn(o[3]));
+            if (live_hi)
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint2float_rn(o[4]), __uint2float_rn(o[5]), __uint2float_rn(o[6]), __uint2float_rn(o[7]));
+        } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (live_hi) *reinterpret_cast<uint4*>(dst + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    };
+    // exclusive prefix over the CTA of one value per thread, for the IB_G rows of a group at once
+    int buf = 0;
+    auto cta_excl = [&](const unsigned int (&tot)[IB_G], unsigned int (&excl)[IB_G]) {
+        unsigned int incl[IB_G];
+#pragma unroll
+        for (int g = 0; g < IB_G; ++g) incl[g] = tot[g];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int g = 0; g < IB_G; ++g) {
+                const unsigned int n = __shfl_up_sync(full, incl[g], o);
+                incl[g] += lane >= o ? n : 0u;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int g = 0; g < IB_G; ++g) wtot[buf][warp][g] = incl[g];
+        }
+        __syncthreads();
+        unsigned int wb[IB_G];
+#pragma unroll
+        for (int g = 0; g < IB_G; ++g) wb[g] = 0u;
+#pragma unroll
+        for (int w = 0; w < NWARP - 1; ++w) {                   // totals of the warps before this one
+            const uint2 v = *reinterpret_cast<const uint2*>(&wtot[buf][w][0]);
+            if (w < warp) { wb[0] += v.x; if (IB_G > 1) wb[IB_G - 1] += v.y; }
+        }
+#pragma unroll
+        for (int g = 0; g < IB_G; ++g) excl[g] = wb[g] + incl[g] - tot[g];
+        buf ^= 1;
+    };
+    static_assert(IB_G == 2, "the warp-total exchange above moves two rows per load");
+
+    // integral row above the band: row prefix of the column sums of the bands above
+    unsigned int acc[IB_PX];
+    {
+        unsigned int base[IB_PX];
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j) base[j] = 0u;
+        if (live) {
+            const unsigned int* cs = colsum + (size_t)z * nb * CP + IB_PX * t;
+#pragma unroll 4
+            for (int q = 0; q < k; ++q) {
+                const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(cs + (size_t)q * CP)), c1 = __ldg(reinterpret_cast<const uint4*>(cs + (size_t)q * CP + 4));
+                base[0] += c0.x; base[1] += c0.y; base[2] += c0.z; base[3] += c0.w;
+                base[4] += c1.x; base[5] += c1.y; base[6] += c1.z; base[7] += c1.w;
+            }
+        }
+#pragma unroll
+        for (int j = 1; j < IB_PX; ++j) base[j] += base[j - 1];
+        unsigned int tot[IB_G] = {base[IB_PX - 1], 0u}, excl[IB_G];
+        cta_excl(tot, excl);
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j) acc[j] = excl[0] + base[j];
+    }
+    if (k == 0) {
+        unsigned int zero[IB_PX];
+#pragma unroll
+        for (int j = 0; j < IB_PX; ++j) zero[j] = 0u;
+        put(0, zero);                                            // the zero row of bad.py:72
+    }
+    auto fetch = [&](int y, TIn (&dst)[IB_G][IB_PX]) {
+#pragma unroll
+        for (int g = 0; g < IB_G; ++g)      // (threads beyond the pitch have in == 0: their clamped loads are masked to zero)
+            band_fetch<TIn, ALIGNED>(img + (size_t)clampi(min(y + g, y1 - 1) - pad, 0, H - 1) * W, bc, dst[g]);
+    };
+    auto scan_rows = [&](int y, const TIn (&raw)[IB_G][IB_PX]) {
+        unsigned int v[IB_G][IB_PX], tot[IB_G], excl[IB_G];
+#pragma unroll
+        for (int g = 0; g < IB_G; ++g) {
+#pragma unroll
+            for (int j = 0; j < IB_PX; ++j) v[g][j] = band_uint<TIn>(raw[g][j]);
+            if (bc.in != 0xFFu) {                               // edge threads only: column 0, columns beyond the padded width
+#pragma unroll
+                for (int j = 0; j < IB_PX; ++j) v[g][j] = ((bc.in >> j) & 1u) ? v[g][j] : 0u;
+            }
+#pragma unroll
+            for (int j = 1; j < IB_PX; ++j) v[g][j] += v[g][j - 1];      // inclusive prefix of the thread's eight pixels
+            tot[g] = v[g][IB_PX - 1];
+        }
+        cta_excl(tot, excl);
+#pragma unroll
+        for (int g = 0; g < IB_G; ++g) {
+            if (y + g < y1) {                                   // block-uniform
+#pragma unroll
+                for (int j = 0; j < IB_PX; ++j) acc[j] = acc[j] + v[g][j] + excl[g];
+                put(y + g + 1, acc);
+            }
+        }
+    };
+    // three ring slots, rotated by name so that every index stays a compile-time constant
+    TIn ga[IB_G][IB_PX], gb[IB_G][IB_PX], gc[IB_G][IB_PX];
+    fetch(y0, ga);
+    fetch(y0 + IB_G, gb);
+    for (int y = y0; y < y1; y += 3 * IB_G) {
+        fetch(y + 2 * IB_G, gc);
+        scan_rows(y, ga);
+        if (y + IB_G >= y1) break;
+        fetch(y + 3 * IB_G, ga);
+        scan_rows(y + IB_G, gb);
+        if (y + 2 * IB_G >= y1) break;
+        fetch(y + 4 * IB_G, gb);
+        scan_rows(y + 2 * IB_G, gc);
+    }
+}
+
+inline int band_colsum_pitch(int W, int pad) { return (ipitch(W, pad) + IB_PX - 1) / IB_PX * IB_PX; }
+
+// ipitch <= 8 * NT.  Returns OM_ERR_LIMIT when the image is too wide for one CTA per band (the caller falls back).
+template <typename TIn, typename TOut>
+int build_integral_banded(const TIn* image, int B, int H, int W, int pad, float maxv, unsigned int* colsum, TOut* I,
+                          unsigned int* flags, cudaStream_t st) {
+    const int Hp = H + 2 * pad, IP = ipitch(W, pad), CP = band_colsum_pitch(W, pad);
+    const int IB_ROWS = g_band_rows;
+    const int nb = (Hp + IB_ROWS - 1) / IB_ROWS;
+    if (CP > IB_PX * 1024 || B > 65535) return OM_ERR_LIMIT;
+    const dim3 grid(nb, B);
+    const bool aligned = (W & 7) == 0 && ((1 + pad) & 7) == 0 && (reinterpret_cast<uintptr_t>(image) & (IB_PX * sizeof(TIn) - 1)) == 0;
+#define OM_BAND_LAUNCH(NT)                                                                                              \
+    do {                                                                                                                \
+        if (aligned) band_colsum_kernel<TIn, NT, true><<<grid, NT, 0, st>>>(image, H, W, pad, nb, IB_ROWS, CP, maxv, colsum, flags);      \
+        else band_colsum_kernel<TIn, NT, false><<<grid, NT, 0, st>>>(image, H, W, pad, nb, IB_ROWS, CP, maxv, colsum, flags);             \
+        OM_AFTER_LAUNCH();                                                                                              \
+        if (aligned) integral_band_kernel<TIn, TOut, NT, true><<<grid, NT, 0, st>>>(image, H, W, pad, nb, IB_ROWS, IP, CP, colsum, I);    \
+        else integral_band_kernel<TIn, TOut, NT, false><<<grid, NT, 0, st>>>(image, H, W, pad, nb, IB_ROWS, IP, CP, colsum, I);           \
+        OM_AFTER_LAUNCH();                                                                                              \
+    } while (0)
+    if (CP <= IB_PX * 64) OM_BAND_LAUNCH(64);
+    else if (CP <= IB_PX * 96) OM_BAND_LAUNCH(96);
+    else if (CP <= IB_PX * 128) OM_BAND_LAUNCH(128);
+    else if (CP <= IB_PX * 256) OM_BAND_LAUNCH(256);
+    else if (CP <= IB_PX * 512) OM_BAND_LAUNCH(512);
+    else OM_BAND_LAUNCH(1024);
+#undef OM_BAND_LAUNCH
+    return OM_OK;
+}
+inline size_t band_colsum_bytes(int B, int H, int W, int pad) {
+    const int nb = (H + 2 * pad + 8 - 1) / 8;                   // sized for the smallest band height (8 rows)
+    return align_up((size_t)B * nb * band_colsum_pitch(W, pad) * sizeof(unsigned int));
 }
 
 // box mean of the reference's dense path at padded-integral centre (cy,cx) (already +MAXR):
@@ -1220,9 +1541,11 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* map, int B, in
 }
 
 struct DenseWs {
-    float* T;       // (B, H+14, W+14)
+    float* T;       // (B, H+14, W+14)   column pass of the two-pass build (float-valued images only)
     float* I;       // (B, H+15, ipitch)
     float* planes;  // (B, 8, H, W)   (dense map only)
+    unsigned int* flags;    // (B+1) banded build: image has a pixel that is not a small integer; [B] = any image
+    unsigned int* colsum;   // banded build: (B, bands, ipitch)
 };
 
 DenseWs carve_dense(void* ws, int B, int H, int W) {
@@ -1233,19 +1556,25 @@ DenseWs carve_dense(void* ws, int B, int H, int W) {
     d.I = (float*)p;
     p += align_up((size_t)B * (H + 2 * MAXR + 1) * ipitch(W, MAXR) * sizeof(float));
     d.planes = (float*)p;
+    p += align_up((size_t)B * (MAXR + 1) * H * W * sizeof(float));
+    d.flags = (unsigned int*)p;
+    p += align_up((size_t)(B + 1) * sizeof(unsigned int));
+    d.colsum = (unsigned int*)p;
     return d;
 }
 
 struct SparseWs {
     unsigned int* flags;   // (B+1) non-integer-pixel flag per image, [B] = any image flagged
-    unsigned int* T;       // (B, H+2pad, W+2pad)
+    unsigned int* T;       // (B, H+2pad, W+2pad)   column pass of the two-pass build (very wide images only)
     unsigned int* I;       // (B, H+2pad+1, ipitch)
+    unsigned int* colsum;  // banded build: (B, bands, ipitch)
 };
 
 // keypoint groups per CTA of the window kernels (10 groups per CTA, i.e. 20 windows per SM instead of 16, measured no faster)
 constexpr int KPG = 4;
 // window half size / integral padding per mode (see sparse_win_kernel)
-constexpr int HS_PLAIN = 23, PAD_PLAIN = 23, HS_ORI = 30, PAD_ORI = 32;
+// (1 + pad) % 4 == 0 so that a thread's four integral columns are four ALIGNED pixels of the image (banded build)
+constexpr int HS_PLAIN = 23, PAD_PLAIN = 23, HS_ORI = 30, PAD_ORI = 31;
 
 SparseWs carve_sparse(void* ws, int B, int H, int W, int pad) {
     SparseWs d;
@@ -1255,6 +1584,8 @@ SparseWs carve_sparse(void* ws, int B, int H, int W, int pad) {
     d.T = (unsigned int*)p;
     p += align_up((size_t)B * (H + 2 * pad) * (W + 2 * pad) * sizeof(unsigned int));
     d.I = (unsigned int*)p;
+    p += align_up((size_t)B * (H + 2 * pad + 1) * ipitch(W, pad) * sizeof(unsigned int));
+    d.colsum = (unsigned int*)p;
     return d;
 }
 
@@ -1264,8 +1595,23 @@ int check_table(const float* table, int P) {
     return OM_OK;
 }
 
-int build_integral(const float* image, int B, int H, int W, const DenseWs& d, cudaStream_t st) {
-    return build_prefix<false>(image, B, H, W, MAXR, d.T, d.I, nullptr, st);
+// float32 integral of the dense path.  Integer-valued pixels (every uint8 image; float images are checked): banded exact
+// build, RN(exact) == the reference's double-accumulated cumsums.  A float image with a non-integer (or huge) pixel raises
+// the batch flag and the two-pass double-accumulating build, launched behind and gated on that flag, redoes the batch.
+int build_integral(const void* image, int image_u8, int B, int H, int W, const DenseWs& d, cudaStream_t st) {
+    const double cells = (double)(H + 2 * MAXR) * (double)(W + 2 * MAXR);
+    const float maxv = (float)fmin(65535.0, floor(4294967295.0 / cells));     // every partial sum stays below 2^32
+    OM_CUDA(cudaMemsetAsync(d.flags, 0, (size_t)(B + 1) * sizeof(unsigned int), st));
+    int rc;
+    if (image_u8) rc = build_integral_banded<unsigned char, float>((const unsigned char*)image, B, H, W, MAXR, maxv, d.colsum, d.I, d.flags, st);
+    else rc = build_integral_banded<float, float>((const float*)image, B, H, W, MAXR, maxv, d.colsum, d.I, d.flags, st);
+    if (rc == OM_ERR_LIMIT) {                                 // too wide for one CTA per band
+        if (image_u8) return OM_ERR_LIMIT;
+        return build_prefix<false>((const float*)image, B, H, W, MAXR, d.T, d.I, nullptr, st);
+    }
+    OM_TRY(rc);
+    if (image_u8) return OM_OK;
+    return build_prefix<false>((const float*)image, B, H, W, MAXR, d.T, d.I, nullptr, st, d.flags + B);
 }
 
 }  // namespace
@@ -1275,10 +1621,10 @@ size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode) {
     const int pad = theta_mode == OM_THETA_NONE ? PAD_PLAIN : PAD_ORI;
     return align_up((size_t)(B + 1) * sizeof(unsigned int)) +
            align_up((size_t)B * (H + 2 * pad) * (W + 2 * pad) * sizeof(unsigned int)) +
-           align_up((size_t)B * (H + 2 * pad + 1) * ipitch(W, pad) * sizeof(unsigned int));
+           align_up((size_t)B * (H + 2 * pad + 1) * ipitch(W, pad) * sizeof(unsigned int)) + band_colsum_bytes(B, H, W, pad);
 }
 
-int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
+int sparse_bad_launch(const void* image, int image_u8, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
                       const float* orientation, const float* moment_kernels, int patch_size, float* desc,
                       void* ws, size_t ws_bytes, cudaStream_t st, int phase) {
@@ -1300,11 +1646,15 @@ int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts
     const SparseWs w = carve_sparse(ws, B, H, W, pad);
     if (phase != 2) {
         OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)(B + 1) * sizeof(unsigned int), st));
-        OM_TRY(build_prefix<true>(image, B, H, W, pad, w.T, w.I, w.flags, st));
+        int rc;
+        if (image_u8) rc = build_integral_banded<unsigned char, unsigned int>((const unsigned char*)image, B, H, W, pad, 65535.0f, w.colsum, w.I, w.flags, st);
+        else rc = build_integral_banded<float, unsigned int>((const float*)image, B, H, W, pad, 65535.0f, w.colsum, w.I, w.flags, st);
+        if (rc == OM_ERR_LIMIT && !image_u8) rc = build_prefix<true>((const float*)image, B, H, W, pad, w.T, w.I, w.flags, st);
+        OM_TRY(rc);
     }
     if (phase == 1) return OM_OK;
     SparseArgs a{};
-    a.image = image; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P;
+    a.image = image; a.image_u8 = image_u8; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P;
     a.mode = desc_mode; a.temperature = temperature; a.normalize = normalize;
     a.bilinear = sampling_mode == OM_SAMPLE_BILINEAR; a.theta_mode = theta_mode; a.orientation = orientation;
     a.moments = moment_kernels; a.patch_size = patch_size; a.desc = desc;
@@ -1325,10 +1675,11 @@ size_t dense_bad_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     return align_up((size_t)B * (H + 2 * MAXR) * (W + 2 * MAXR) * sizeof(float)) +
            align_up((size_t)B * (H + 2 * MAXR + 1) * ipitch(W, MAXR) * sizeof(float)) +
-           align_up((size_t)B * (MAXR + 1) * H * W * sizeof(float));
+           align_up((size_t)B * (MAXR + 1) * H * W * sizeof(float)) + align_up((size_t)(B + 1) * sizeof(unsigned int)) +
+           band_colsum_bytes(B, H, W, MAXR);
 }
 
-int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const float* kpts, int K,
+int dense_bad_at_kpts_launch(const void* image, int image_u8, int B, int H, int W, const float* kpts, int K,
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                              float* desc, void* ws, size_t ws_bytes, cudaStream_t st, int phase) {
     if (image == nullptr || kpts == nullptr || desc == nullptr) return OM_ERR_NULL;
@@ -1337,7 +1688,7 @@ int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const floa
     if (desc_mode < OM_DESC_RAW || desc_mode > OM_DESC_HARD) return OM_ERR_PARAM;
     if (ws == nullptr || ws_bytes < dense_bad_workspace_bytes(B, H, W)) return OM_ERR_WORKSPACE;
     const DenseWs d = carve_dense(ws, B, H, W);
-    if (phase != 2) OM_TRY(build_integral(image, B, H, W, d, st));
+    if (phase != 2) OM_TRY(build_integral(image, image_u8, B, H, W, d, st));
     if (phase == 1) return OM_OK;
     DenseKpArgs a{};
     a.I = d.I; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P; a.mode = desc_mode;
@@ -1350,6 +1701,7 @@ int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const floa
 using namespace om;
 
 extern "C" void om_debug_dense_window(int tma) { g_dense_window_tma = tma; }
+extern "C" void om_debug_band_rows(int rows) { g_band_rows = rows >= 8 && rows <= 256 ? rows / 2 * 2 : 32; }
 
 extern "C" int om_angle_map_f32(const float* image, int B, int H, int W, const float* moment_kernels, int patch_size,
                                 float* angle_map, void* stream) {
@@ -1372,7 +1724,7 @@ extern "C" int om_sparse_bad_f32(const float* image, int B, int H, int W, const 
                                  const float* moment_kernels, int patch_size, float* desc, void* ws, size_t ws_bytes,
                                  void* stream) {
     OM_ON_DEVICE_OF(image);
-    return sparse_bad_launch(image, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, sampling_mode,
+    return sparse_bad_launch(image, 0, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, sampling_mode,
                              theta_mode, orientation, moment_kernels, patch_size, desc, ws, ws_bytes,
                              (cudaStream_t)stream);
 }
@@ -1393,7 +1745,7 @@ extern "C" int om_dense_bad_f32(const float* image, int B, int H, int W, const f
     if (ws == nullptr || ws_bytes < dense_bad_workspace_bytes(B, H, W)) return OM_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const DenseWs d = carve_dense(ws, B, H, W);
-    OM_TRY(build_integral(image, B, H, W, d, st));
+    OM_TRY(build_integral(image, 0, B, H, W, d, st));
     const dim3 grid((W + 127) / 128, H, B);
     box_planes_kernel<<<grid, 128, 0, st>>>(d.I, H, W, d.planes);
     OM_AFTER_LAUNCH();
@@ -1406,7 +1758,7 @@ extern "C" int om_dense_bad_at_kpts_f32(const float* image, int B, int H, int W,
                                         const float* pair_table, int P, int desc_mode, float temperature,
                                         int normalize, float* desc, void* ws, size_t ws_bytes, void* stream) {
     OM_ON_DEVICE_OF(image);
-    return dense_bad_at_kpts_launch(image, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, desc, ws,
+    return dense_bad_at_kpts_launch(image, 0, B, H, W, kpts, K, pair_table, P, desc_mode, temperature, normalize, desc, ws,
                                     ws_bytes, (cudaStream_t)stream);
 }
 
@@ -1433,7 +1785,7 @@ extern "C" int om_debug_dense_stage(const float* image, int B, int H, int W, con
     if (ws == nullptr || ws_bytes < dense_bad_workspace_bytes(B, H, W)) return OM_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const DenseWs d = carve_dense(ws, B, H, W);
-    if (stage == 0) return build_integral(image, B, H, W, d, st);
+    if (stage == 0) return build_integral(image, 0, B, H, W, d, st);
     DenseKpArgs a{};
     a.I = d.I; a.B = B; a.H = H; a.W = W; a.kpts = kpts; a.K = K; a.table = pair_table; a.P = P; a.mode = desc_mode;
     a.temperature = temperature; a.normalize = normalize; a.desc = desc;

@@ -131,20 +131,21 @@ struct DetectCfg {
     int block_size, nms_radius, border_margin;
     float score_threshold;
     int K;
+    int image_u8;          // 1: the image pointer is uint8, 0: float32
 };
 
 size_t topk_workspace_bytes(int B, int H, int W, int K);
-int detect_launch(const float* image, const DetectCfg& c, float* score_map, float* kpts, float* kpt_scores,
+int detect_launch(const void* image, const DetectCfg& c, float* score_map, float* kpts, float* kpt_scores,
                   void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode);
-int sparse_bad_launch(const float* image, int B, int H, int W, const float* kpts, int K, const float* pair_table,
+int sparse_bad_launch(const void* image, int image_u8, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,
                       const float* orientation, const float* moment_kernels, int patch_size, float* desc,
                       void* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);   // phase 1: integral only, 2: descriptors only
 
 size_t dense_bad_workspace_bytes(int B, int H, int W);
-int dense_bad_at_kpts_launch(const float* image, int B, int H, int W, const float* kpts, int K,
+int dense_bad_at_kpts_launch(const void* image, int image_u8, int B, int H, int W, const float* kpts, int K,
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                              float* desc, void* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);
 

@@ -46,8 +46,8 @@ class HostBatchMatcher:
     nothing waits -- call :meth:`synchronize` (or wait on the returned tensors' producer streams)
     before reading results; a result set is overwritten ``depth`` calls later.
 
-    uint8 host images are accepted (4x less PCIe traffic): they are widened to float32 on the device,
-    which is exact, so results are identical to passing the same values as float32.
+    uint8 host images are accepted (4x less PCIe traffic): the score and integral-image kernels read the bytes
+    natively (no widened copy exists), results are identical to passing the same values as float32.
 
     Any module whose forward(image1, image2) returns a tuple of tensors with the pair batch as their first dimension
     works: the three-output matchers, ``MatchExtractionWrapper`` (matches only: no (K+1)^2 matrix crosses PCIe) or the
@@ -107,9 +107,7 @@ class HostBatchMatcher:
             with torch.cuda.stream(s):
                 d1 = image1[lo:hi].to(self.device, non_blocking=True)
                 d2 = image2[lo:hi].to(self.device, non_blocking=True)
-                if d1.dtype != torch.float32:
-                    d1, d2 = d1.float(), d2.float()
-                outs = self.model(d1, d2)
+                outs = self.model(d1, d2)          # uint8 stays uint8: the fused kernels read the bytes natively
                 outs = (outs,) if torch.is_tensor(outs) else tuple(outs)
                 if host is None:
                     host = self._outputs(slot, B, outs, hi - lo)

@@ -1020,3 +1020,66 @@ def test_same_pairs_alone_or_inside_a_larger_batch_are_byte_identical():
             part = model(*_cuda(i1[lo:hi], i2[lo:hi]))
             for w, x in zip(whole, part):
                 assert sha(w[lo:hi]) == sha(x)
+
+
+# ------------------------------------------------------------------------------------------
+# uint8 ingest and the banded integral-image build
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flavour", ["dense", "sparse", "angle", "export", "block7"])
+@pytest.mark.parametrize("shape", [(3, 150, 210), (2, 240, 320), (1, 37, 52)])
+def test_uint8_images_are_read_natively_with_identical_results(flavour, shape):
+    """uint8 CUDA images go through the fused matcher without a widened copy (score and integral kernels read bytes);
+    keypoints, descriptors and P must be bit-identical to the same pixels passed as float32.  Widths that are / are not
+    multiples of 4 (vector / scalar loads), an image smaller than one band, and the routings without a uint8 score kernel
+    (NMS radius 5, block size 7: exact widening first)."""
+    i1, i2 = O.texture_images(*shape, seed=91)
+    K = 64 if shape[1] < 100 else 200
+    if flavour == "export":
+        model = om.ShiTomasiSparseBADSinkhornMatcher(K, num_pairs=512, binarize=True, soft_binarize=False, epsilon=0.05, nms_radius=5)
+    elif flavour == "block7":
+        model = om.ShiTomasiSparseBADSinkhornMatcher(K, block_size=7, nms_radius=2)
+    else:
+        model = dict(sparse=om.ShiTomasiSparseBADSinkhornMatcher, dense=om.ShiTomasiBADSinkhornMatcher,
+                     angle=om.ShiTomasiAngleSparseBADSinkhornMatcher)[flavour](K)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        want = model.match(i1.to(DEV), i2.to(DEV))
+        got = model.match(i1.to(torch.uint8).to(DEV), i2.to(torch.uint8).to(DEV))
+    for w, x in zip(want, got):
+        assert torch.equal(w, x)
+    dk, ds = _ops.detect(i1.to(torch.uint8).to(DEV), K, 3, 3, 0.0, 4)
+    rk, rs = O.detect(i1, K, 3, 3, 0.0, 4)
+    assert PR.keypoint_mismatches(dk, rk, rs) == 0 and PR.scores_close(ds, rs)
+
+
+def test_dense_path_float_valued_and_mixed_batch():
+    """Dense BAD on images with non-integer pixels: the banded exact integral flags the batch and the double-accumulating
+    two-pass build (gated on that flag) takes over -- the dense map must stay bit-equal to the reference arithmetic, for
+    the flagged image and for the integer-valued image that shares its batch."""
+    img, _ = O.texture_images(2, 48, 72, seed=43)
+    img = img.clone()
+    img[0] = img[0] * 0.731 + 0.123
+    ref = O.dense_bad(img)
+    got = om.BADDescriptor().to(DEV)(img.to(DEV)).cpu()
+    assert int((got != ref).sum()) == 0, float((got - ref).abs().max())
+    k, _ = O.detect(img.round(), 40, 3, 3, 0.0, 0)
+    rd = torch.cat([O.dense_descriptors_at_keypoints(O.dense_bad(img[b:b + 1]), k[b:b + 1]) for b in range(2)])
+    gd = _ops.dense_bad_at_keypoints(img.to(DEV), k.to(DEV), om.BADDescriptor()._pair_table.to(DEV), 0, 10.0, True)
+    assert PR.desc_metrics(gd, rd)["rows_within"] == 1.0
+
+
+@pytest.mark.parametrize("shape", [(1, 20, 33), (2, 64, 100), (1, 131, 517), (1, 600, 1100)])
+def test_banded_integral_shapes(shape):
+    """The banded build over ragged sizes: fewer rows than a band, widths that need every CTA width (128 .. 512
+    threads), through both consumers (exact uint32 windows of SparseBAD, float32 integral of the dense path)."""
+    B, H, W = shape
+    img = O.noise_images(B, H, W, seed=H + W)
+    g = torch.Generator().manual_seed(H)
+    k = torch.stack([torch.randint(0, H, (B, 60), generator=g), torch.randint(0, W, (B, 60), generator=g)], -1).float()
+    ref = O.sparse_bad(img, k, None)
+    got = om.SparseBAD().to(DEV)(img.to(DEV), k.to(DEV))
+    assert PR.desc_metrics(got, ref)["rows_within"] == 1.0
+    if H * W <= 131 * 517:
+        rd = torch.cat([O.dense_descriptors_at_keypoints(O.dense_bad(img[b:b + 1]), k[b:b + 1]) for b in range(B)])
+        gd = _ops.dense_bad_at_keypoints(img.to(DEV), k.to(DEV), om.BADDescriptor()._pair_table.to(DEV), 0, 10.0, True)
+        assert PR.desc_metrics(gd, rd)["rows_within"] == 1.0
