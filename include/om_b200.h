@@ -161,6 +161,39 @@ int om_sinkhorn_f32(const float* desc1, const float* desc2, int B, int N, int M,
                     int iterations, float epsilon, float unused_score, int distance_l1,
                     float* P, void* ws, size_t ws_bytes, void* stream);
 
+/* Everything the matching stage can hand back.  When the tcgen05 cluster kernel applies (L2 cost, N, M <= 512, descriptor
+ * length a multiple of 32, exp(-unused/eps) not near underflow) the requested pieces are computed in that kernel's epilogue
+ * from the probabilities it holds in registers, and `probs` may be NULL: the (N+1)(M+1) matrix then never leaves the chip
+ * (what 4 of the reference's 8 exported models need).  Otherwise P is stored (in the workspace if probs is NULL)
+ * and the separate kernels below run on it; results are the same.
+ *   scores0 / scores1   SinkhornMatcherWithScores, matching/sinkhorn.py:211-259 (NULL: not wanted)
+ *   filters             SinkhornMatcherWithFilters, matching/sinkhorn.py:262-465: ratio_threshold <= 0 / dustbin_margin < 0
+ *                       disable a test; rejected rows of probs are rewritten (core 0, dustbin 1); filter_valid (B,N) bytes
+ *   matches             MutualNearestNeighborMatcher, matching/match_extraction.py:46-184, on the (filtered) matrix:
+ *                       matched_kpts1/2 (B,max_matches,2), match_scores (B,max_matches), match_valid (B,max_matches) bytes */
+typedef struct om_sinkhorn_outputs {
+    float* probs;
+    float* scores0;
+    float* scores1;
+    int filters;
+    float ratio_threshold, dustbin_margin;
+    unsigned char* filter_valid;
+    int matches;
+    const float* kpts1;
+    const float* kpts2;
+    int max_matches;
+    float match_threshold;
+    float* matched_kpts1;
+    float* matched_kpts2;
+    float* match_scores;
+    unsigned char* match_valid;
+} om_sinkhorn_outputs;
+
+size_t om_sinkhorn_ex_workspace_bytes(int B, int N, int M, int D);
+int om_sinkhorn_ex_f32(const float* desc1, const float* desc2, int B, int N, int M, int D,
+                       int iterations, float epsilon, float unused_score, int distance_l1,
+                       const om_sinkhorn_outputs* out, void* ws, size_t ws_bytes, void* stream);
+
 /* SinkhornMatcherWithFilters epilogue, matching/sinkhorn.py:311-465, IN PLACE on probs (B,N+1,M+1): rows that fail
  * the best/second-best ratio test (ratio_threshold <= 0 disables it) or the best-minus-dustbin margin test
  * (dustbin_margin < 0 disables it) get their core zeroed and their dustbin entry set to 1; valid (B,N) bytes 0/1. */
@@ -238,6 +271,15 @@ int om_match_pairs(const om_match_params* p, const void* image1, const void* ima
                    float* kpts1, float* kpts2, float* probs /* B,K+1,K+1 */,
                    float* desc1, float* desc2,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* The fused matcher with the matching stage's optional outputs (see om_sinkhorn_outputs; out->kpts1/2 are ignored: the
+ * matcher's own keypoints are used).  out->probs may be NULL when only matches / scores are wanted.  Workspace:
+ * om_match_ex_workspace_bytes. */
+size_t om_match_ex_workspace_bytes(const om_match_params* p);
+int om_match_pairs_ex(const om_match_params* p, const void* image1, const void* image2,
+                      const float* pair_table, const float* moment_kernels,
+                      float* kpts1, float* kpts2, float* desc1, float* desc2,
+                      const om_sinkhorn_outputs* out, void* ws, size_t ws_bytes, void* stream);
 
 /* om_detect_f32 on uint8 images (block 3 / 5 with NMS radius 3 read the bytes natively, other routings widen first). */
 int om_detect_u8(const unsigned char* image, int B, int H, int W, int block_size, int nms_radius,

@@ -27,6 +27,16 @@ class MatchParams(Structure):
     ]
 
 
+class SinkhornOutputs(Structure):
+    """struct om_sinkhorn_outputs (include/om_b200.h)."""
+    _fields_ = [
+        ("probs", c_void_p), ("scores0", c_void_p), ("scores1", c_void_p),
+        ("filters", c_int), ("ratio_threshold", c_float), ("dustbin_margin", c_float), ("filter_valid", c_void_p),
+        ("matches", c_int), ("kpts1", c_void_p), ("kpts2", c_void_p), ("max_matches", c_int), ("match_threshold", c_float),
+        ("matched_kpts1", c_void_p), ("matched_kpts2", c_void_p), ("match_scores", c_void_p), ("match_valid", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/om_b200.h declares
 SIGNATURES = {
     "om_version": (c_int, []),
@@ -70,6 +80,12 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "om_detect_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_size_t, c_void_p]),
+    "om_sinkhorn_ex_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "om_sinkhorn_ex_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                                   POINTER(SinkhornOutputs), c_void_p, c_size_t, c_void_p]),
+    "om_match_ex_workspace_bytes": (c_size_t, [POINTER(MatchParams)]),
+    "om_match_pairs_ex": (c_int, [POINTER(MatchParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, POINTER(SinkhornOutputs), c_void_p, c_size_t, c_void_p]),
     "om_debug_detect_stage": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "om_debug_dense_stage": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float,

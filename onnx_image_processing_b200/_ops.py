@@ -281,6 +281,74 @@ def _(desc1, desc2, iterations, epsilon, unused_score, distance_l1):
     return desc1.new_empty((desc1.shape[0], desc1.shape[1] + 1, desc2.shape[1] + 1), dtype=torch.float32)
 
 
+def _epilogue_outputs(dev, B: int, N: int, M: int, want_probs: bool, want_scores: bool, use_filters: bool, ratio: float,
+                      margin: float, max_matches: int, match_threshold: float, kpts1=None, kpts2=None):
+    """(struct om_sinkhorn_outputs, tensors): probs (B,N+1,M+1), scores0 (B,N), scores1 (B,M), filter_valid (B,N) uint8,
+    matched_kpts1/2 (B,max_matches,2), match_scores (B,max_matches), match_valid (B,max_matches) uint8 -- an unrequested
+    piece is an empty tensor and a NULL pointer."""
+    f = dict(dtype=torch.float32, device=dev)
+    f8 = dict(dtype=torch.uint8, device=dev)
+    mm = int(max_matches)
+    t = dict(                                      # (every output its own tensor: custom ops may not return aliases)
+        probs=torch.empty((B, N + 1, M + 1) if want_probs else (0,), **f),
+        scores0=torch.empty((B, N) if want_scores else (0,), **f),
+        scores1=torch.empty((B, M) if want_scores else (0,), **f),
+        filter_valid=torch.empty((B, N) if use_filters else (0,), **f8),
+        mk1=torch.empty((B, mm, 2) if mm > 0 else (0,), **f),
+        mk2=torch.empty((B, mm, 2) if mm > 0 else (0,), **f),
+        mscores=torch.empty((B, mm) if mm > 0 else (0,), **f),
+        mvalid=torch.empty((B, mm) if mm > 0 else (0,), **f8),
+    )
+    q = lambda x: x.data_ptr() if x.numel() else None  # noqa: E731
+    out = nat.SinkhornOutputs(q(t["probs"]), q(t["scores0"]), q(t["scores1"]), int(use_filters), float(ratio), float(margin),
+                              q(t["filter_valid"]), int(mm > 0), kpts1.data_ptr() if kpts1 is not None else None,
+                              kpts2.data_ptr() if kpts2 is not None else None, mm, float(match_threshold), q(t["mk1"]), q(t["mk2"]),
+                              q(t["mscores"]), q(t["mvalid"]))
+    return out, t
+
+
+def _fake_epilogue(like, B, N, M, want_probs, want_scores, use_filters, max_matches):
+    f = dict(dtype=torch.float32)
+    mm = int(max_matches)
+    return (like.new_empty((B, N + 1, M + 1) if want_probs else (0,), **f), like.new_empty((B, N) if want_scores else (0,), **f),
+            like.new_empty((B, M) if want_scores else (0,), **f), like.new_empty((B, N) if use_filters else (0,), dtype=torch.bool),
+            like.new_empty((B, mm, 2) if mm else (0,), **f), like.new_empty((B, mm, 2) if mm else (0,), **f),
+            like.new_empty((B, mm) if mm else (0,), **f), like.new_empty((B, mm) if mm else (0,), dtype=torch.bool))
+
+
+@torch.library.custom_op("b200match::sinkhorn_ex", mutates_args=(), device_types="cuda")
+def sinkhorn_ex(desc1: torch.Tensor, desc2: torch.Tensor, iterations: int, epsilon: float, unused_score: float,
+                distance_l1: bool, want_probs: bool, want_scores: bool, use_filters: bool, ratio_threshold: float,
+                dustbin_margin: float, keypoints1: Optional[torch.Tensor], keypoints2: Optional[torch.Tensor], max_matches: int,
+                match_threshold: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                                                 torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Sinkhorn with the matching stage's optional outputs in ONE call (om_sinkhorn_ex_f32): (probs, scores0, scores1,
+    filter_valid, matched_kpts1, matched_kpts2, match_scores, match_valid); unrequested pieces are empty tensors.  With the
+    tcgen05 cluster kernel everything is computed in its epilogue and probs may be skipped altogether."""
+    d1 = _f32(desc1, "desc1")
+    d2 = _f32(desc2, "desc2")
+    B, N, D = d1.shape
+    M = int(d2.shape[1])
+    if d2.shape[0] != B or d2.shape[2] != D:
+        raise RuntimeError(f"descriptor shapes do not match: {tuple(d1.shape)} vs {tuple(d2.shape)}")
+    k1 = _f32(keypoints1, "keypoints1") if max_matches > 0 else None
+    k2 = _f32(keypoints2, "keypoints2") if max_matches > 0 else None
+    lib, st = _begin(d1)
+    out, t = _epilogue_outputs(d1.device, B, N, M, want_probs, want_scores, use_filters, ratio_threshold, dustbin_margin,
+                               max_matches, match_threshold, k1, k2)
+    ws = _ws(lib.om_sinkhorn_ex_workspace_bytes(B, N, M, D), d1)
+    nat.check(lib.om_sinkhorn_ex_f32(_p(d1), _p(d2), B, N, M, D, iterations, float(epsilon), float(unused_score),
+                                     int(distance_l1), ctypes.byref(out), _p(ws), ws.numel(), st), "om_sinkhorn_ex_f32")
+    return (t["probs"], t["scores0"], t["scores1"], t["filter_valid"].to(torch.bool), t["mk1"], t["mk2"], t["mscores"],
+            t["mvalid"].to(torch.bool))
+
+
+@sinkhorn_ex.register_fake
+def _(desc1, desc2, iterations, epsilon, unused_score, distance_l1, want_probs, want_scores, use_filters, ratio_threshold,
+      dustbin_margin, keypoints1, keypoints2, max_matches, match_threshold):
+    return _fake_epilogue(desc1, desc1.shape[0], desc1.shape[1], desc2.shape[1], want_probs, want_scores, use_filters, max_matches)
+
+
 @torch.library.custom_op("b200match::filter_rows", mutates_args=(), device_types="cuda")
 def filter_rows(probs: torch.Tensor, ratio_threshold: float, dustbin_margin: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """(filtered copy of P, valid mask): the outlier filters of SinkhornMatcherWithFilters."""
@@ -439,6 +507,59 @@ def match_pairs(image1: torch.Tensor, image2: torch.Tensor, pair_table: torch.Te
     nat.check(lib.om_match_pairs(ctypes.byref(prm), _p(i1), _p(i2), _p(tb), _p(mk), _p(k1), _p(k2), _p(probs),
                                  _p(d1), _p(d2), _p(ws), ws.numel(), st), "om_match_pairs")
     return k1, k2, probs, d1, d2
+
+
+@torch.library.custom_op("b200match::match_pairs_ex", mutates_args=(), device_types="cuda")
+def match_pairs_ex(image1: torch.Tensor, image2: torch.Tensor, pair_table: torch.Tensor,
+                   moment_kernels: Optional[torch.Tensor], flavour: int, max_keypoints: int, block_size: int,
+                   nms_radius: int, border_margin: int, score_threshold: float, mode: int, temperature: float,
+                   normalize: bool, sampling: int, iterations: int, epsilon: float, unused_score: float,
+                   distance_l1: bool, want_probs: bool, want_scores: bool, use_filters: bool, ratio_threshold: float,
+                   dustbin_margin: float, max_matches: int, match_threshold: float
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                              torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Whole matcher forward with the matching stage's optional outputs (om_match_pairs_ex): (kpts1, kpts2, probs, scores0,
+    scores1, filter_valid, matched_kpts1, matched_kpts2, match_scores, match_valid).  With want_probs=False and K <= 512 the
+    (K+1)^2 matrix is never written: matches come out of the Sinkhorn kernel's epilogue."""
+    i1, B, H, W, u8 = _images_native(image1, "image1")
+    i2, B2, H2, W2, u8b = _images_native(image2, "image2")
+    if (B, H, W) != (B2, H2, W2):
+        raise RuntimeError("image1 and image2 must have the same shape")
+    if u8 != u8b:
+        i1, i2, u8 = i1.float(), i2.float(), 0
+    K = max_keypoints
+    if K > H * W:
+        raise RuntimeError("selected index k out of range")
+    tb = _f32(pair_table, "pair_table")
+    P = int(tb.shape[0])
+    mk = _f32(moment_kernels, "moment_kernels") if moment_kernels is not None else None
+    ps = int(mk.shape[-1]) if mk is not None else 0
+    lib, st = _begin(i1)
+    prm = make_match_params(flavour, B, H, W, K, block_size, nms_radius, border_margin, score_threshold, P, mode,
+                            temperature, normalize, sampling, ps, iterations, epsilon, unused_score, distance_l1, u8)
+    dev = i1.device
+    k1 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    k2 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    out, t = _epilogue_outputs(dev, B, K, K, want_probs, want_scores, use_filters, ratio_threshold, dustbin_margin, max_matches,
+                               match_threshold)
+    nbytes = lib.om_match_ex_workspace_bytes(ctypes.byref(prm))
+    if nbytes == 0:
+        raise RuntimeError("om_match_ex_workspace_bytes rejected the parameters")
+    ws = _ws(nbytes, i1)
+    nat.check(lib.om_match_pairs_ex(ctypes.byref(prm), _p(i1), _p(i2), _p(tb), _p(mk), _p(k1), _p(k2), _p(None), _p(None),
+                                    ctypes.byref(out), _p(ws), ws.numel(), st), "om_match_pairs_ex")
+    return (k1, k2, t["probs"], t["scores0"], t["scores1"], t["filter_valid"].to(torch.bool), t["mk1"], t["mk2"], t["mscores"],
+            t["mvalid"].to(torch.bool))
+
+
+@match_pairs_ex.register_fake
+def _(image1, image2, pair_table, moment_kernels, flavour, max_keypoints, block_size, nms_radius, border_margin,
+      score_threshold, mode, temperature, normalize, sampling, iterations, epsilon, unused_score, distance_l1, want_probs,
+      want_scores, use_filters, ratio_threshold, dustbin_margin, max_matches, match_threshold):
+    B, K = image1.shape[0], max_keypoints
+    f = dict(dtype=torch.float32)
+    return (image1.new_empty((B, K, 2), **f), image1.new_empty((B, K, 2), **f)) + \
+        _fake_epilogue(image1, B, K, K, want_probs, want_scores, use_filters, max_matches)
 
 
 @match_pairs.register_fake

@@ -160,7 +160,7 @@ int check_params(const om_match_params* p) {
     return OM_OK;
 }
 
-MatchWs plan(const om_match_params* p, void* base) {
+MatchWs plan(const om_match_params* p, void* base, bool ex = false) {
     MatchWs w{};
     char* c = (char*)base;
     size_t off = 0;
@@ -176,7 +176,7 @@ MatchWs plan(const om_match_params* p, void* base) {
                                                      p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE);
     w.dense[0] = c + off; off += align_up(w.dense_bytes);
     w.dense[1] = c + off; off += align_up(w.dense_bytes);
-    w.sink_bytes = sinkhorn_workspace_bytes(p->B, p->K, p->K, p->P);
+    w.sink_bytes = ex ? sinkhorn_ex_workspace_bytes(p->B, p->K, p->K, p->P) : sinkhorn_workspace_bytes(p->B, p->K, p->K, p->P);
     w.sink = c + off; off += align_up(w.sink_bytes);
     w.total = off;
     return w;
@@ -209,17 +209,48 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
     return om_match_pairs(p, image1, image2, pair_table, moment_kernels, kpts1, kpts2, probs, desc1, desc2, ws, ws_bytes, stream);
 }
 
+namespace {
+int match_pairs_impl(const om_match_params* p, const void* image1, const void* image2, const float* pair_table,
+                     const float* moment_kernels, float* kpts1, float* kpts2, float* probs, float* desc1, float* desc2,
+                     const SinkhornEpilogue* epi, void* ws, size_t ws_bytes, void* stream);
+}
+
 extern "C" int om_match_pairs(const om_match_params* p, const void* image1, const void* image2,
                               const float* pair_table, const float* moment_kernels, float* kpts1, float* kpts2,
                               float* probs, float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream) {
+    if (probs == nullptr) return OM_ERR_NULL;
+    return match_pairs_impl(p, image1, image2, pair_table, moment_kernels, kpts1, kpts2, probs, desc1, desc2, nullptr, ws, ws_bytes,
+                            stream);
+}
+
+extern "C" size_t om_match_ex_workspace_bytes(const om_match_params* p) {
+    if (check_params(p) != OM_OK) return 0;
+    return plan(p, nullptr, true).total;
+}
+
+extern "C" int om_match_pairs_ex(const om_match_params* p, const void* image1, const void* image2, const float* pair_table,
+                                 const float* moment_kernels, float* kpts1, float* kpts2, float* desc1, float* desc2,
+                                 const om_sinkhorn_outputs* out, void* ws, size_t ws_bytes, void* stream) {
+    if (out == nullptr) return OM_ERR_NULL;
+    SinkhornEpilogue e = epilogue_from_outputs(out);
+    e.kpts1 = kpts1;                                  // the matcher's own keypoints
+    e.kpts2 = kpts2;
+    if (!e.any() && out->probs == nullptr) return OM_ERR_NULL;
+    return match_pairs_impl(p, image1, image2, pair_table, moment_kernels, kpts1, kpts2, out->probs, desc1, desc2, &e, ws, ws_bytes,
+                            stream);
+}
+
+namespace {
+int match_pairs_impl(const om_match_params* p, const void* image1, const void* image2, const float* pair_table,
+                     const float* moment_kernels, float* kpts1, float* kpts2, float* probs, float* desc1, float* desc2,
+                     const SinkhornEpilogue* epi, void* ws, size_t ws_bytes, void* stream) {
     OM_ON_DEVICE_OF(image1);
     OM_TRY(check_params(p));
-    if (image1 == nullptr || image2 == nullptr || pair_table == nullptr || kpts1 == nullptr || kpts2 == nullptr ||
-        probs == nullptr)
-        return OM_ERR_NULL;
+    if (image1 == nullptr || image2 == nullptr || pair_table == nullptr || kpts1 == nullptr || kpts2 == nullptr) return OM_ERR_NULL;
     if (p->flavour == OM_MATCH_ANGLE && moment_kernels == nullptr) return OM_ERR_NULL;
-    if (ws == nullptr || ws_bytes < plan(p, nullptr).total) return OM_ERR_WORKSPACE;
-    const MatchWs w = plan(p, ws);
+    const bool ex = epi != nullptr;
+    if (ws == nullptr || ws_bytes < plan(p, nullptr, ex).total) return OM_ERR_WORKSPACE;
+    const MatchWs w = plan(p, ws, ex);
     cudaStream_t st = (cudaStream_t)stream;
     float* d1 = desc1 ? desc1 : w.desc1;
     float* d2 = desc2 ? desc2 : w.desc2;
@@ -284,6 +315,10 @@ extern "C" int om_match_pairs(const om_match_params* p, const void* image1, cons
         if (e2 != cudaSuccess && rc == OM_OK) rc = OM_ERR_CUDA_BASE + (int)e2;
     }
     if (rc != OM_OK) return rc;
+    if (ex)
+        return sinkhorn_ex_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
+                                  probs, *epi, w.sink, w.sink_bytes, st);
     return sinkhorn_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
                            probs, w.sink, w.sink_bytes, st);                     // needs both descriptor sets
 }
+}  // namespace

@@ -149,10 +149,49 @@ int dense_bad_at_kpts_launch(const void* image, int image_u8, int B, int H, int 
                              const float* pair_table, int P, int desc_mode, float temperature, int normalize,
                              float* desc, void* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);
 
+// What the Sinkhorn stage can produce besides (or instead of) the probability matrix: fused into the tcgen05 cluster kernel's
+// epilogue when that kernel runs in its scaling form, separate kernels on a stored P otherwise.
+struct SinkhornEpilogue {
+    float* scores0 = nullptr;             // (B,N) best core probability per row        SinkhornMatcherWithScores, sinkhorn.py:251-257
+    float* scores1 = nullptr;             // (B,M) best core probability per column
+    int filters = 0;                      // SinkhornMatcherWithFilters, sinkhorn.py:311-465
+    float ratio_threshold = -1.0f, dustbin_margin = -1.0f;
+    unsigned char* filter_valid = nullptr;   // (B,N)
+    int matches = 0;                      // MutualNearestNeighborMatcher, match_extraction.py:46-184
+    const float* kpts1 = nullptr;
+    const float* kpts2 = nullptr;
+    int max_matches = 0;
+    float match_threshold = 0.0f;
+    float* mk1 = nullptr;                 // (B,max_matches,2)
+    float* mk2 = nullptr;
+    float* mscores = nullptr;             // (B,max_matches)
+    unsigned char* mvalid = nullptr;      // (B,max_matches)
+    bool any() const { return scores0 != nullptr || scores1 != nullptr || filters != 0 || matches != 0; }
+};
+
 extern int g_tc_allow_scaling, g_tc_allow_f16;   // sinkhorn_tc.cu; test hooks
 // tcgen05 / TMEM cluster kernel (sinkhorn_tc.cu); limits: L2 cost, N <= 512, M <= 512, D % 16 == 0
 int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                         float unused, float* P, cudaStream_t st);
+// the same with the fused epilogue; P may be null.  Returns OM_ERR_PARAM when this configuration cannot take the fused form
+// (log-domain loop needed, descriptor length not a multiple of 32): the caller then stores P and runs the separate kernels.
+int sinkhorn_cluster_tc_epi(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
+                            float unused, float* P, const SinkhornEpilogue& e, cudaStream_t st);
+bool sinkhorn_epilogue_can_fuse(int N, int M, int D, float eps, float unused, int distance_l1);
+size_t sinkhorn_ex_workspace_bytes(int B, int N, int M, int D);
+// Sinkhorn + optional outputs; P may be null when the epilogue is fused (otherwise it is kept in the workspace)
+int sinkhorn_ex_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
+                       float unused_score, int distance_l1, float* P, const SinkhornEpilogue& e, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+SinkhornEpilogue epilogue_from_outputs(const om_sinkhorn_outputs* o);
+// separate-kernel forms of the epilogue pieces (matches.cu)
+int mutual_matches_launch(const float* probs, const float* kpts1, const float* kpts2, int B, int N, int M, int max_matches,
+                          float threshold, float* mk1, float* mk2, float* scores, unsigned char* valid, void* ws, size_t ws_bytes,
+                          cudaStream_t st);
+size_t mutual_matches_workspace_bytes(int B, int N, int M);
+int filter_rows_launch(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin, unsigned char* valid,
+                       cudaStream_t st);
+int sinkhorn_scores_launch(const float* probs, int B, int N, int M, float* scores0, float* scores1, cudaStream_t st);
 
 size_t sinkhorn_workspace_bytes(int B, int N, int M, int D);
 // cost matrix of the generic Sinkhorn path on tcgen05 (sinkhorn_tc.cu); D % 32 == 0; *ovf != 0: does nothing

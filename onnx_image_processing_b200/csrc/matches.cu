@@ -174,51 +174,45 @@ __global__ void __launch_bounds__(256) col_max_kernel(const float* P, int N, int
 
 }  // namespace
 
-}  // namespace om
-
-using namespace om;
-
-extern "C" int om_sinkhorn_filter_rows_f32(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin,
-                                           unsigned char* valid, void* stream) {
-    OM_ON_DEVICE_OF(probs);
-    if (probs == nullptr || valid == nullptr) return OM_ERR_NULL;
-    if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
-    if (B > 65535) return OM_ERR_LIMIT;
-    filter_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, (cudaStream_t)stream>>>(probs, N, M, ratio_threshold,
-                                                                                               dustbin_margin, valid);
-    OM_AFTER_LAUNCH();
-    return OM_OK;
-}
-
-extern "C" int om_sinkhorn_scores_f32(const float* probs, int B, int N, int M, float* scores0, float* scores1, void* stream) {
-    OM_ON_DEVICE_OF(probs);
-    if (probs == nullptr || scores0 == nullptr || scores1 == nullptr) return OM_ERR_NULL;
-    if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
-    if (B > 65535) return OM_ERR_LIMIT;
-    cudaStream_t st = (cudaStream_t)stream;
-    match_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, st>>>(probs, N, M, scores0, nullptr);
-    OM_AFTER_LAUNCH();
-    col_max_kernel<<<dim3((M + 255) / 256, B), 256, 0, st>>>(probs, N, M, scores1);
-    OM_AFTER_LAUNCH();
-    return OM_OK;
-}
-
-extern "C" size_t om_mutual_matches_workspace_bytes(int B, int N, int M) {
+size_t mutual_matches_workspace_bytes(int B, int N, int M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;
     return align_up((size_t)B * N * sizeof(float)) + align_up((size_t)B * N * sizeof(int)) + align_up((size_t)B * M * sizeof(int));
 }
 
-extern "C" int om_mutual_matches_f32(const float* probs, const float* kpts1, const float* kpts2, int B, int N, int M,
-                                     int max_matches, float threshold, float* matched_kpts1, float* matched_kpts2,
-                                     float* scores, unsigned char* valid, void* ws, size_t ws_bytes, void* stream) {
-    OM_ON_DEVICE_OF(probs);
+int filter_rows_launch(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin, unsigned char* valid,
+                       cudaStream_t st) {
+    if (probs == nullptr || valid == nullptr) return OM_ERR_NULL;
+    if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
+    if (B > 65535) return OM_ERR_LIMIT;
+    filter_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, st>>>(probs, N, M, ratio_threshold, dustbin_margin, valid);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+int sinkhorn_scores_launch(const float* probs, int B, int N, int M, float* scores0, float* scores1, cudaStream_t st) {
+    if (probs == nullptr) return OM_ERR_NULL;
+    if (B <= 0 || N <= 0 || M <= 0) return OM_ERR_SHAPE;
+    if (B > 65535) return OM_ERR_LIMIT;
+    if (scores0 != nullptr) {
+        match_rows_kernel<<<dim3((N + MT / 32 - 1) / (MT / 32), B), MT, 0, st>>>(probs, N, M, scores0, nullptr);
+        OM_AFTER_LAUNCH();
+    }
+    if (scores1 != nullptr) {
+        col_max_kernel<<<dim3((M + 255) / 256, B), 256, 0, st>>>(probs, N, M, scores1);
+        OM_AFTER_LAUNCH();
+    }
+    return OM_OK;
+}
+
+int mutual_matches_launch(const float* probs, const float* kpts1, const float* kpts2, int B, int N, int M, int max_matches,
+                          float threshold, float* matched_kpts1, float* matched_kpts2, float* scores, unsigned char* valid,
+                          void* ws, size_t ws_bytes, cudaStream_t st) {
     if (probs == nullptr || kpts1 == nullptr || kpts2 == nullptr || matched_kpts1 == nullptr || matched_kpts2 == nullptr ||
         scores == nullptr || valid == nullptr)
         return OM_ERR_NULL;
     if (B <= 0 || N <= 0 || M <= 0 || max_matches <= 0) return OM_ERR_SHAPE;
     if (B > 65535 || N > 16384) return OM_ERR_LIMIT;
-    if (ws == nullptr || ws_bytes < om_mutual_matches_workspace_bytes(B, N, M)) return OM_ERR_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
+    if (ws == nullptr || ws_bytes < mutual_matches_workspace_bytes(B, N, M)) return OM_ERR_WORKSPACE;
     char* p = (char*)ws;
     float* row_max = (float*)p;
     p += align_up((size_t)B * N * sizeof(float));
@@ -236,4 +230,30 @@ extern "C" int om_mutual_matches_f32(const float* probs, const float* kpts1, con
                                              matched_kpts1, matched_kpts2, scores, valid);
     OM_AFTER_LAUNCH();
     return OM_OK;
+}
+
+}  // namespace om
+
+using namespace om;
+
+extern "C" int om_sinkhorn_filter_rows_f32(float* probs, int B, int N, int M, float ratio_threshold, float dustbin_margin,
+                                           unsigned char* valid, void* stream) {
+    OM_ON_DEVICE_OF(probs);
+    return filter_rows_launch(probs, B, N, M, ratio_threshold, dustbin_margin, valid, (cudaStream_t)stream);
+}
+
+extern "C" int om_sinkhorn_scores_f32(const float* probs, int B, int N, int M, float* scores0, float* scores1, void* stream) {
+    OM_ON_DEVICE_OF(probs);
+    if (scores0 == nullptr || scores1 == nullptr) return OM_ERR_NULL;
+    return sinkhorn_scores_launch(probs, B, N, M, scores0, scores1, (cudaStream_t)stream);
+}
+
+extern "C" size_t om_mutual_matches_workspace_bytes(int B, int N, int M) { return mutual_matches_workspace_bytes(B, N, M); }
+
+extern "C" int om_mutual_matches_f32(const float* probs, const float* kpts1, const float* kpts2, int B, int N, int M,
+                                     int max_matches, float threshold, float* matched_kpts1, float* matched_kpts2,
+                                     float* scores, unsigned char* valid, void* ws, size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(probs);
+    return mutual_matches_launch(probs, kpts1, kpts2, B, N, M, max_matches, threshold, matched_kpts1, matched_kpts2, scores, valid,
+                                 ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -668,9 +668,76 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
     return sinkhorn_generic(d1, d2, B, N, M, D, iterations, epsilon, dustbin, distance_l1, P, ws, st);
 }
 
+size_t sinkhorn_ex_workspace_bytes(int B, int N, int M, int D) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    return align_up(sinkhorn_workspace_bytes(B, N, M, D)) + align_up((size_t)B * (N + 1) * (M + 1) * sizeof(float)) +
+           align_up(mutual_matches_workspace_bytes(B, N, M));
+}
+
+int sinkhorn_ex_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
+                       float unused_score, int distance_l1, float* P, const SinkhornEpilogue& e, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    if (!e.any()) {
+        if (P == nullptr) return OM_ERR_NULL;
+        return sinkhorn_launch(d1, d2, B, N, M, D, iterations, epsilon, unused_score, distance_l1, P, ws, ws_bytes, st);
+    }
+    if (d1 == nullptr || d2 == nullptr) return OM_ERR_NULL;
+    if (B <= 0 || N <= 0 || M <= 0 || D <= 0) return OM_ERR_SHAPE;
+    if (iterations <= 0 || !(epsilon > 0.0f)) return OM_ERR_PARAM;
+    if (B > 65535) return OM_ERR_LIMIT;
+    if (e.matches && (e.kpts1 == nullptr || e.kpts2 == nullptr || e.mk1 == nullptr || e.mk2 == nullptr || e.mscores == nullptr ||
+                      e.mvalid == nullptr))
+        return OM_ERR_NULL;
+    if (e.matches && e.max_matches <= 0) return OM_ERR_SHAPE;
+    if (e.filters && e.filter_valid == nullptr) return OM_ERR_NULL;
+    // fused: the epilogue runs on the P values in the cluster kernel's registers; P is written only if the caller wants it
+    if (g_sinkhorn_variant == 0) g_tc_allow_scaling = g_tc_allow_f16 = 1;     // (test variants leave these switched)
+    if (g_sinkhorn_variant == 0 && (long long)B * CL < (1ll << 31) &&
+        sinkhorn_epilogue_can_fuse(N, M, D, epsilon, unused_score, distance_l1))
+        return sinkhorn_cluster_tc_epi(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, e, st);
+    // separate kernels on a stored P (more than 512 keypoints, L1 cost, log-domain loop, test variants)
+    if (ws == nullptr || ws_bytes < sinkhorn_ex_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    char* c = (char*)ws;
+    void* sink_ws = c;
+    c += align_up(sinkhorn_workspace_bytes(B, N, M, D));
+    float* Pbuf = P != nullptr ? P : (float*)c;
+    c += align_up((size_t)B * (N + 1) * (M + 1) * sizeof(float));
+    OM_TRY(sinkhorn_launch(d1, d2, B, N, M, D, iterations, epsilon, unused_score, distance_l1, Pbuf, sink_ws,
+                           sinkhorn_workspace_bytes(B, N, M, D), st));
+    if (e.filters) OM_TRY(filter_rows_launch(Pbuf, B, N, M, e.ratio_threshold, e.dustbin_margin, e.filter_valid, st));
+    if (e.scores0 != nullptr || e.scores1 != nullptr) OM_TRY(sinkhorn_scores_launch(Pbuf, B, N, M, e.scores0, e.scores1, st));
+    if (e.matches)
+        OM_TRY(mutual_matches_launch(Pbuf, e.kpts1, e.kpts2, B, N, M, e.max_matches, e.match_threshold, e.mk1, e.mk2, e.mscores,
+                                     e.mvalid, c, mutual_matches_workspace_bytes(B, N, M), st));
+    return OM_OK;
+}
+
+SinkhornEpilogue epilogue_from_outputs(const om_sinkhorn_outputs* o) {
+    SinkhornEpilogue e;
+    if (o == nullptr) return e;
+    e.scores0 = o->scores0; e.scores1 = o->scores1;
+    e.filters = o->filters; e.ratio_threshold = o->ratio_threshold; e.dustbin_margin = o->dustbin_margin;
+    e.filter_valid = o->filter_valid;
+    e.matches = o->matches; e.kpts1 = o->kpts1; e.kpts2 = o->kpts2; e.max_matches = o->max_matches;
+    e.match_threshold = o->match_threshold; e.mk1 = o->matched_kpts1; e.mk2 = o->matched_kpts2; e.mscores = o->match_scores;
+    e.mvalid = o->match_valid;
+    return e;
+}
+
 }  // namespace om
 
 using namespace om;
+
+extern "C" size_t om_sinkhorn_ex_workspace_bytes(int B, int N, int M, int D) { return sinkhorn_ex_workspace_bytes(B, N, M, D); }
+
+extern "C" int om_sinkhorn_ex_f32(const float* desc1, const float* desc2, int B, int N, int M, int D, int iterations,
+                                  float epsilon, float unused_score, int distance_l1, const om_sinkhorn_outputs* out, void* ws,
+                                  size_t ws_bytes, void* stream) {
+    OM_ON_DEVICE_OF(desc1);
+    if (out == nullptr) return OM_ERR_NULL;
+    return sinkhorn_ex_launch(desc1, desc2, B, N, M, D, iterations, epsilon, unused_score, distance_l1, out->probs,
+                              epilogue_from_outputs(out), ws, ws_bytes, (cudaStream_t)stream);
+}
 
 extern "C" void om_debug_force_generic_sinkhorn(int on) { g_sinkhorn_variant = on ? 2 : 0; }
 extern "C" void om_debug_sinkhorn_variant(int variant) { g_sinkhorn_variant = variant; }

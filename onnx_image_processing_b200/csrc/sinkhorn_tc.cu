@@ -58,8 +58,15 @@ constexpr int OFF_CW = OFF_RECV + 2 * CL * NCOL;           // [NW][NCOL] per-war
 constexpr int OFF_N1 = OFF_CW + NW * NCOL;                 // squared norms of the local d1 rows
 constexpr int OFF_N2 = OFF_N1 + 64;                        // squared norms of all d2 rows
 constexpr int OFF_CP = OFF_N2 + MAXM;                      // [2][NCOL] this CTA's column partials (bulk-copy source)
-constexpr int OFF_BAR = OFF_CP + 2 * NCOL;                 // 7 mbarriers + TMEM base address
-constexpr int SMEM_FLOATS = OFF_BAR + 16;
+constexpr int OFF_BAR = OFF_CP + 2 * NCOL;                 // 8 mbarriers + TMEM base address
+constexpr int SMEM_FLOATS = OFF_BAR + 32;
+// epilogue tables (fused match extraction): they live in the receive area, which is idle once the iterations are over
+constexpr int EPI_COLVAL = OFF_RECV + 1024;                // [CL][64] best value of the owned columns, one row per sender
+constexpr int EPI_COLIDX = OFF_RECV + 1536;                // [CL][64] row that attains it
+constexpr int EPI_COLARG = OFF_RECV + 2048;                // [MAXM] argmax row of every column (all-gathered)
+constexpr int EPI_KEYS = OFF_RECV + 2560;                  // [MAXM] 64-bit sort keys (rank 0)
+constexpr int EPI_END = EPI_KEYS + 2 * MAXM;
+static_assert(EPI_END <= OFF_CW && (EPI_KEYS * 4) % 8 == 0, "epilogue tables must fit the receive area");
 constexpr uint32_t PART_BYTES = NCOL * 4;                  // one rank's partial column sums
 static_assert(2 * STAGE_BYTES <= OFF_N1 * 4, "staging must not reach the norms / barriers");
 static_assert((OFF_BAR * 4) % 8 == 0 && (OFF_RECV * 4) % 16 == 0 && (OFF_CW * 4) % 16 == 0 && (OFF_CP * 4) % 16 == 0,
@@ -166,9 +173,23 @@ struct TcArgs {
     int iterations;
     float scale2;       // log2(e)/eps
     float dustbin2;     // (-unused/eps) * log2(e)
-    float* P;
+    float* P;           // EPI kernels: may be null (P never leaves the chip)
     long long* trace;   // optional (debug): per CTA 8 clock64 stamps
+    SinkhornEpilogue e; // EPI kernels only
 };
+
+__device__ __forceinline__ void st_async_b64(uint32_t dst_cluster, unsigned long long v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster), "l"(v),
+                 "r"(bar_cluster) : "memory");
+}
+// float -> unsigned with the same order (so that -1 sorts below every probability); as in matches.cu
+__device__ __forceinline__ unsigned int ordered_bits_tc(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits_tc(unsigned int o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
 
 #define OM_STAMP(slot)                                                                   \
     do {                                                                                 \
@@ -180,8 +201,9 @@ struct TcArgs {
 // TF32 terms with kind::tf32 (K = 8): same three products hi*hi + hi*lo + lo*hi, a quarter of the MMA instructions
 // and half the staged bytes.  x = hi + lo holds 22 bits, so the dot products are as accurate as FP32 FFMA.  fp16
 // overflows at 65504: the producers watch max|x| and a CTA that saw |x| >= 60000 recomputes its dots with FFMA.
-template <bool XD, bool F16>
+template <bool XD, bool F16, bool EPI = false>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_kernel(TcArgs a) {
+    static_assert(!EPI || XD, "the fused epilogue lives in the scaling-form kernel");
     extern __shared__ __align__(128) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -199,7 +221,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
     float* sCP = sm + OFF_CP;
     // [0,1] stage free (MMAs done), [2] GEMM done, [3,4] partials landed, [5,6] stage full (operands stored)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int r0 = rank * RPC;
     const int nreal = max(0, min(RPC, N - r0));
@@ -215,6 +237,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
         mbar_init(smem_u32(&bars[4]), 1);
         mbar_init(smem_u32(&bars[5]), F16 ? 15 * 32 : NP);        // producers of a stage (F16: warp 15 is the MMA issuer)
         mbar_init(smem_u32(&bars[6]), F16 ? 15 * 32 : NP);
+        mbar_init(smem_u32(&bars[7]), 1);                          // epilogue: sort keys landed (rank 0)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -654,7 +677,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
             x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;
         }
         // ---------------- P = a_i K_ij b_j (sinkhorn.py:145, :206) -----------------------------------------
-        float* Pz = a.P + (size_t)z * (N + 1) * (M + 1);
+        float* Pz = a.P != nullptr ? a.P + (size_t)z * (N + 1) * (M + 1) : nullptr;
+        if constexpr (!EPI) {
         if (warp < NW) {
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
@@ -687,6 +711,213 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) sinkhorn_tc_
                 if (lane == 0) out[M] = f * bM;
             }
         }
+        } else {
+        // ======== fused epilogue: filters (sinkhorn.py:311-465), scores (:211-259), mutual matches (match_extraction.py:46-184)
+        // on the P values in registers.  P itself is written only when the caller wants it.
+        const SinkhornEpilogue& e = a.e;
+        const uint32_t epar = (uint32_t)(a.iterations & 1);             // phase of bars[3] / bars[4] after the loop
+        float* eWVal = sS;                                              // [NW][MAXM] per-warp column maxima (score slab is dead)
+        int* eWIdx = reinterpret_cast<int*>(sS + NW * MAXM);            // [NW][MAXM] local row attaining them
+        float* eColVal = sm + EPI_COLVAL;
+        int* eColIdx = reinterpret_cast<int*>(sm + EPI_COLIDX);
+        int* eColArg = reinterpret_cast<int*>(sm + EPI_COLARG);
+        unsigned long long* eKeys = reinterpret_cast<unsigned long long*>(sm + EPI_KEYS);
+        const bool want_cols = e.scores1 != nullptr || e.matches;
+        if (tid == 0 && want_cols) {
+            mbar_arrive_expect_tx(smem_u32(&bars[3]), (uint32_t)CL * 64u * 8u);
+            if (e.matches) {
+                mbar_arrive_expect_tx(smem_u32(&bars[4]), (uint32_t)MAXM * 4u);
+                if (rank == 0) mbar_arrive_expect_tx(smem_u32(&bars[7]), (uint32_t)MAXM * 8u);
+            }
+        }
+        // P in place of K (same expression as the plain kernel's write: bit-identical values)
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                kreg[rr][c].x = areg[rr] * kreg[rr][c].x * breg[c].x;
+                kreg[rr][c].y = areg[rr] * kreg[rr][c].y * breg[c].y;
+            }
+        }
+        // ---- row statistics: best / second-best core value and the first column attaining the best ----
+        float rbest[4];
+        int rarg[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            float b1 = -CUDART_INF_F, b2 = -CUDART_INF_F;
+            int arg = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = 128 * k + 4 * lane + q;
+                    const float v = q == 0 ? kreg[rr][2 * k].x : (q == 1 ? kreg[rr][2 * k].y : (q == 2 ? kreg[rr][2 * k + 1].x : kreg[rr][2 * k + 1].y));
+                    if (col < M) {
+                        if (v > b1) { b2 = b1; b1 = v; arg = col; } else if (v > b2) b2 = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                b2 = fmaxf(fminf(b1, o1), fmaxf(b2, o2));               // topk(2): a duplicated maximum counts twice
+                if (o1 > b1 || (o1 == b1 && oa < arg)) { b1 = o1; arg = oa; }
+            }
+            const int li = 4 * warp + rr;
+            float pdust = areg[rr] * kd * bM;
+            bool ok = true;
+            if (e.filters) {
+                if (e.ratio_threshold > 0.0f) {
+                    const float second = M >= 2 ? b2 : 0.0f;            // sinkhorn.py:339-341
+                    ok = ok && (__fdiv_rn(b1, __fadd_rn(second, 1e-8f)) >= e.ratio_threshold);
+                }
+                if (e.dustbin_margin >= 0.0f) ok = ok && (__fsub_rn(b1, pdust) >= e.dustbin_margin);
+                if (!ok) {                                              // rejected: core -> 0, dustbin -> 1 (:448-457)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) kreg[rr][c] = make_float2(0.0f, 0.0f);
+                    pdust = 1.0f;
+                    b1 = 0.0f;
+                    arg = 0;
+                }
+                if (lane == 0 && li < nreal && e.filter_valid != nullptr) e.filter_valid[(size_t)z * N + r0 + li] = ok ? 1 : 0;
+            }
+            rbest[rr] = b1;
+            rarg[rr] = arg;
+            if (lane == 0 && li < nreal && e.scores0 != nullptr) e.scores0[(size_t)z * N + r0 + li] = b1;
+            if (Pz != nullptr && li < nreal) {                          // warp-uniform
+                float* stage = sS + li * SPITCH;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    *reinterpret_cast<float4*>(stage + 128 * k + 4 * lane) =
+                        make_float4(kreg[rr][2 * k].x, kreg[rr][2 * k].y, kreg[rr][2 * k + 1].x, kreg[rr][2 * k + 1].y);
+                __syncwarp();
+                float* out = Pz + (size_t)(r0 + li) * (M + 1);
+#pragma unroll
+                for (int k = 0; k < MAXM / 32; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < M) out[c] = stage[c];
+                }
+                if (lane == 0) out[M] = pdust;
+            }
+        }
+        if (Pz != nullptr && has_dust && warp == 0) {                   // dustbin row: never filtered (:459-460)
+            float* out = Pz + (size_t)N * (M + 1);
+            const float f = aN * kd;
+            for (int c = lane; c < M; c += 32) out[c] = f * sB[c];
+            if (lane == 0) out[M] = f * bM;
+        }
+        if (want_cols) {
+            bar_sweep();                                                // every warp is done with its staging rows in sS
+            // ---- column statistics: warp partial over its 4 rows -> CTA -> owner of the column ----
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float v4[4];
+                int i4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float best = -CUDART_INF_F;
+                    int arg = 0;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {                    // ascending rows, strict >: the first maximal row wins
+                        const float v = q == 0 ? kreg[rr][2 * k].x : (q == 1 ? kreg[rr][2 * k].y : (q == 2 ? kreg[rr][2 * k + 1].x : kreg[rr][2 * k + 1].y));
+                        if (4 * warp + rr < nreal && v > best) { best = v; arg = 4 * warp + rr; }
+                    }
+                    v4[q] = best;
+                    i4[q] = arg;
+                }
+                *reinterpret_cast<float4*>(eWVal + warp * MAXM + 128 * k + 4 * lane) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                *reinterpret_cast<int4*>(eWIdx + warp * MAXM + 128 * k + 4 * lane) = make_int4(i4[0], i4[1], i4[2], i4[3]);
+            }
+            bar_sweep();
+            {   // one column per thread: CTA partial -> the column's owner (rows of lower warps first, strict >)
+                float best = eWVal[tid];
+                int arg = eWIdx[tid];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) {
+                    const float v = eWVal[w * MAXM + tid];
+                    if (v > best) { best = v; arg = eWIdx[w * MAXM + tid]; }
+                }
+                const uint32_t owner = (uint32_t)tid >> 6;
+                const uint32_t slot = (uint32_t)(rank * 64 + (tid & 63)) * 4u;
+                const uint32_t obar = mapa_u32(smem_u32(&bars[3]), owner);
+                st_async_f32(mapa_u32(smem_u32(eColVal) + slot, owner), best, obar);
+                st_async_f32(mapa_u32(smem_u32(eColIdx) + slot, owner), __int_as_float(r0 + arg), obar);
+            }
+            mbar_wait(smem_u32(&bars[3]), epar);
+            if (tid < 64) {                                             // owner: best over the 8 row slices, lowest rank first
+                float best = eColVal[tid];
+                int arg = eColIdx[tid];
+#pragma unroll
+                for (int r = 1; r < CL; ++r) {
+                    const float v = eColVal[r * 64 + tid];
+                    if (v > best) { best = v; arg = eColIdx[r * 64 + tid]; }
+                }
+                const int col = 64 * rank + tid;
+                if (col < M && e.scores1 != nullptr) e.scores1[(size_t)z * M + col] = best;
+                if (e.matches) {
+#pragma unroll
+                    for (int dst = 0; dst < CL; ++dst)
+                        st_async_f32(mapa_u32(smem_u32(eColArg) + (uint32_t)col * 4u, (uint32_t)dst), __int_as_float(arg),
+                                     mapa_u32(smem_u32(&bars[4]), (uint32_t)dst));
+                }
+            }
+        }
+        if (e.matches) {
+            mbar_wait(smem_u32(&bars[4]), epar);
+            // ---- mutual check + threshold (match_extraction.py:95-121): one 64-bit key per row to rank 0 ----
+            if (lane < 4) {
+                const int rr = lane;
+                const int li = 4 * warp + rr;
+                const float b1 = rr == 0 ? rbest[0] : (rr == 1 ? rbest[1] : (rr == 2 ? rbest[2] : rbest[3]));
+                const int arg = rr == 0 ? rarg[0] : (rr == 1 ? rarg[1] : (rr == 2 ? rarg[2] : rarg[3]));
+                unsigned long long key = 0ull;                          // rows beyond N sort last
+                if (li < nreal) {
+                    const int gi = r0 + li;
+                    const bool mutual = eColArg[arg] == gi;
+                    const float sc = (mutual && b1 >= e.match_threshold) ? b1 : -1.0f;
+                    key = ((unsigned long long)ordered_bits_tc(sc) << 32) | (unsigned long long)(((0x3FFu - (unsigned)gi) << 16) | (unsigned)arg);
+                }
+                st_async_b64(mapa_u32(smem_u32(eKeys) + (uint32_t)(r0 + li) * 8u, 0u), key, mapa_u32(smem_u32(&bars[7]), 0u));
+            }
+            if (rank == 0) {
+                mbar_wait(smem_u32(&bars[7]), 0u);
+                const unsigned long long key0 = eKeys[0];               // row 0's key (its argmax column pads short outputs)
+                bar_sweep();
+                // descending bitonic sort of the MAXM keys (torch.topk sorted, :124-130; equal scores in ascending row order)
+                for (int size = 2; size <= MAXM; size <<= 1) {
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        if (tid < MAXM / 2) {
+                            const int lo = 2 * tid - (tid & (stride - 1));
+                            const int hi = lo + stride;
+                            const bool desc = (lo & size) == 0;
+                            const unsigned long long x = eKeys[lo], y = eKeys[hi];
+                            if ((x < y) == desc) { eKeys[lo] = y; eKeys[hi] = x; }
+                        }
+                        bar_sweep();
+                    }
+                }
+                const int take = min(e.max_matches, N);
+                for (int m = tid; m < e.max_matches; m += NT) {
+                    float sc = 0.0f;                                    // zero padding when N < max_matches (:133-142)
+                    unsigned long long key = key0;
+                    if (m < take) {
+                        key = eKeys[m];
+                        sc = from_ordered_bits_tc((unsigned int)(key >> 32));
+                    }
+                    const int i = m < take ? (int)(0x3FFu - (unsigned)((key >> 16) & 0x3FFu)) : 0;
+                    const int j = min((int)(key & 0xFFFFu), M - 1);
+                    const size_t o = ((size_t)z * e.max_matches + m) * 2;
+                    e.mk1[o] = e.kpts1[((size_t)z * N + i) * 2];
+                    e.mk1[o + 1] = e.kpts1[((size_t)z * N + i) * 2 + 1];
+                    e.mk2[o] = e.kpts2[((size_t)z * M + j) * 2];
+                    e.mk2[o + 1] = e.kpts2[((size_t)z * M + j) * 2 + 1];
+                    e.mscores[(size_t)z * e.max_matches + m] = sc;
+                    e.mvalid[(size_t)z * e.max_matches + m] = sc > 0.0f ? 1 : 0;      // :181
+                }
+            }
+        }
+        }   // EPI
         OM_STAMP(6);
         cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
     } else {
@@ -1023,6 +1254,28 @@ int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, i
         OM_TRY(set_smem((sinkhorn_tc_kernel<false, false>), smem));
         sinkhorn_tc_kernel<false, false><<<B * CL, NT, smem, st>>>(a);
     }
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+bool sinkhorn_epilogue_can_fuse(int N, int M, int D, float eps, float unused, int distance_l1) {
+    const double log2e = 1.4426950408889634;
+    return !distance_l1 && N <= RPC * CL && M <= MAXM && D % 32 == 0 && g_tc_allow_scaling && g_tc_allow_f16 &&
+           (double)unused / (double)eps * log2e <= 60.0 && unused >= 0.0f;
+}
+
+int sinkhorn_cluster_tc_epi(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
+                            float unused, float* P, const SinkhornEpilogue& e, cudaStream_t st) {
+    if (!sinkhorn_epilogue_can_fuse(N, M, D, eps, unused, 0)) return OM_ERR_PARAM;
+    TcArgs a{};
+    a.trace = nullptr;
+    a.d1 = d1; a.d2 = d2; a.N = N; a.M = M; a.D = D; a.iterations = iterations; a.P = P; a.e = e;
+    const double log2e = 1.4426950408889634;
+    a.scale2 = (float)(log2e / (double)eps);
+    a.dustbin2 = (float)((-(double)unused / (double)eps) * log2e);
+    const size_t smem = (size_t)SMEM_FLOATS * sizeof(float);
+    OM_TRY(set_smem((sinkhorn_tc_kernel<true, true, true>), smem));
+    sinkhorn_tc_kernel<true, true, true><<<B * CL, NT, smem, st>>>(a);
     OM_AFTER_LAUNCH();
     return OM_OK;
 }

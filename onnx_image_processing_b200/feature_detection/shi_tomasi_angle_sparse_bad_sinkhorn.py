@@ -32,14 +32,17 @@ class ShiTomasiAngleSparseBADSinkhornMatcher(nn.Module):
         self.matcher = SinkhornMatcher(iterations=sinkhorn_iterations, epsilon=epsilon, unused_score=unused_score,
                                        distance_type=distance_type)
 
-    def match(self, image1: torch.Tensor, image2: torch.Tensor):
+    def _match_args(self):
         d, m = self.descriptor, self.matcher
-        return _ops.match_pairs(image1, image2, d._pair_table, self.detector.angle_estimator.moment_kernels,
-                                _ops.MATCH_ANGLE, int(self.max_keypoints), self.detector.shi_tomasi.block_size,
-                                int(self.nms_radius), int(self.border_margin), float(self.score_threshold), d._mode(),
-                                float(d.temperature), bool(d.normalize_descriptors),
-                                _ops.sampling_code(d.sampling_mode), m.iterations, float(m.epsilon),
-                                float(m.unused_score), m.distance_type == "l1")
+        return (d._pair_table, self.detector.angle_estimator.moment_kernels,
+                _ops.MATCH_ANGLE, int(self.max_keypoints), self.detector.shi_tomasi.block_size,
+                int(self.nms_radius), int(self.border_margin), float(self.score_threshold), d._mode(),
+                float(d.temperature), bool(d.normalize_descriptors),
+                _ops.sampling_code(d.sampling_mode), m.iterations, float(m.epsilon),
+                float(m.unused_score), m.distance_type == "l1")
+
+    def match(self, image1: torch.Tensor, image2: torch.Tensor):
+        return _ops.match_pairs(image1, image2, *self._match_args())
 
     def forward(self, image1: torch.Tensor, image2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         k1, k2, probs, _, _ = self.match(image1, image2)
@@ -63,7 +66,10 @@ class ShiTomasiAngleSparseBADSinkhornMatcherWithFilters(ShiTomasiAngleSparseBADS
                                                   distance_type=distance_type, ratio_threshold=ratio_threshold,
                                                   dustbin_margin=dustbin_margin)
 
+    def _filter_args(self):
+        return True, float(self.matcher.ratio_threshold), float(self.matcher.dustbin_margin)
+
     def forward(self, image1: torch.Tensor, image2: torch.Tensor):
-        k1, k2, probs, _, _ = self.match(image1, image2)
-        valid = _ops.filter_rows_(probs, float(self.matcher.ratio_threshold), float(self.matcher.dustbin_margin))   # P is ours: in place
-        return k1, k2, probs, valid
+        # one C call: the filters run in the Sinkhorn kernel's epilogue on the probabilities it holds in registers
+        out = _ops.match_pairs_ex(image1, image2, *self._match_args(), True, False, *self._filter_args(), 0, 0.0)
+        return out[0], out[1], out[2], out[5]

@@ -38,13 +38,16 @@ class ShiTomasiBADSinkhornMatcher(nn.Module):
                          dim=-1)
         return _ops.gather_descriptors(descriptor_map, kc, True) * valid.unsqueeze(-1)
 
-    def match(self, image1: torch.Tensor, image2: torch.Tensor):
+    def _match_args(self):
         d, m = self.detector.descriptor, self.matcher
-        return _ops.match_pairs(image1, image2, d._pair_table, None, _ops.MATCH_DENSE, int(self.max_keypoints),
-                                self.detector.corner_detector.block_size, int(self.nms_radius), 0,
-                                float(self.score_threshold), _ops.desc_mode(d.binarize, d.soft_binarize),
-                                float(d.temperature), bool(self.normalize_descriptors), _ops.SAMPLE_NEAREST,
-                                m.iterations, float(m.epsilon), float(m.unused_score), m.distance_type == "l1")
+        return (d._pair_table, None, _ops.MATCH_DENSE, int(self.max_keypoints),
+                self.detector.corner_detector.block_size, int(self.nms_radius), 0,
+                float(self.score_threshold), _ops.desc_mode(d.binarize, d.soft_binarize),
+                float(d.temperature), bool(self.normalize_descriptors), _ops.SAMPLE_NEAREST,
+                m.iterations, float(m.epsilon), float(m.unused_score), m.distance_type == "l1")
+
+    def match(self, image1: torch.Tensor, image2: torch.Tensor):
+        return _ops.match_pairs(image1, image2, *self._match_args())
 
     def forward(self, image1: torch.Tensor, image2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         k1, k2, probs, _, _ = self.match(image1, image2)

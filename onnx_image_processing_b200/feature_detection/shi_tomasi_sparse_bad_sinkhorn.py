@@ -35,14 +35,17 @@ class ShiTomasiSparseBADSinkhornMatcher(nn.Module):
         self.matcher = SinkhornMatcher(iterations=sinkhorn_iterations, epsilon=epsilon, unused_score=unused_score,
                                        distance_type=distance_type)
 
+    def _match_args(self):
+        d, m = self.descriptor, self.matcher
+        return (d._pair_table, None, _ops.MATCH_SPARSE, int(self.max_keypoints),
+                self.corner_detector.block_size, int(self.nms_radius), int(self.border_margin),
+                float(self.score_threshold), d._mode(), float(d.temperature),
+                bool(d.normalize_descriptors), _ops.sampling_code(d.sampling_mode), m.iterations,
+                float(m.epsilon), float(m.unused_score), m.distance_type == "l1")
+
     def match(self, image1: torch.Tensor, image2: torch.Tensor):
         """forward plus the two descriptor sets: (kpts1, kpts2, probs, desc1, desc2)."""
-        d, m = self.descriptor, self.matcher
-        return _ops.match_pairs(image1, image2, d._pair_table, None, _ops.MATCH_SPARSE, int(self.max_keypoints),
-                                self.corner_detector.block_size, int(self.nms_radius), int(self.border_margin),
-                                float(self.score_threshold), d._mode(), float(d.temperature),
-                                bool(d.normalize_descriptors), _ops.sampling_code(d.sampling_mode), m.iterations,
-                                float(m.epsilon), float(m.unused_score), m.distance_type == "l1")
+        return _ops.match_pairs(image1, image2, *self._match_args())
 
     def forward(self, image1: torch.Tensor, image2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         k1, k2, probs, _, _ = self.match(image1, image2)

@@ -31,9 +31,9 @@ class SinkhornMatcherWithScores(SinkhornMatcher):
     """Also returns the best non-dustbin probability per row and per column (sinkhorn.py:211-259)."""
 
     def forward(self, desc1: torch.Tensor, desc2: torch.Tensor):
-        P = super().forward(desc1, desc2)
-        scores0, scores1 = _ops.sinkhorn_scores(P)
-        return P, scores0, scores1
+        out = _ops.sinkhorn_ex(desc1, desc2, self.iterations, float(self.epsilon), float(self.unused_score),
+                               self.distance_type == "l1", True, True, False, -1.0, -1.0, None, None, 0, 0.0)
+        return out[0], out[1], out[2]
 
 
 class SinkhornMatcherWithFilters(SinkhornMatcher):
@@ -47,6 +47,7 @@ class SinkhornMatcherWithFilters(SinkhornMatcher):
         self.dustbin_margin = dustbin_margin if dustbin_margin is not None else -1.0
 
     def forward(self, desc1: torch.Tensor, desc2: torch.Tensor):
-        P = super().forward(desc1, desc2)                # fresh tensor owned here: filtered in place, no copy
-        valid = _ops.filter_rows_(P, float(self.ratio_threshold), float(self.dustbin_margin))
-        return P, valid
+        out = _ops.sinkhorn_ex(desc1, desc2, self.iterations, float(self.epsilon), float(self.unused_score),
+                               self.distance_type == "l1", True, False, True, float(self.ratio_threshold),
+                               float(self.dustbin_margin), None, None, 0, 0.0)
+        return out[0], out[3]

@@ -1083,3 +1083,86 @@ def test_banded_integral_shapes(shape):
         rd = torch.cat([O.dense_descriptors_at_keypoints(O.dense_bad(img[b:b + 1]), k[b:b + 1]) for b in range(B)])
         gd = _ops.dense_bad_at_keypoints(img.to(DEV), k.to(DEV), om.BADDescriptor()._pair_table.to(DEV), 0, 10.0, True)
         assert PR.desc_metrics(gd, rd)["rows_within"] == 1.0
+
+
+# ------------------------------------------------------------------------------------------
+# matching-stage outputs fused into the Sinkhorn kernel's epilogue
+# ------------------------------------------------------------------------------------------
+def _descs(B, N, M, seed, noise=0.3):
+    g = torch.Generator().manual_seed(seed)
+    d1 = torch.nn.functional.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    pick = (torch.randperm(max(N, M), generator=g) % N)[:M]
+    d2 = torch.nn.functional.normalize(d1[:, pick] + noise * torch.randn(B, M, 256, generator=g), dim=-1)
+    k1 = torch.rand(B, N, 2, generator=g) * 400
+    k2 = torch.rand(B, M, 2, generator=g) * 400
+    return d1, d2, k1, k2
+
+
+@pytest.mark.parametrize("variant", [0, 2], ids=["fused-epilogue", "separate-kernels"])
+@pytest.mark.parametrize("N,M,eps,ratio,margin,mm,thr", [
+    (512, 512, 0.1, -1.0, -1.0, 100, 0.2), (512, 512, 0.05, 1.5, 0.05, 600, 0.0), (300, 257, 0.1, 1.05, -1.0, 50, 0.1),
+    (77, 512, 0.2, -1.0, 0.0, 100, 0.05), (1, 1, 1.0, 2.0, 0.1, 5, 0.0), (449, 64, 0.1, 1.2, 0.01, 64, 0.3)])
+def test_sinkhorn_epilogue_outputs(N, M, eps, ratio, margin, mm, thr, variant):
+    """om_sinkhorn_ex_f32 with everything switched on: P, scores, filters and mutual matches from ONE call.  The probabilities
+    are those of the plain kernel bit for bit; every other output must equal the reference arithmetic (oracle) applied to that
+    very P -- in the fused form (epilogue of the tcgen05 cluster kernel) and through the separate kernels."""
+    d1, d2, k1, k2 = _descs(2, N, M, seed=N * 3 + M)
+    use_f = ratio > 0 or margin >= 0
+    plain = _with_variant(variant, lambda: _ops.sinkhorn(d1.to(DEV), d2.to(DEV), 20, eps, 1.0, False)).cpu()
+    out = _with_variant(variant, lambda: _ops.sinkhorn_ex(d1.to(DEV), d2.to(DEV), 20, eps, 1.0, False, True, True, use_f, ratio,
+                                                         margin, k1.to(DEV), k2.to(DEV), mm, thr))
+    p, s0, s1, fv, mk1, mk2, ms, mv = [t.cpu() for t in out]
+    ref_p, ref_valid = O.filter_rows(plain, ratio, margin) if use_f else (plain, None)
+    assert torch.equal(p, ref_p)
+    if use_f:
+        assert torch.equal(fv, ref_valid)
+    assert torch.equal(s0, ref_p[:, :N, :M].max(dim=-1).values) and torch.equal(s1, ref_p[:, :N, :M].max(dim=-2).values)
+    assert _same_matches((mk1, mk2, ms, mv), O.mutual_matches(ref_p, k1, k2, mm, thr))
+    # matches only: nothing else requested, P not written
+    only = _with_variant(variant, lambda: _ops.sinkhorn_ex(d1.to(DEV), d2.to(DEV), 20, eps, 1.0, False, False, False, use_f, ratio,
+                                                          margin, k1.to(DEV), k2.to(DEV), mm, thr))
+    assert only[0].numel() == 0 and only[1].numel() == 0
+    for a, b in zip(only[4:], (mk1, mk2, ms, mv)):
+        assert torch.equal(a.cpu(), b)
+
+
+def test_sinkhorn_epilogue_ties_and_degenerate_rows():
+    """Equal probabilities (duplicate descriptors, zero descriptors): argmax takes the first index in rows and columns, a
+    duplicated maximum counts twice in the ratio filter, exactly as torch.argmax / topk(2) do."""
+    g = torch.Generator().manual_seed(3)
+    d1 = torch.nn.functional.normalize(torch.randn(1, 200, 256, generator=g), dim=-1)
+    d2 = d1.clone()
+    d2[0, 50] = d2[0, 10]            # two identical columns
+    d1[0, 120] = d1[0, 30]           # two identical rows
+    d1[0, -3:] = 0.0                 # zero descriptors participate unmasked
+    k = torch.rand(1, 200, 2, generator=g) * 100
+    plain = _ops.sinkhorn(d1.to(DEV), d2.to(DEV), 20, 0.1, 1.0, False).cpu()
+    out = [t.cpu() for t in _ops.sinkhorn_ex(d1.to(DEV), d2.to(DEV), 20, 0.1, 1.0, False, True, True, True, 1.01, 0.0,
+                                             k.to(DEV), k.to(DEV), 200, 0.0)]
+    ref_p, ref_valid = O.filter_rows(plain, 1.01, 0.0)
+    assert torch.equal(out[0], ref_p) and torch.equal(out[3], ref_valid)
+    assert _same_matches(tuple(out[4:]), O.mutual_matches(ref_p, k, k, 200, 0.0))
+
+
+@pytest.mark.parametrize("flavour", ["dense", "sparse", "angle-filters", "export"])
+def test_match_extraction_wrapper_fused_equals_stored_p(flavour):
+    """MatchExtractionWrapper over the unified matchers takes the fused path (no (K+1)^2 matrix); the result must equal the
+    extraction from the matcher's own stored P (MutualNearestNeighborMatcher module on it), K <= 512 and K > 512."""
+    i1, i2 = O.texture_images(3, 240, 320, seed=97)
+    if flavour == "dense":
+        model = om.ShiTomasiBADSinkhornMatcher(256, epsilon=0.1)
+    elif flavour == "sparse":
+        model = om.ShiTomasiSparseBADSinkhornMatcher(300, epsilon=0.05)
+    elif flavour == "export":
+        model = om.ShiTomasiSparseBADSinkhornMatcher(700, num_pairs=512, binarize=True, soft_binarize=False, epsilon=0.05, nms_radius=5)
+    else:
+        model = om.ShiTomasiAngleSparseBADSinkhornMatcherWithFilters(256, epsilon=0.1, ratio_threshold=1.1, dustbin_margin=0.0)
+    model = model.to(DEV).eval()
+    wrapped = om.MatchExtractionWrapper(model, max_matches=120, match_threshold=0.05).to(DEV).eval()
+    with torch.no_grad():
+        got = wrapped(i1.to(DEV), i2.to(DEV))
+        outs = model(i1.to(DEV), i2.to(DEV))
+        ref = om.MutualNearestNeighborMatcher(120, 0.05)(outs[2], outs[0], outs[1])
+    assert int(got[3].sum()) > 20
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
