@@ -178,6 +178,12 @@ int sinkhorn_cluster_tc(const float* d1, const float* d2, int B, int N, int M, i
 int sinkhorn_cluster_tc_epi(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps,
                             float unused, float* P, const SinkhornEpilogue& e, cudaStream_t st);
 bool sinkhorn_epilogue_can_fuse(int N, int M, int D, float eps, float unused, int distance_l1);
+// hybrid-resident cluster kernel (sinkhorn_hy.cu): K half in registers, half in shared memory; 4-CTA clusters up to
+// 512 x 512, 16-CTA clusters up to 1024 x 1024; scaling form, squared-L2 cost, D % 32 == 0.  `e` may be null (P only).
+bool sinkhorn_hy_eligible(int N, int M, int D, float eps, float unused, int distance_l1);
+size_t sinkhorn_hy_workspace_bytes(int B, int N, int M, int D);
+int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                       float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t sinkhorn_ex_workspace_bytes(int B, int N, int M, int D);
 // Sinkhorn + optional outputs; P may be null when the epilogue is fused (otherwise it is kept in the workspace)
 int sinkhorn_ex_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,

@@ -634,6 +634,8 @@ int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int 
 // 3: tcgen05 cluster kernel with the log-domain loop forced, 4: tcgen05 cluster kernel with the 3xTF32 GEMM forced,
 // 5: generic kernels with the log-domain loop forced (2 = generic kernels, scaling form when safe),
 // 7: generic kernels with the FP32 FFMA cost GEMM (2 / 5: cost GEMM on tcgen05 when D % 32 == 0)
+// 0 takes the hybrid-resident cluster kernel (sinkhorn_hy.cu) whenever it is eligible; 8: the 8-CTA tcgen05 kernel as 0 did
+// before the hybrid kernel existed (K <= 512) / the generic kernels (K > 512)
 int g_sinkhorn_variant = 0;
 
 }  // namespace
@@ -641,9 +643,17 @@ int g_sinkhorn_variant = 0;
 size_t sinkhorn_workspace_bytes(int B, int N, int M, int D) {
     (void)D;
     if (B <= 0 || N <= 0 || M <= 0) return 0;
-    return align_up((size_t)B * N * sizeof(float)) + align_up((size_t)B * M * sizeof(float)) +
+    const size_t generic = align_up((size_t)B * N * sizeof(float)) + align_up((size_t)B * M * sizeof(float)) +
            align_up((size_t)B * (N + 1) * sizeof(float)) + align_up((size_t)B * (M + 1) * sizeof(float)) +
            align_up((size_t)B * ((N + 1 + XR - 1) / XR) * (M + 1) * sizeof(float));   // column partials of the scaling-form generic path
+    const size_t hy = D % 32 == 0 ? sinkhorn_hy_workspace_bytes(B, N, M, D) : 0;       // packed fp16 operands of the hybrid kernel
+    return generic > hy ? generic : hy;
+}
+
+static size_t generic_workspace_bytes(int B, int N, int M) {
+    return align_up((size_t)B * N * sizeof(float)) + align_up((size_t)B * M * sizeof(float)) +
+           align_up((size_t)B * (N + 1) * sizeof(float)) + align_up((size_t)B * (M + 1) * sizeof(float)) +
+           align_up((size_t)B * ((N + 1 + XR - 1) / XR) * (M + 1) * sizeof(float));
 }
 
 int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
@@ -656,13 +666,17 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
                       g_sinkhorn_variant != 5 && g_sinkhorn_variant != 7 && (long long)B * CL < (1ll << 31);
     g_generic_allow_scaling = g_sinkhorn_variant != 5;
     g_generic_tc = g_sinkhorn_variant != 7;
-    if (fast && (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 3 || g_sinkhorn_variant == 4)) {
+    if (g_sinkhorn_variant == 0 && (long long)B * 16 < (1ll << 31) &&
+        sinkhorn_hy_eligible(N, M, D, epsilon, unused_score, distance_l1) && ws != nullptr &&
+        ws_bytes >= sinkhorn_hy_workspace_bytes(B, N, M, D))
+        return sinkhorn_hy_launch(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, nullptr, ws, ws_bytes, st);
+    if (fast && (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 8 || g_sinkhorn_variant == 3 || g_sinkhorn_variant == 4)) {
         g_tc_allow_scaling = g_sinkhorn_variant != 3;
         g_tc_allow_f16 = g_sinkhorn_variant != 4;
         return sinkhorn_cluster_tc(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
     }
     if (fast) return sinkhorn_cluster(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
-    if (ws == nullptr || ws_bytes < sinkhorn_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    if (ws == nullptr || ws_bytes < generic_workspace_bytes(B, N, M)) return OM_ERR_WORKSPACE;
     // dustbin score is computed in double by the reference (python floats) and cast once, sinkhorn.py:182
     const float dustbin = (float)(-(double)unused_score / (double)epsilon);
     return sinkhorn_generic(d1, d2, B, N, M, D, iterations, epsilon, dustbin, distance_l1, P, ws, st);
@@ -691,8 +705,12 @@ int sinkhorn_ex_launch(const float* d1, const float* d2, int B, int N, int M, in
     if (e.matches && e.max_matches <= 0) return OM_ERR_SHAPE;
     if (e.filters && e.filter_valid == nullptr) return OM_ERR_NULL;
     // fused: the epilogue runs on the P values in the cluster kernel's registers; P is written only if the caller wants it
-    if (g_sinkhorn_variant == 0) g_tc_allow_scaling = g_tc_allow_f16 = 1;     // (test variants leave these switched)
-    if (g_sinkhorn_variant == 0 && (long long)B * CL < (1ll << 31) &&
+    if (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 8) g_tc_allow_scaling = g_tc_allow_f16 = 1;     // (test variants leave these switched)
+    if (g_sinkhorn_variant == 0 && (long long)B * 16 < (1ll << 31) &&
+        sinkhorn_hy_eligible(N, M, D, epsilon, unused_score, distance_l1) && ws != nullptr &&
+        ws_bytes >= sinkhorn_hy_workspace_bytes(B, N, M, D))
+        return sinkhorn_hy_launch(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, &e, ws, ws_bytes, st);
+    if ((g_sinkhorn_variant == 0 || g_sinkhorn_variant == 8) && (long long)B * CL < (1ll << 31) &&
         sinkhorn_epilogue_can_fuse(N, M, D, epsilon, unused_score, distance_l1))
         return sinkhorn_cluster_tc_epi(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, e, st);
     // separate kernels on a stored P (more than 512 keypoints, L1 cost, log-domain loop, test variants)

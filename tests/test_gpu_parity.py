@@ -210,7 +210,8 @@ def test_gather_functions():
 # ------------------------------------------------------------------------------------------
 # Sinkhorn
 # ------------------------------------------------------------------------------------------
-VARIANTS = {0: "tcgen05", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32", 5: "generic-log", 7: "generic-ffma-cost"}
+VARIANTS = {0: "hybrid", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32", 5: "generic-log", 7: "generic-ffma-cost",
+            8: "tcgen05-8cta"}
 
 
 def _with_variant(variant, fn):
@@ -223,7 +224,7 @@ def _with_variant(variant, fn):
 
 
 @pytest.mark.parametrize("name", G.names("sinkhorn"))
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 8], ids=lambda v: VARIANTS[v])
 def test_sinkhorn_golden(name, variant):
     g = G.load(name)
     got = _with_variant(variant, lambda: om.SinkhornMatcher(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"])))
@@ -233,7 +234,7 @@ def test_sinkhorn_golden(name, variant):
     assert m64["core"] <= PR.PROB_TOL, m64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 8], ids=lambda v: VARIANTS[v])
 @pytest.mark.parametrize("N,M,eps,unused", [(512, 512, 1.0, 1.0), (512, 512, 0.05, 1.0), (300, 512, 0.1, 0.5),
                                             (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0),
                                             (509, 511, 0.03, 1.0), (512, 512, 0.2, 0.0)])
@@ -259,7 +260,7 @@ def test_sinkhorn_variants_agree_on_matched_descriptors():
     d1 = torch.nn.functional.normalize(torch.randn(3, 512, 256, generator=g), dim=-1)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(512, generator=g)] + 0.02 * torch.randn(3, 512, 256, generator=g), dim=-1)
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.05, 1.0).float()
-    for variant in (0, 1, 2, 3, 4, 5, 7):
+    for variant in (0, 1, 2, 3, 4, 5, 7, 8):
         got = _with_variant(variant, lambda: om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2)))
         m = PR.prob_metrics(got, ref)
         assert PR.probs_ok(m), (VARIANTS[variant], m)
@@ -277,11 +278,12 @@ def test_sinkhorn_descriptors_beyond_fp16_range():
     assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
 
 
-@pytest.mark.parametrize("variant", [0, 5, 7], ids=lambda v: {0: "scaling", 5: "log-domain", 7: "ffma-cost"}[v])
-@pytest.mark.parametrize("N,M,eps,dist", [(700, 700, 0.05, "l2"), (1024, 1024, 0.05, "l2"), (600, 901, 1.0, "l2"), (530, 520, 0.2, "l1")])
+@pytest.mark.parametrize("variant", [0, 2, 5, 7], ids=lambda v: {0: "hybrid16-or-scaling", 2: "scaling", 5: "log-domain", 7: "ffma-cost"}[v])
+@pytest.mark.parametrize("N,M,eps,dist", [(700, 700, 0.05, "l2"), (1024, 1024, 0.05, "l2"), (600, 901, 1.0, "l2"), (530, 520, 0.2, "l1"),
+                                          (1024, 300, 0.1, "l2"), (513, 1000, 0.05, "l2"), (1100, 900, 0.1, "l2")])
 def test_sinkhorn_large_k_generic_path(N, M, eps, dist, variant):
-    """Beyond the cluster kernel's 512 x 512 (the export default K = 1024 and config 5's K = 2048 live here): the
-    global-memory kernels in scaling form and in log-domain form against the oracle."""
+    """Beyond 512 x 512 (the export default K = 1024 and config 5's K = 2048 live here): the 16-CTA hybrid-resident cluster
+    kernel up to 1024 x 1024 (variant 0), the global-memory kernels in scaling form and in log-domain form against the oracle."""
     g = torch.Generator().manual_seed(5)
     d1 = torch.nn.functional.normalize(torch.randn(2, N, 256, generator=g), dim=-1)
     pick = (torch.randperm(max(N, M), generator=g) % N)[:M]
@@ -1098,10 +1100,11 @@ def _descs(B, N, M, seed, noise=0.3):
     return d1, d2, k1, k2
 
 
-@pytest.mark.parametrize("variant", [0, 2], ids=["fused-epilogue", "separate-kernels"])
+@pytest.mark.parametrize("variant", [0, 2, 8], ids=["fused-epilogue", "separate-kernels", "fused-epilogue-8cta"])
 @pytest.mark.parametrize("N,M,eps,ratio,margin,mm,thr", [
     (512, 512, 0.1, -1.0, -1.0, 100, 0.2), (512, 512, 0.05, 1.5, 0.05, 600, 0.0), (300, 257, 0.1, 1.05, -1.0, 50, 0.1),
-    (77, 512, 0.2, -1.0, 0.0, 100, 0.05), (1, 1, 1.0, 2.0, 0.1, 5, 0.0), (449, 64, 0.1, 1.2, 0.01, 64, 0.3)])
+    (77, 512, 0.2, -1.0, 0.0, 100, 0.05), (1, 1, 1.0, 2.0, 0.1, 5, 0.0), (449, 64, 0.1, 1.2, 0.01, 64, 0.3),
+    (1024, 1024, 0.05, 1.2, 0.02, 300, 0.1), (700, 1000, 0.1, -1.0, -1.0, 1200, 0.0), (1000, 530, 0.1, 1.1, -1.0, 100, 0.2)])
 def test_sinkhorn_epilogue_outputs(N, M, eps, ratio, margin, mm, thr, variant):
     """om_sinkhorn_ex_f32 with everything switched on: P, scores, filters and mutual matches from ONE call.  The probabilities
     are those of the plain kernel bit for bit; every other output must equal the reference arithmetic (oracle) applied to that
