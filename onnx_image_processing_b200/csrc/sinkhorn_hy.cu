@@ -27,16 +27,21 @@ namespace om {
 
 namespace {
 
+// 4-CTA form: rows per warp (of 8) whose K values live in registers.  Measured (64 pairs, K = 512): 4 rows = 64 values per
+// thread leave the loop 20 spilled values short of registers (re-read from local memory every sweep: 244 us), 3 rows = 48
+// values and 5 rows in shared memory run without spills (202 us)
+#define HY_RR4 3
 constexpr int NW = 16;              // warps per CTA
 constexpr int NT = NW * 32;
 
-template <int CL_, int MAXM_>
+template <int CL_, int MAXM_, int RR_>
 struct Hy {
     static constexpr int CL = CL_;                   // CTAs per cluster == per descriptor pair
     static constexpr int MAXM = MAXM_;               // columns (keypoints of image 2) at most
     static constexpr int NK = MAXM / 128;            // float4 column groups per lane: lane l owns columns 128k + 4l .. +3
-    static constexpr int RR = 16 / NK;               // rows per warp in registers (64 K values per thread) == rows per warp in smem
-    static constexpr int RPW = 2 * RR;               // rows per warp
+    static constexpr int RPW = 32 / NK;              // rows per warp (128 K values per thread)
+    static constexpr int RR = RR_;                   // rows per warp kept in registers (16 RR / ... K values per thread)
+    static constexpr int RS = RPW - RR;              // rows per warp kept in shared memory
     static constexpr int RPC = NW * RPW;             // rows per CTA: 128 (MAXM 512) / 64 (MAXM 1024)
     static constexpr int OWN = MAXM / CL;            // columns whose sums this CTA finishes: 128 / 64
     static constexpr int PSTR = OWN + 8;             // pitch of the partial table (slot OWN: dustbin column, last rank)
@@ -48,8 +53,8 @@ struct Hy {
     static constexpr int NMB = MAXM / 128;           // M blocks of the (transposed) GEMM
     static constexpr int TMEM_COLS = 512;            // NMB * RPC
     // shared memory, in floats
-    static constexpr int OFF_KS = 0;                               // [NW][RR][MAXM] rows of K kept in shared memory
-    static constexpr int OFF_CW = OFF_KS + NW * RR * MAXM;         // [NW][MAXM] per-warp column partials | bounce | P staging
+    static constexpr int OFF_KS = 0;                               // [NW][RS][MAXM] rows of K kept in shared memory
+    static constexpr int OFF_CW = OFF_KS + NW * RS * MAXM;         // [NW][MAXM] per-warp column partials | bounce | P staging
     static constexpr int OFF_B = OFF_CW + NW * MAXM;               // b: MAXM entries + dustbin column at [MAXM]
     static constexpr int OFF_PART = OFF_B + MAXM + 32;             // [CL][PSTR] partial column sums of the owned columns
     static constexpr int OFF_AS = OFF_PART + CL * PSTR;            // per-warp sum of a
@@ -57,11 +62,17 @@ struct Hy {
     static constexpr int OFF_MISC = OFF_N1 + RPC;                  // fused epilogue, written by peers: column argmax [MAXM],
                                                                    // (value, row) words of the owned columns [CL][OWN] x 8 B,
                                                                    // sort keys [CL * RPC] x 8 B (rank 0)
-    static constexpr int OFF_BAR = OFF_MISC + 5 * MAXM + 64;       // 8 mbarriers + TMEM base address
+    // all-to-all exchange of the column partials (small clusters only): [2 buffers][CL ranks][XSTR]; slot MAXM of a rank's
+    // row carries its share of the dustbin column
+    static constexpr bool A2A = CL <= 4;
+    static constexpr int XSTR = MAXM + 8;
+    static constexpr int OFF_X = OFF_MISC + 5 * MAXM + 64;
+    static constexpr int OFF_BAR = OFF_X + (A2A ? 2 * CL * XSTR : 0);   // 10 mbarriers + TMEM base address
     static constexpr int SMEM_FLOATS = OFF_BAR + 32;
     static_assert(NMB * RPC == TMEM_COLS, "accumulators fill the tensor memory");
     static_assert(2 * STAGE <= OFF_B * 4, "GEMM staging must alias only the K rows and the column partials");
-    static_assert((OFF_BAR * 4) % 8 == 0 && (OFF_MISC * 4) % 8 == 0 && (OFF_B * 4) % 16 == 0 && (OFF_CW * 4) % 16 == 0, "alignment");
+    static_assert((OFF_BAR * 4) % 8 == 0 && (OFF_MISC * 4) % 8 == 0 && (OFF_B * 4) % 16 == 0 && (OFF_CW * 4) % 16 == 0 &&
+                  (OFF_X * 4) % 16 == 0 && (XSTR * 4) % 16 == 0, "alignment");
     static_assert(CL * PSTR >= MAXM, "the partial table doubles as the epilogue's column-row table");
     static_assert(SMEM_FLOATS * 4 <= 227 * 1024, "shared memory");
 };
@@ -82,6 +93,11 @@ __device__ __forceinline__ void st_async32(uint32_t dst_cluster, float v, uint32
 }
 __device__ __forceinline__ void st_async64(uint32_t dst_cluster, unsigned long long v, uint32_t bar_cluster) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster), "l"(v),
+                 "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, const float4& v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
                  "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
@@ -181,6 +197,13 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const float* d, int rows,
     if (lane == 0 && !(mx < 60000.0f)) atomicOr(&ovf[z], 1u);
 }
 
+// out-of-fp16-range fallback of one similarity (rare): kept out of line, the unrolled epilogue calls it from 128 places
+__device__ __noinline__ float dot_f32_slow(const float* x, const float* y, int D) {
+    float dot = 0.0f;
+    for (int k = 0; k < D; ++k) dot = fmaf(__ldg(x + k), __ldg(y + k), dot);
+    return dot;
+}
+
 struct HyArgs {
     const unsigned char* d1p;   // packed fp16 terms of d1 / d2 (pack_f16_kernel)
     const unsigned char* d2p;
@@ -203,10 +226,10 @@ struct HyArgs {
         if (a.trace != nullptr && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64();    \
     } while (0)
 
-template <int CL, int MAXM, bool EPI>
+template <int CL, int MAXM, int RRT, bool EPI>
 __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
-    using C = Hy<CL, MAXM>;
-    constexpr int NK = C::NK, RR = C::RR, RPW = C::RPW, RPC = C::RPC, OWN = C::OWN, PSTR = C::PSTR, KC = C::KC, G = C::G;
+    using C = Hy<CL, MAXM, RRT>;
+    constexpr int NK = C::NK, RR = C::RR, RS = C::RS, RPW = C::RPW, RPC = C::RPC, OWN = C::OWN, PSTR = C::PSTR, KC = C::KC, G = C::G;
     extern __shared__ __align__(128) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -221,9 +244,9 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     float* sAs = sm + C::OFF_AS;
     float* sN1 = sm + C::OFF_N1;
     // [0,1] stage full (bulk copies landed), [2,3] stage free (MMAs retired), [4] GEMM done, [5] partials landed,
-    // [6] b landed, [7] epilogue: sort keys landed (rank 0)
+    // [6] b landed, [7] epilogue: sort keys landed (rank 0), [8,9] all-to-all partials landed (even / odd iterations)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int r0 = rank * RPC;
     const int nreal = max(0, min(RPC, N - r0));
@@ -231,7 +254,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < 10; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -239,7 +262,8 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                      "n"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < RPC; i += NT) sN1[i] = a.n1[((size_t)z * CL + rank) * RPC + i];
+    for (int i = tid; i < RPC; i += NT)                                 // rows beyond N: +inf (their K becomes exactly 0)
+        sN1[i] = r0 + i < N ? a.n1[((size_t)z * CL + rank) * RPC + i] : CUDART_INF_F;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -305,6 +329,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     float4 kreg[RR][NK];
     {
         const bool overflow = a.ovf[z] != 0u;
+        const float nscale2 = -a.scale2;
         const int mbw = warp >> 2, q = warp & 3;
         constexpr int WPB = 32 / RPW;                                   // warps per 32-row block
         for (int h = 0; h < RPC / 32; ++h) {
@@ -312,30 +337,43 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                 const int j = 128 * mb + 32 * q + lane;
                 uint32_t r[32];
                 tmem_ld32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(mb * RPC + 32 * h), r);
-                const float n2j = a.n2[(size_t)z * Mp + j];
                 const bool jv = j < M;
+                // rows beyond N and columns beyond M carry a squared norm of +inf (sN1 / n2j): their cost is +inf and their
+                // K is exactly 0 without a per-element test
+                const float n2j = jv ? a.n2[(size_t)z * Mp + j] : CUDART_INF_F;
+                if (!overflow) {
 #pragma unroll
-                for (int ii = 0; ii < 32; ++ii) {
-                    const int li = 32 * h + ii;
-                    float dot = __uint_as_float(r[ii]);
-                    if (overflow && jv && li < nreal) {                 // out of fp16 range: plain FP32 dot product (slow, rare)
-                        const float* x = a.d1 + ((size_t)z * N + r0 + li) * D;
-                        const float* y = a.d2 + ((size_t)z * M + j) * D;
-                        dot = 0.0f;
-                        for (int k = 0; k < D; ++k) dot = fmaf(__ldg(x + k), __ldg(y + k), dot);
+                    for (int ii = 0; ii < 32; ++ii) {
+                        const int li = 32 * h + ii;
+                        // sinkhorn.py:98-103; 2 * dot is exact, so the fused form rounds exactly like (n1 + n2) - 2 * dot
+                        const float cost = fmaxf(fmaf(-2.0f, __uint_as_float(r[ii]), __fadd_rn(sN1[li], n2j)), 0.0f);
+                        const float kv = ex2h(__fmul_rn(cost, nscale2));
+                        const int wl = ii / RPW, ri = ii % RPW;         // compile-time after unrolling
+                        if (ri >= RR) sKs[((WPB * h + wl) * RS + (ri - RR)) * MAXM + j] = kv;
+                        else sCW[(wl * RR + ri) * MAXM + j] = kv;
                     }
-                    const float cost = fmaxf(__fsub_rn(__fadd_rn(sN1[li], n2j), __fmul_rn(2.0f, dot)), 0.0f);   // sinkhorn.py:98-103
-                    const float kv = (jv && li < nreal) ? ex2h(__fmul_rn(-cost, a.scale2)) : 0.0f;
-                    const int wl = ii / RPW, ri = ii % RPW;             // compile-time after unrolling
-                    if (ri >= RR) sKs[((WPB * h + wl) * RR + (ri - RR)) * MAXM + j] = kv;
-                    else sCW[(wl * RR + ri) * MAXM + j] = kv;
+                } else {                                                // out of fp16 range (rare): FP32 dot products, out of line
+#pragma unroll
+                    for (int ii = 0; ii < 32; ++ii) {
+                        const int li = 32 * h + ii;
+                        const bool ev = jv && li < nreal;
+                        float kv = 0.0f;
+                        if (ev) {
+                            const float dot = dot_f32_slow(a.d1 + ((size_t)z * N + r0 + li) * D, a.d2 + ((size_t)z * M + j) * D, D);
+                            const float cost = fmaxf(__fsub_rn(__fadd_rn(sN1[li], n2j), __fmul_rn(2.0f, dot)), 0.0f);
+                            kv = ex2h(__fmul_rn(cost, nscale2));
+                        }
+                        const int wl = ii / RPW, ri = ii % RPW;
+                        if (ri >= RR) sKs[((WPB * h + wl) * RS + (ri - RR)) * MAXM + j] = kv;
+                        else sCW[(wl * RR + ri) * MAXM + j] = kv;
+                    }
                 }
             }
             if (nmb < C::NMB) {                                          // columns beyond Mp: zero
                 for (int e2 = tid; e2 < 32 * (MAXM - Mp); e2 += NT) {
                     const int ii = e2 / (MAXM - Mp), j = Mp + e2 % (MAXM - Mp);
                     const int wl = ii / RPW, ri = ii % RPW;
-                    if (ri >= RR) sKs[((WPB * h + wl) * RR + (ri - RR)) * MAXM + j] = 0.0f;
+                    if (ri >= RR) sKs[((WPB * h + wl) * RS + (ri - RR)) * MAXM + j] = 0.0f;
                     else sCW[(wl * RR + ri) * MAXM + j] = 0.0f;
                 }
             }
@@ -370,7 +408,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     const uint32_t part_bytes = (uint32_t)CL * (has_dust ? (uint32_t)OWN + 1u : (uint32_t)OWN) * 4u;
     const uint32_t b_bytes = (uint32_t)(MAXM + 1) * 4u;
     const float4* sB4 = reinterpret_cast<const float4*>(sB);
-    const float4* sKs4 = reinterpret_cast<const float4*>(sKs) + (size_t)warp * RR * (MAXM / 4) + lane;
+    const float4* sKs4 = reinterpret_cast<const float4*>(sKs) + (size_t)warp * RS * (MAXM / 4) + lane;
     float4* sCW4 = reinterpret_cast<float4*>(sCW) + (size_t)warp * (MAXM / 4) + lane;
     cluster.sync();      // every CTA is past its GEMM and has initialised its barriers and its b
     HY_STAMP(4);
@@ -379,11 +417,18 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     float aN = 0.0f, bM = 1.0f;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) av[r] = 0.0f;
+    float* sX = sm + C::OFF_X;
     for (int it = 0; it < a.iterations; ++it) {
         const uint32_t par = (uint32_t)(it & 1);
+        const uint32_t xbuf = (uint32_t)(it & 1), xpar = (uint32_t)((it >> 1) & 1);
+        const uint32_t loc_bar_x = smem_u32(&bars[8 + xbuf]);
         if (tid == 0) {
-            mbar_arrive_expect_tx(loc_bar_part, part_bytes);
-            mbar_arrive_expect_tx(loc_bar_b, b_bytes);
+            if constexpr (C::A2A) {
+                mbar_arrive_expect_tx(loc_bar_x, (uint32_t)CL * (uint32_t)(MAXM + 1) * 4u);
+            } else {
+                mbar_arrive_expect_tx(loc_bar_part, part_bytes);
+                mbar_arrive_expect_tx(loc_bar_b, b_bytes);
+            }
         }
         // ---- a_i = mu_i / rowsum_i ----
         float rs[RPW], sb = 0.0f;
@@ -396,20 +441,58 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
 #pragma unroll
             for (int rr = 0; rr < RR; ++rr) rs[rr] = dot4(kreg[rr][k], b4, rs[rr]);
 #pragma unroll
-            for (int sr = 0; sr < RR; ++sr) rs[RR + sr] = dot4(sKs4[sr * (MAXM / 4) + 32 * k], b4, rs[RR + sr]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int r = 0; r < RPW; ++r) rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            for (int sr = 0; sr < RS; ++sr) rs[RR + sr] = dot4(sKs4[sr * (MAXM / 4) + 32 * k], b4, rs[RR + sr]);
         }
         bM = sB[MAXM];
         float asum = 0.0f;
+        if constexpr (RPW == 8) {
+            // transposing butterfly: after the steps with partners 16, 8 and 4 a lane carries ONE row's partial sum (row
+            // lane >> 2), so the five steps take 4 + 2 + 1 + 1 + 1 shuffles instead of 8 x 5; the additions of a row are those
+            // of the plain xor butterfly (16, 8, 4, 2, 1) in the same order
+            float x[4], y[2], zr;
+            {
+                const bool hi = (lane & 16) != 0;
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            av[r] = (RPW * warp + r < nreal) ? __fdividef(1.0f, fmaf(kd, bM, rs[r])) : 0.0f;
-            asum += av[r];
+                for (int r = 0; r < 4; ++r) {
+                    const float send = hi ? rs[r] : rs[r + 4], keep = hi ? rs[r + 4] : rs[r];
+                    x[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            {
+                const bool hi = (lane & 8) != 0;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float send = hi ? x[r] : x[r + 2], keep = hi ? x[r + 2] : x[r];
+                    y[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+            }
+            {
+                const bool hi = (lane & 4) != 0;
+                const float send = hi ? y[0] : y[1], keep = hi ? y[1] : y[0];
+                zr = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            zr += __shfl_xor_sync(0xffffffffu, zr, 2);
+            zr += __shfl_xor_sync(0xffffffffu, zr, 1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            const float mine = (RPW * warp + (lane >> 2) < nreal) ? __fdividef(1.0f, fmaf(kd, bM, zr)) : 0.0f;
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                av[r] = __shfl_sync(0xffffffffu, mine, 4 * r);
+                asum += av[r];
+            }
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                av[r] = (RPW * warp + r < nreal) ? __fdividef(1.0f, fmaf(kd, bM, rs[r])) : 0.0f;
+                asum += av[r];
+            }
         }
         aN = __fdividef(Mf, kd * (sb + bM));                            // dustbin row: mu_N = M (sinkhorn.py:197-198)
         // ---- column sums: warp partials -> CTA partials -> owners ----
@@ -423,7 +506,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                 t4.z = fmaf(kreg[rr][k].z, av[rr], t4.z); t4.w = fmaf(kreg[rr][k].w, av[rr], t4.w);
             }
 #pragma unroll
-            for (int sr = 0; sr < RR; ++sr) {
+            for (int sr = 0; sr < RS; ++sr) {
                 const float4 ks = sKs4[sr * (MAXM / 4) + 32 * k];
                 t4.x = fmaf(ks.x, av[RR + sr], t4.x); t4.y = fmaf(ks.y, av[RR + sr], t4.y);
                 t4.z = fmaf(ks.z, av[RR + sr], t4.z); t4.w = fmaf(ks.w, av[RR + sr], t4.w);
@@ -432,39 +515,89 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
         }
         if (lane == 0) sAs[warp] = asum;
         bar_all();
+        if constexpr (C::A2A) {
+            // ---- one hop: every CTA sends its partials of ALL columns to every CTA (itself included, so that one mbarrier
+            // covers the lot), then each CTA finishes every b_j itself: same additions in the same order in all CTAs ----
+            if (tid < MAXM / 4) {                                       // four adjacent columns per thread
+                const float4* c4 = reinterpret_cast<const float4*>(sCW) + tid;
+                float4 s0 = c4[0], s1 = c4[MAXM / 4], s2 = c4[2 * (MAXM / 4)], s3 = c4[3 * (MAXM / 4)];
 #pragma unroll
-        for (int cc = 0; cc < MAXM / NT; ++cc) {                        // one column per thread (two at MAXM = 1024)
-            const int col = tid + NT * cc;
-            float s0 = sCW[col], s1 = sCW[MAXM + col], s2 = sCW[2 * MAXM + col], s3 = sCW[3 * MAXM + col];
+                for (int w = 4; w < NW; w += 4) {
+                    const float4 q0 = c4[w * (MAXM / 4)], q1 = c4[(w + 1) * (MAXM / 4)], q2 = c4[(w + 2) * (MAXM / 4)],
+                                 q3 = c4[(w + 3) * (MAXM / 4)];
+                    s0.x += q0.x; s0.y += q0.y; s0.z += q0.z; s0.w += q0.w;
+                    s1.x += q1.x; s1.y += q1.y; s1.z += q1.z; s1.w += q1.w;
+                    s2.x += q2.x; s2.y += q2.y; s2.z += q2.z; s2.w += q2.w;
+                    s3.x += q3.x; s3.y += q3.y; s3.z += q3.z; s3.w += q3.w;
+                }
+                float4 sum;
+                sum.x = (s0.x + s1.x) + (s2.x + s3.x); sum.y = (s0.y + s1.y) + (s2.y + s3.y);
+                sum.z = (s0.z + s1.z) + (s2.z + s3.z); sum.w = (s0.w + s1.w) + (s2.w + s3.w);
+                const uint32_t dst = smem_u32(sX + ((int)xbuf * CL + rank) * C::XSTR + 4 * tid);
 #pragma unroll
-            for (int w = 4; w < NW; w += 4) {
-                s0 += sCW[w * MAXM + col]; s1 += sCW[(w + 1) * MAXM + col];
-                s2 += sCW[(w + 2) * MAXM + col]; s3 += sCW[(w + 3) * MAXM + col];
+                for (int p = 0; p < CL; ++p) st_async_v4(mapa32(dst, (uint32_t)p), sum, mapa32(loc_bar_x, (uint32_t)p));
+            } else if (tid == MAXM / 4) {
+                float as = 0.0f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) as += sAs[w];
+                const uint32_t dst = smem_u32(sX + ((int)xbuf * CL + rank) * C::XSTR + MAXM);
+#pragma unroll
+                for (int p = 0; p < CL; ++p) st_async32(mapa32(dst, (uint32_t)p), kd * as, mapa32(loc_bar_x, (uint32_t)p));
             }
-            const uint32_t owner = (uint32_t)(col / OWN);
-            st_async32(mapa32(my_part + (uint32_t)(col % OWN) * 4u, owner), (s0 + s1) + (s2 + s3), mapa32(loc_bar_part, owner));
-        }
-        if (tid == 0) {
-            float as = 0.0f;
+            mbar_wait(loc_bar_x, xpar);
+            const float* xb = sX + (int)xbuf * CL * C::XSTR;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) as += sAs[w];
-            st_async32(mapa32(my_part + (uint32_t)OWN * 4u, (uint32_t)(CL - 1)), kd * as, mapa32(loc_bar_part, (uint32_t)(CL - 1)));
-        }
-        // ---- owners: b_j = nu_j / colsum_j, sent to every CTA ----
-        mbar_wait(loc_bar_part, par);
-        if (tid < OWN || (tid == OWN && has_dust)) {
-            float t = 0.0f;
+            for (int cc = 0; cc < MAXM / NT; ++cc) {
+                const int col = tid + NT * cc;
+                float t = 0.0f;
 #pragma unroll
-            for (int r = 0; r < CL; ++r) t += sPart[r * PSTR + tid];
-            const int c = tid == OWN ? M : OWN * rank + tid;            // global column (M = dustbin column)
-            t = fmaf(kd, aN, t);
-            const float bnew = (tid == OWN) ? __fdividef(Nf, t) : (c < M ? __fdividef(1.0f, t) : 0.0f);   // nu_M = N (:199-200)
-            const uint32_t slot = (uint32_t)(tid == OWN ? MAXM : c) * 4u;
+                for (int r = 0; r < CL; ++r) t += xb[r * C::XSTR + col];
+                t = fmaf(kd, aN, t);
+                sB[col] = col < M ? __fdividef(1.0f, t) : 0.0f;
+            }
+            if (tid == NT - 1) {
+                float t = 0.0f;
 #pragma unroll
-            for (int dst = 0; dst < CL; ++dst)
-                st_async32(mapa32(loc_b + slot, (uint32_t)dst), bnew, mapa32(loc_bar_b, (uint32_t)dst));
+                for (int r = 0; r < CL; ++r) t += xb[r * C::XSTR + MAXM];
+                t = fmaf(kd, aN, t);
+                sB[MAXM] = __fdividef(Nf, t);                           // nu_M = N (:199-200)
+            }
+            bar_all();
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < MAXM / NT; ++cc) {                    // one column per thread (two at MAXM = 1024)
+                const int col = tid + NT * cc;
+                float s0 = sCW[col], s1 = sCW[MAXM + col], s2 = sCW[2 * MAXM + col], s3 = sCW[3 * MAXM + col];
+#pragma unroll
+                for (int w = 4; w < NW; w += 4) {
+                    s0 += sCW[w * MAXM + col]; s1 += sCW[(w + 1) * MAXM + col];
+                    s2 += sCW[(w + 2) * MAXM + col]; s3 += sCW[(w + 3) * MAXM + col];
+                }
+                const uint32_t owner = (uint32_t)(col / OWN);
+                st_async32(mapa32(my_part + (uint32_t)(col % OWN) * 4u, owner), (s0 + s1) + (s2 + s3), mapa32(loc_bar_part, owner));
+            }
+            if (tid == 0) {
+                float as = 0.0f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) as += sAs[w];
+                st_async32(mapa32(my_part + (uint32_t)OWN * 4u, (uint32_t)(CL - 1)), kd * as, mapa32(loc_bar_part, (uint32_t)(CL - 1)));
+            }
+            // ---- owners: b_j = nu_j / colsum_j, sent to every CTA ----
+            mbar_wait(loc_bar_part, par);
+            if (tid < OWN || (tid == OWN && has_dust)) {
+                float t = 0.0f;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) t += sPart[r * PSTR + tid];
+                const int c = tid == OWN ? M : OWN * rank + tid;        // global column (M = dustbin column)
+                t = fmaf(kd, aN, t);
+                const float bnew = (tid == OWN) ? __fdividef(Nf, t) : (c < M ? __fdividef(1.0f, t) : 0.0f);   // nu_M = N (:199-200)
+                const uint32_t slot = (uint32_t)(tid == OWN ? MAXM : c) * 4u;
+#pragma unroll
+                for (int dst = 0; dst < CL; ++dst)
+                    st_async32(mapa32(loc_b + slot, (uint32_t)dst), bnew, mapa32(loc_bar_b, (uint32_t)dst));
+            }
+            mbar_wait(loc_bar_b, par);
         }
-        mbar_wait(loc_bar_b, par);
     }
     bM = sB[MAXM];
     HY_STAMP(5);
@@ -508,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
         // ======== fused epilogue: filters (sinkhorn.py:311-465), scores (:211-259), mutual matches (match_extraction.py:46-184)
         // on the P values while they are on the chip.  P itself is written only when the caller wants it.
         const SinkhornEpilogue& e = a.e;
-        const uint32_t epar = (uint32_t)(a.iterations & 1);             // phase of bars[5] / bars[6] after the loop
+        const uint32_t epar = C::A2A ? 0u : (uint32_t)(a.iterations & 1);   // phase of bars[5] / bars[6] after the loop
         // CTA-local tables reuse b and the partial table (idle once the iterations are over and P has been formed); the
         // tables that PEERS write into have their own space: a faster peer may send while this CTA still forms its P rows
         float* eColBest = sB;                                           // [MAXM] CTA-level column maxima
@@ -733,10 +866,10 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
 }
 
-template <int CL, int MAXM, bool EPI>
+template <int CL, int MAXM, int RRT, bool EPI>
 int launch_hy(const HyArgs& a, int B, cudaStream_t st) {
-    using C = Hy<CL, MAXM>;
-    auto kern = sinkhorn_hy_kernel<CL, MAXM, EPI>;
+    using C = Hy<CL, MAXM, RRT>;
+    auto kern = sinkhorn_hy_kernel<CL, MAXM, RRT, EPI>;
     const size_t smem = (size_t)C::SMEM_FLOATS * sizeof(float);
     OM_TRY(set_smem(kern, smem));
     if (CL > 8) OM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -815,8 +948,8 @@ int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, in
     a.dustbin2 = (float)((-(double)unused / (double)eps) * log2e);
     const bool epi = e != nullptr && e->any();
     if (epi) a.e = *e;
-    if (CLv == 4) return epi ? launch_hy<4, 512, true>(a, B, st) : launch_hy<4, 512, false>(a, B, st);
-    return epi ? launch_hy<16, 1024, true>(a, B, st) : launch_hy<16, 1024, false>(a, B, st);
+    if (CLv == 4) return epi ? launch_hy<4, 512, HY_RR4, true>(a, B, st) : launch_hy<4, 512, HY_RR4, false>(a, B, st);
+    return epi ? launch_hy<16, 1024, 2, true>(a, B, st) : launch_hy<16, 1024, 2, false>(a, B, st);
 }
 
 }  // namespace om
