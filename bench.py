@@ -286,7 +286,7 @@ def per_kernel_times(model, workload, i1, i2, steps, warmup):
     def sk():
         nat.check(lib.om_sinkhorn_f32(ptr(desc), ptr(d2), B, Kk, Kk, Pn, m.iterations, float(m.epsilon),
                                       float(m.unused_score), 0, ptr(probs), ptr(sws), sws.numel(), sp), "om_sinkhorn_f32")
-    name = "sinkhorn_hy_kernel(+pack_f16_kernel x2)" if Kk <= 512 else "sinkhorn_generic_kernels(cost_tc+xd_row/xd_col x iterations)"
+    name = "sinkhorn_hy_kernel" if Kk <= 1024 else "sinkhorn_generic_kernels(cost_tc+xd_row/xd_col x iterations)"
     out[name] = dict(ms=event_time_ms(sk, steps, warmup, st), per_step=1, stage="sinkhorn",
                      bytes=B * (2 * Kk * Pn * 4 + (Kk + 1) * (Kk + 1) * 4),
                      flops=B * (2.0 * Kk * Kk * Pn + 2.0 * m.iterations * 2 * (Kk + 1) * (Kk + 1)))

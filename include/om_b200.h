@@ -61,6 +61,8 @@ extern "C" {
 #define OM_MATCH_SPARSE 0    /* feature_detection/shi_tomasi_sparse_bad_sinkhorn.py:134-182 */
 #define OM_MATCH_ANGLE 1     /* feature_detection/shi_tomasi_angle_sparse_bad_sinkhorn.py:132-180 */
 #define OM_MATCH_DENSE 2     /* feature_detection/shi_tomasi_bad_sinkhorn.py:162-219 */
+#define OM_MATCH_MAPS 3      /* score (and orientation) maps come from the caller's own detector, everything after them is
+                              * this library's: feature_detection/akaze_sparse_bad_sinkhorn.py:148-196 (om_match_pairs_from_maps_f32) */
 
 int om_version(void);
 /* The library links its own (static) CUDA runtime: select the device the caller's pointers and
@@ -101,6 +103,24 @@ int om_detect_f32(const float* image, int B, int H, int W, int block_size, int n
                   int border_margin, float score_threshold, int K,
                   float* score_map, float* kpts, float* kpt_scores,
                   void* ws, size_t ws_bytes, void* stream);
+
+/* Fused apply_nms_maxpool + select_topk_keypoints on a CALLER's score map (utils/keypoint_utils.py:12-117 as called at
+ * feature_detection/akaze_sparse_bad_sinkhorn.py:155-170): the NMS mask is never materialised.  scores (B,H,W) >= 0.
+ * Workspace: om_topk_workspace_bytes. */
+int om_detect_from_scores_f32(const float* scores, int B, int H, int W, int nms_radius, int border_margin,
+                              float score_threshold, int K, float* kpts, float* kpt_scores,
+                              void* ws, size_t ws_bytes, void* stream);
+
+/* ---- ingest -------------------------------------------------------------------------------- */
+
+/* The real callers' preprocessing in one kernel (sample/visual_odometry.py:65-92 load_image_from_array: cv2.cvtColor(BGR2GRAY),
+ * cv2.resize(INTER_LINEAR), astype(float32)): src is (B,Hin,Win,channels) uint8, channels 3 (B,G,R interleaved) or 1; the grey
+ * value is OpenCV's 15-bit fixed-point luma, the resize is OpenCV's 11-bit fixed-point bilinear (same coordinates, same
+ * coefficient rounding, same border rules, its vector-path final rounding: identical to cv2 4.13 on every size tried).  dst_u8 (B,Hout,Wout) and / or dst_f32 (B,Hout,Wout) receive the
+ * result (either may be NULL, not both); the uint8 form feeds om_match_pairs (OM_IMAGE_U8) directly.  Same size in and
+ * out copies (cv2.resize does).  No workspace. */
+int om_preprocess_u8(const unsigned char* src, int B, int Hin, int Win, int channels, int Hout, int Wout,
+                     unsigned char* dst_u8, float* dst_f32, void* stream);
 
 /* ---- orientation ------------------------------------------------------------------------- */
 
@@ -280,6 +300,16 @@ int om_match_pairs_ex(const om_match_params* p, const void* image1, const void* 
                       const float* pair_table, const float* moment_kernels,
                       float* kpts1, float* kpts2, float* desc1, float* desc2,
                       const om_sinkhorn_outputs* out, void* ws, size_t ws_bytes, void* stream);
+
+/* OM_MATCH_MAPS: the matcher behind another detector.  scores1/2 (B,H,W) are that detector's score maps, orient1/2 (B,H,W)
+ * its orientation maps in radians (both NULL: non-oriented descriptors); NMS + top-k, (oriented) sparse BAD at the keypoints
+ * (descriptor/bad.py:487-517 samples the orientation map at the keypoint) and Sinkhorn run here, as in
+ * feature_detection/akaze_sparse_bad_sinkhorn.py:148-196.  p->flavour must be OM_MATCH_MAPS, p->image_dtype OM_IMAGE_F32;
+ * p->block_size / patch_size are ignored.  Workspace: om_match_workspace_bytes(p). */
+int om_match_pairs_from_maps_f32(const om_match_params* p, const float* image1, const float* image2,
+                                 const float* scores1, const float* scores2, const float* orient1, const float* orient2,
+                                 const float* pair_table, float* kpts1, float* kpts2, float* probs /* B,K+1,K+1 */,
+                                 float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream);
 
 /* om_detect_f32 on uint8 images (block 3 / 5 with NMS radius 3 read the bytes natively, other routings widen first). */
 int om_detect_u8(const unsigned char* image, int B, int H, int W, int block_size, int nms_radius,

@@ -4,7 +4,7 @@ feature_detection}).  All arithmetic runs in hand-written sm_100a CUDA kernels i
 _lib/libom_b200.so, reached through the C ABI of include/om_b200.h.  No CPU path exists.
 """
 from . import _native  # noqa: F401
-from .detector import ShiTomasiScore
+from .detector import ShiTomasiScore, AKAZE
 from .descriptor import BADDescriptor, SparseBAD
 from .orientation import AngleEstimator
 from .matching import SinkhornMatcher, SinkhornMatcherWithScores, SinkhornMatcherWithFilters, MutualNearestNeighborMatcher
@@ -21,7 +21,9 @@ from .feature_detection import (
     ShiTomasiAngleSparseBADSinkhornMatcherWithFilters,
     MatchExtractionWrapper,
     ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix,
+    AKAZESparseBADSinkhornMatcher,
 )
+from .ingest import FrameIngest, load_image_from_array
 
 __all__ = [
     "ShiTomasiScore", "BADDescriptor", "SparseBAD", "AngleEstimator", "SinkhornMatcher",
@@ -30,5 +32,6 @@ __all__ = [
     "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector", "ShiTomasiAngleSparseBADSinkhornMatcher",
     "MutualNearestNeighborMatcher", "MatchExtractionWrapper", "SinkhornMatcherWithFilters",
     "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters", "EssentialMatrixEstimator",
-    "ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix",
+    "ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix", "AKAZE", "AKAZESparseBADSinkhornMatcher", "FrameIngest",
+    "load_image_from_array",
 ]

@@ -51,6 +51,12 @@ SIGNATURES = {
                                    c_void_p, c_size_t, c_void_p]),
     "om_detect_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size_t, c_void_p]),
+    "om_detect_from_scores_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_size_t, c_void_p]),
+    "om_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "om_match_pairs_from_maps_f32": (c_int, [POINTER(MatchParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_void_p]),
     "om_angle_map_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "om_sparse_bad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "om_sparse_bad_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_float,

@@ -17,7 +17,7 @@ from . import _native as nat
 DESC_RAW, DESC_SOFT, DESC_HARD = 0, 1, 2
 SAMPLE_NEAREST, SAMPLE_BILINEAR = 0, 1
 THETA_NONE, THETA_MAP, THETA_MOMENTS = 0, 1, 2
-MATCH_SPARSE, MATCH_ANGLE, MATCH_DENSE = 0, 1, 2
+MATCH_SPARSE, MATCH_ANGLE, MATCH_DENSE, MATCH_MAPS = 0, 1, 2, 3
 
 
 def desc_mode(binarize: bool, soft_binarize: bool) -> int:
@@ -460,6 +460,108 @@ def essential_matrix(probs: torch.Tensor, pts1: torch.Tensor, pts2: torch.Tensor
 @essential_matrix.register_fake
 def _(probs, pts1, pts2, valid1, valid2, top_k, n_iter, n_iter_manifold):
     return probs.new_empty((probs.shape[0], 3, 3), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200match::detect_from_scores", mutates_args=(), device_types="cuda")
+def detect_from_scores(scores: torch.Tensor, max_keypoints: int, nms_radius: int, score_threshold: float,
+                       border_margin: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """apply_nms_maxpool + select_topk_keypoints on a caller's score map in one call, no mask array
+    (feature_detection/akaze_sparse_bad_sinkhorn.py:155-170)."""
+    sc, B, H, W = _images(scores, "scores")
+    if max_keypoints > H * W:
+        raise RuntimeError("selected index k out of range")
+    lib, st = _begin(sc)
+    K = max_keypoints
+    kpts = torch.empty((B, K, 2), dtype=torch.float32, device=sc.device)
+    ks = torch.empty((B, K), dtype=torch.float32, device=sc.device)
+    ws = _ws(lib.om_topk_workspace_bytes(B, H, W, K), sc)
+    nat.check(lib.om_detect_from_scores_f32(_p(sc), B, H, W, nms_radius, int(border_margin), float(score_threshold), K,
+                                            _p(kpts), _p(ks), _p(ws), ws.numel(), st), "om_detect_from_scores_f32")
+    return kpts, ks
+
+
+@detect_from_scores.register_fake
+def _(scores, max_keypoints, nms_radius, score_threshold, border_margin):
+    B = scores.shape[0]
+    return (scores.new_empty((B, max_keypoints, 2), dtype=torch.float32),
+            scores.new_empty((B, max_keypoints), dtype=torch.float32))
+
+
+@torch.library.custom_op("b200match::preprocess_u8", mutates_args=(), device_types="cuda")
+def preprocess_u8(frames: torch.Tensor, height: int, width: int, as_float: bool) -> torch.Tensor:
+    """Camera frames (B,Hin,Win,3) BGR or (B,Hin,Win[,1]) grey, uint8 -> (B,1,height,width) grey model input, uint8 or
+    float32 (sample/visual_odometry.py:65-92: cv2.cvtColor + cv2.resize(INTER_LINEAR) + astype(float32)), one kernel."""
+    if not frames.is_cuda or frames.dtype != torch.uint8:
+        raise RuntimeError("frames must be a CUDA uint8 tensor: onnx_image_processing_b200 has no CPU path")
+    if frames.dim() == 3:
+        frames = frames.unsqueeze(-1)
+    if frames.dim() != 4 or frames.shape[-1] not in (1, 3):
+        raise RuntimeError(f"frames: expected (B,H,W,3), (B,H,W,1) or (B,H,W), got {tuple(frames.shape)}")
+    f = frames.contiguous()
+    B, Hin, Win, C = f.shape
+    lib, st = _begin(f)
+    out = torch.empty((B, 1, height, width), dtype=torch.float32 if as_float else torch.uint8, device=f.device)
+    nat.check(lib.om_preprocess_u8(_p(f), B, Hin, Win, C, height, width, _p(None if as_float else out),
+                                   _p(out if as_float else None), st), "om_preprocess_u8")
+    return out
+
+
+@preprocess_u8.register_fake
+def _(frames, height, width, as_float):
+    return frames.new_empty((frames.shape[0], 1, height, width), dtype=torch.float32 if as_float else torch.uint8)
+
+
+@torch.library.custom_op("b200match::match_pairs_from_maps", mutates_args=(), device_types="cuda")
+def match_pairs_from_maps(image1: torch.Tensor, image2: torch.Tensor, scores1: torch.Tensor, scores2: torch.Tensor,
+                          orient1: Optional[torch.Tensor], orient2: Optional[torch.Tensor], pair_table: torch.Tensor,
+                          max_keypoints: int, nms_radius: int, border_margin: int, score_threshold: float, mode: int,
+                          temperature: float, normalize: bool, sampling: int, iterations: int, epsilon: float,
+                          unused_score: float, distance_l1: bool
+                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The matcher behind another detector (om_match_pairs_from_maps_f32): score / orientation maps in, (kpts1, kpts2, probs,
+    desc1, desc2) out -- NMS, top-k, oriented sparse BAD and Sinkhorn in one C call."""
+    i1, B, H, W = _images(image1, "image1")
+    i2, B2, H2, W2 = _images(image2, "image2")
+    s1, Bs, Hs, Ws = _images(scores1, "scores1")
+    s2, Bt, Ht, Wt = _images(scores2, "scores2")
+    if not ((B, H, W) == (B2, H2, W2) == (Bs, Hs, Ws) == (Bt, Ht, Wt)):
+        raise RuntimeError("images and score maps must have the same shape")
+    if (orient1 is None) != (orient2 is None):
+        raise RuntimeError("orientation maps: give both or neither")
+    o1 = _images(orient1, "orient1")[0] if orient1 is not None else None
+    o2 = _images(orient2, "orient2")[0] if orient2 is not None else None
+    K = max_keypoints
+    if K > H * W:
+        raise RuntimeError("selected index k out of range")
+    tb = _f32(pair_table, "pair_table")
+    P = int(tb.shape[0])
+    lib, st = _begin(i1)
+    prm = make_match_params(MATCH_MAPS, B, H, W, K, 1, nms_radius, border_margin, score_threshold, P, mode, temperature,
+                            normalize, sampling, 0, iterations, epsilon, unused_score, distance_l1, 0)
+    dev = i1.device
+    k1 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    k2 = torch.empty((B, K, 2), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, K + 1, K + 1), dtype=torch.float32, device=dev)
+    d1 = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+    d2 = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+    nbytes = lib.om_match_workspace_bytes(ctypes.byref(prm))
+    if nbytes == 0:
+        raise RuntimeError("om_match_workspace_bytes rejected the parameters")
+    ws = _ws(nbytes, i1)
+    nat.check(lib.om_match_pairs_from_maps_f32(ctypes.byref(prm), _p(i1), _p(i2), _p(s1), _p(s2), _p(o1), _p(o2), _p(tb),
+                                               _p(k1), _p(k2), _p(probs), _p(d1), _p(d2), _p(ws), ws.numel(), st),
+              "om_match_pairs_from_maps_f32")
+    return k1, k2, probs, d1, d2
+
+
+@match_pairs_from_maps.register_fake
+def _(image1, image2, scores1, scores2, orient1, orient2, pair_table, max_keypoints, nms_radius, border_margin,
+      score_threshold, mode, temperature, normalize, sampling, iterations, epsilon, unused_score, distance_l1):
+    B, K, P = image1.shape[0], max_keypoints, pair_table.shape[0]
+    f = dict(dtype=torch.float32)
+    return (image1.new_empty((B, K, 2), **f), image1.new_empty((B, K, 2), **f),
+            image1.new_empty((B, K + 1, K + 1), **f), image1.new_empty((B, K, P), **f),
+            image1.new_empty((B, K, P), **f))
 
 
 def make_match_params(flavour: int, B: int, H: int, W: int, K: int, block_size: int, nms_radius: int,

@@ -144,12 +144,13 @@ int side_set_for(int device, cudaStream_t owner, SideSet** out) {
 // Everything a stage launcher would reject is rejected HERE, before any work is forked onto side streams
 int check_params(const om_match_params* p) {
     if (p == nullptr) return OM_ERR_NULL;
-    if (p->flavour < OM_MATCH_SPARSE || p->flavour > OM_MATCH_DENSE) return OM_ERR_PARAM;
+    if (p->flavour < OM_MATCH_SPARSE || p->flavour > OM_MATCH_MAPS) return OM_ERR_PARAM;
     if (p->B <= 0 || p->H <= 1 || p->W <= 1 || p->K <= 0) return OM_ERR_SHAPE;
     if ((long long)p->K > (long long)p->H * p->W) return OM_ERR_SHAPE;   // torch.topk raises too
     if ((long long)p->H * p->W >= (1ll << 31) || p->B > 65535 || p->K > OM_MAX_K) return OM_ERR_LIMIT;
     if (p->P != 256 && p->P != 512) return OM_ERR_PARAM;                 // descriptor/bad.py:385-388
-    if (p->block_size < 1 || p->block_size % 2 == 0 || p->block_size / 2 > OM_MAX_BLOCK_HALF) return OM_ERR_PARAM;
+    if (p->flavour != OM_MATCH_MAPS && (p->block_size < 1 || p->block_size % 2 == 0 || p->block_size / 2 > OM_MAX_BLOCK_HALF))
+        return OM_ERR_PARAM;
     if (p->nms_radius < 0 || p->nms_radius > OM_MAX_NMS_RADIUS) return OM_ERR_PARAM;
     if (p->desc_mode < OM_DESC_RAW || p->desc_mode > OM_DESC_HARD) return OM_ERR_PARAM;
     if (p->flavour != OM_MATCH_DENSE && p->sampling_mode != OM_SAMPLE_NEAREST && p->sampling_mode != OM_SAMPLE_BILINEAR)
@@ -157,6 +158,7 @@ int check_params(const om_match_params* p) {
     if (p->flavour == OM_MATCH_ANGLE && (p->patch_size < 1 || p->patch_size % 2 == 0 || p->patch_size > 31)) return OM_ERR_PARAM;
     if (p->iterations <= 0 || !(p->epsilon > 0.0f)) return OM_ERR_PARAM;  // matching/sinkhorn.py:66-69
     if (p->image_dtype != OM_IMAGE_F32 && p->image_dtype != OM_IMAGE_U8) return OM_ERR_PARAM;
+    if (p->flavour == OM_MATCH_MAPS && p->image_dtype != OM_IMAGE_F32) return OM_ERR_PARAM;
     return OM_OK;
 }
 
@@ -173,7 +175,8 @@ MatchWs plan(const om_match_params* p, void* base, bool ex = false) {
     w.dense_bytes = p->flavour == OM_MATCH_DENSE
                         ? dense_bad_workspace_bytes(p->B, p->H, p->W)
                         : sparse_bad_workspace_bytes(p->B, p->H, p->W,
-                                                     p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE);
+                                                     p->flavour == OM_MATCH_ANGLE || p->flavour == OM_MATCH_MAPS ? OM_THETA_MOMENTS
+                                                                                                              : OM_THETA_NONE);
     w.dense[0] = c + off; off += align_up(w.dense_bytes);
     w.dense[1] = c + off; off += align_up(w.dense_bytes);
     w.sink_bytes = ex ? sinkhorn_ex_workspace_bytes(p->B, p->K, p->K, p->P) : sinkhorn_workspace_bytes(p->B, p->K, p->K, p->P);
@@ -210,9 +213,25 @@ extern "C" int om_match_pairs_f32(const om_match_params* p, const float* image1,
 }
 
 namespace {
+struct MatchMaps {                  // OM_MATCH_MAPS: the caller's detector outputs
+    const float* scores[2];
+    const float* orient[2];         // both null: non-oriented descriptors
+};
 int match_pairs_impl(const om_match_params* p, const void* image1, const void* image2, const float* pair_table,
                      const float* moment_kernels, float* kpts1, float* kpts2, float* probs, float* desc1, float* desc2,
-                     const SinkhornEpilogue* epi, void* ws, size_t ws_bytes, void* stream);
+                     const SinkhornEpilogue* epi, void* ws, size_t ws_bytes, void* stream, const MatchMaps* maps = nullptr);
+}
+
+extern "C" int om_match_pairs_from_maps_f32(const om_match_params* p, const float* image1, const float* image2,
+                                            const float* scores1, const float* scores2, const float* orient1,
+                                            const float* orient2, const float* pair_table, float* kpts1, float* kpts2,
+                                            float* probs, float* desc1, float* desc2, void* ws, size_t ws_bytes, void* stream) {
+    if (p == nullptr || probs == nullptr || scores1 == nullptr || scores2 == nullptr) return OM_ERR_NULL;
+    if (p->flavour != OM_MATCH_MAPS) return OM_ERR_PARAM;
+    if ((orient1 == nullptr) != (orient2 == nullptr)) return OM_ERR_NULL;
+    const MatchMaps maps{{scores1, scores2}, {orient1, orient2}};
+    return match_pairs_impl(p, image1, image2, pair_table, nullptr, kpts1, kpts2, probs, desc1, desc2, nullptr, ws, ws_bytes,
+                            stream, &maps);
 }
 
 extern "C" int om_match_pairs(const om_match_params* p, const void* image1, const void* image2,
@@ -243,9 +262,10 @@ extern "C" int om_match_pairs_ex(const om_match_params* p, const void* image1, c
 namespace {
 int match_pairs_impl(const om_match_params* p, const void* image1, const void* image2, const float* pair_table,
                      const float* moment_kernels, float* kpts1, float* kpts2, float* probs, float* desc1, float* desc2,
-                     const SinkhornEpilogue* epi, void* ws, size_t ws_bytes, void* stream) {
+                     const SinkhornEpilogue* epi, void* ws, size_t ws_bytes, void* stream, const MatchMaps* maps) {
     OM_ON_DEVICE_OF(image1);
     OM_TRY(check_params(p));
+    if ((p->flavour == OM_MATCH_MAPS) != (maps != nullptr)) return OM_ERR_PARAM;
     if (image1 == nullptr || image2 == nullptr || pair_table == nullptr || kpts1 == nullptr || kpts2 == nullptr) return OM_ERR_NULL;
     if (p->flavour == OM_MATCH_ANGLE && moment_kernels == nullptr) return OM_ERR_NULL;
     const bool ex = epi != nullptr;
@@ -281,10 +301,11 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
         if (p->flavour == OM_MATCH_DENSE)
             return dense_bad_at_kpts_launch(images[s], u8, p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode,
                                             p->temperature, p->normalize, ds[s], w.dense[s], w.dense_bytes, q, phase);
-        const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS : OM_THETA_NONE;
+        const int theta = p->flavour == OM_MATCH_ANGLE ? OM_THETA_MOMENTS
+                          : (maps != nullptr && maps->orient[s] != nullptr ? OM_THETA_MAP : OM_THETA_NONE);
         return sparse_bad_launch(images[s], u8, p->B, p->H, p->W, kp[s], p->K, pair_table, p->P, p->desc_mode, p->temperature,
-                                 p->normalize, p->sampling_mode, theta, nullptr, moment_kernels, p->patch_size, ds[s],
-                                 w.dense[s], w.dense_bytes, q, phase);
+                                 p->normalize, p->sampling_mode, theta, maps != nullptr ? maps->orient[s] : nullptr, moment_kernels,
+                                 p->patch_size, ds[s], w.dense[s], w.dense_bytes, q, phase);
     };
     // the forked part: whatever it returns, the side streams are joined back below (an unjoined fork would leave side work
     // running on a workspace the caller may free, and would invalidate a stream capture)
@@ -298,7 +319,10 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
         }
         for (int s = 0; s < 2; ++s) {
             // keypoint scores are discarded by the matcher modules (`keypoints1, _ = ...`)
-            OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
+            if (maps != nullptr)
+                OM_TRY(detect_scores_launch(maps->scores[s], dc, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
+            else
+                OM_TRY(detect_launch(images[s], dc, nullptr, kp[s], nullptr, w.detect[s], w.detect_bytes, chain[s]));
             if (ns == 4) {
                 OM_CUDA(cudaStreamWaitEvent(chain[s], set->pre[s], 0));
                 OM_TRY(descriptors(s, chain[s], 2));

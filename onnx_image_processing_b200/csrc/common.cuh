@@ -138,6 +138,10 @@ size_t topk_workspace_bytes(int B, int H, int W, int K);
 int detect_launch(const void* image, const DetectCfg& c, float* score_map, float* kpts, float* kpt_scores,
                   void* ws, size_t ws_bytes, cudaStream_t st);
 
+// NMS + top-k on a caller's score map (cfg.block_size / image_u8 unused)
+int detect_scores_launch(const float* scores, const DetectCfg& c, float* kpts, float* kpt_scores, void* ws, size_t ws_bytes,
+                         cudaStream_t st);
+
 size_t sparse_bad_workspace_bytes(int B, int H, int W, int theta_mode);
 int sparse_bad_launch(const void* image, int image_u8, int B, int H, int W, const float* kpts, int K, const float* pair_table,
                       int P, int desc_mode, float temperature, int normalize, int sampling_mode, int theta_mode,

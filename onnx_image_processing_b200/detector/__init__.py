@@ -1,3 +1,4 @@
 from .shi_tomasi import ShiTomasiScore
+from .akaze import AKAZE
 
-__all__ = ["ShiTomasiScore"]
+__all__ = ["ShiTomasiScore", "AKAZE"]

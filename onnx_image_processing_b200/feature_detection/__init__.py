@@ -6,10 +6,11 @@ from .shi_tomasi_angle_sparse_bad_sinkhorn import (ShiTomasiAngleSparseBADSinkho
                                                    ShiTomasiAngleSparseBADSinkhornMatcherWithFilters)
 from .shi_tomasi_angle_sparse_bad_sinkhorn_essential_matrix import ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix
 from .match_extraction_wrapper import MatchExtractionWrapper
+from .akaze_sparse_bad_sinkhorn import AKAZESparseBADSinkhornMatcher
 
 __all__ = [
     "ShiTomasiBADDetector", "ShiTomasiBADSinkhornMatcher", "ShiTomasiSparseBADSinkhornMatcher",
     "ShiTomasiWithAngle", "ShiTomasiAngleSparseBAD", "ShiTomasiAngleSparseBADDetector",
     "ShiTomasiAngleSparseBADSinkhornMatcher", "ShiTomasiAngleSparseBADSinkhornMatcherWithFilters",
-    "MatchExtractionWrapper", "ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix",
+    "MatchExtractionWrapper", "ShiTomasiAngleSparseBADSinkhornWithEssentialMatrix", "AKAZESparseBADSinkhornMatcher",
 ]

@@ -509,6 +509,97 @@ def dense_matcher(image1, image2, max_keypoints, block_size=3, num_pairs=256, bi
 # --------------------------------------------------------------------------------------
 # synthetic inputs shared by tests and bench (integer-valued [0,255] so scores are order-exact)
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# f4: the matcher behind another detector (feature_detection/akaze_sparse_bad_sinkhorn.py:148-196) and the callers' ingest
+# --------------------------------------------------------------------------------------
+def akaze_maps(image, num_scales=3, diffusion_iterations=3, kappa=0.05, threshold=0.001, nms_size=5, patch_size=15, sigma=2.5):
+    """detector/akaze.py:331-453 with its parts (:25-134 diffusion, :137-263 Hessian response, :266-328 orientation): the
+    same ATen operators in the same order -> (scores, orientations), both (B,1,H,W)."""
+    def k3(rows, scale):
+        return (torch.tensor(rows, dtype=torch.float32).view(1, 1, 3, 3)) / scale
+    sobel = torch.cat([k3([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], 8.0), k3([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], 8.0)], dim=0)
+    hess = torch.cat([k3([[1, -2, 1], [2, -4, 2], [1, -2, 1]], 16.0), k3([[1, 2, 1], [-2, -4, -2], [1, 2, 1]], 16.0),
+                      k3([[1, 0, -1], [0, 0, 0], [-1, 0, 1]], 4.0)], dim=0)
+    mk = moment_kernels(patch_size, sigma)
+    cur, ss, oo = image, [], []
+    for _ in range(num_scales):
+        for _ in range(diffusion_iterations):                                    # akaze.py:110-132
+            g = F.conv2d(cur, sobel, padding=1)
+            mag = torch.sqrt((g * g).sum(dim=1, keepdim=True) + 1e-8)
+            c = 1.0 / (1.0 + (mag / kappa) ** 2)
+            div = F.conv2d(c * g, sobel, padding=1, groups=2).sum(dim=1, keepdim=True)
+            cur = cur + 0.25 * div
+        h = F.conv2d(cur, hess, padding=1)                                       # :196-205
+        resp = h[:, 0:1] * h[:, 1:2] - h[:, 2:3] * h[:, 2:3]
+        mx = F.max_pool2d(resp, kernel_size=nms_size, stride=1, padding=nms_size // 2)
+        ss.append(torch.clamp(resp * ((resp == mx).float() * (resp > threshold).float()), min=0.0))   # :231-263
+        m = F.conv2d(cur, mk, padding=patch_size // 2)
+        oo.append(torch.atan2(m[:, 1:2], m[:, 0:1]))
+    ss, oo = torch.stack(ss, dim=0), torch.stack(oo, dim=0)
+    scores = ss.amax(dim=0)                                                      # :436-449
+    mask = (ss == scores.unsqueeze(0)).float()
+    mask = mask / mask.sum(dim=0, keepdim=True).clamp(min=1.0)
+    return scores, (oo * mask).sum(dim=0)
+
+
+def maps_matcher(image1, image2, scores1, scores2, orient1, orient2, max_keypoints, num_pairs=256, binarize=False,
+                 soft_binarize=True, temperature=10.0, sinkhorn_iterations=20, epsilon=1.0, unused_score=1.0,
+                 distance_type="l2", nms_radius=3, score_threshold=0.0, normalize_descriptors=True, sampling_mode="nearest",
+                 border_margin=None, return_descriptors=False):
+    """feature_detection/akaze_sparse_bad_sinkhorn.py:155-196 from the detector's maps on."""
+    margin = 7 if border_margin is None else border_margin
+    s1, s2 = scores1.squeeze(1), scores2.squeeze(1)
+    k1, _ = select_topk(s1, nms_mask(s1, nms_radius), max_keypoints, score_threshold, margin)
+    k2, _ = select_topk(s2, nms_mask(s2, nms_radius), max_keypoints, score_threshold, margin)
+    kw = dict(num_pairs=num_pairs, binarize=binarize, soft_binarize=soft_binarize, temperature=temperature,
+              normalize_descriptors=normalize_descriptors, sampling_mode=sampling_mode)
+    d1 = sparse_bad(image1, k1, orient1, **kw)
+    d2 = sparse_bad(image2, k2, orient2, **kw)
+    p = sinkhorn(d1, d2, sinkhorn_iterations, epsilon, unused_score, distance_type)
+    return (k1, k2, p, d1, d2) if return_descriptors else (k1, k2, p)
+
+
+def bgr_to_gray_u8(frame: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) on uint8 (sample/visual_odometry.py:83): OpenCV's 15-bit fixed-point luma."""
+    b, g, r = (frame[..., i].astype(np.int64) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def _linear_coefficients(n_out: int, n_in: int, clamp_weight: bool):
+    """source index and 11-bit weights per output coordinate.  Horizontally OpenCV moves out-of-range positions to the border
+    pixel with weight 0 (clamp_weight); vertically it keeps the fractional weight and only clips the two row indices."""
+    scale = 1.0 / (n_out / n_in)                                                 # cv::resize: inv_scale in double, then 1 / it
+    f = ((np.arange(n_out) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp_weight:
+        lo, hi = s < 0, s >= n_in - 1
+        f[lo], s[lo] = 0, 0
+        f[hi], s[hi] = 0, n_in - 1
+    w0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int64)      # cvRound: half to even
+    w1 = np.rint(f * np.float32(2048)).astype(np.int64)
+    return s, w0, w1
+
+
+def resize_linear_u8(gray: np.ndarray, height: int, width: int) -> np.ndarray:
+    """cv2.resize(gray, (width, height), interpolation=cv2.INTER_LINEAR) on uint8 (sample/visual_odometry.py:88): 11-bit
+    fixed-point weights, 32-bit horizontal pass, the vector path's vertical pass."""
+    h, w = gray.shape
+    sx, ax0, ax1 = _linear_coefficients(width, w, True)
+    sy, ay0, ay1 = _linear_coefficients(height, h, False)
+    S = gray.astype(np.int64)
+    rows = S[:, sx] * ax0 + S[:, np.minimum(sx + 1, w - 1)] * ax1
+    S0, S1 = rows[np.clip(sy, 0, h - 1)], rows[np.clip(sy + 1, 0, h - 1)]
+    out = (((ay0[:, None] * (S0 >> 4)) >> 16) + ((ay1[:, None] * (S1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def load_image_from_array(image: np.ndarray, height: int, width: int) -> np.ndarray:
+    """sample/visual_odometry.py:65-92: (H,W,3) BGR or (H,W) uint8 -> (1,1,height,width) float32 in [0,255]."""
+    gray = bgr_to_gray_u8(image) if image.ndim == 3 else image
+    return resize_linear_u8(gray, height, width).astype(np.float32)[np.newaxis, np.newaxis]
+
+
 def texture_images(batch: int, H: int, W: int, seed: int = 0, shift=(3, 5)):
     """Family T: smooth random texture + fine noise, min-max to [0,255], rounded; image2 = roll(image1)."""
     g = torch.Generator().manual_seed(seed)

@@ -1169,3 +1169,71 @@ def test_match_extraction_wrapper_fused_equals_stored_p(flavour):
     assert int(got[3].sum()) > 20
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# the matcher behind another detector (AKAZE) and the camera-frame ingest
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.names("akaze"))
+def test_matcher_from_maps_golden(name):
+    """Reference AKAZE maps in -> NMS, top-k, orientation-aware sparse BAD, Sinkhorn in one C call -> the reference's outputs."""
+    g = G.load(name)
+    model = om.AKAZESparseBADSinkhornMatcher(g["K"], **g["kwargs"]).to(DEV).eval()
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = model.match_from_maps(*_cuda(g["image1"], g["image2"], g["scores1"], g["scores2"], g["orient1"],
+                                                         g["orient2"]))
+        kk, ks = _ops.detect_from_scores(g["scores1"].to(DEV), g["K"], model.nms_radius, float(model.score_threshold),
+                                         int(model.border_margin))
+    assert PR.keypoint_mismatches(kk, g["kpts1"], g["kscores1"]) == 0 and torch.equal(ks.cpu(), g["kscores1"])
+    m = _check_matcher(g, k1, k2, p, d1, d2, desc_rows=ORIENTED_ROWS_MIN)
+    assert PR.probs_ok(m), m
+
+
+def test_akaze_matcher_module_end_to_end():
+    """The module with its own map detector (torch operators on the GPU): float-valued score maps differ from the CPU
+    reference's in the last bits (cuDNN vs oneDNN summation order), so keypoints are compared as sets; matched against
+    the oracle run on the module's OWN maps everything must agree to the usual tolerances."""
+    g = G.load("akaze_small_default")
+    model = om.AKAZESparseBADSinkhornMatcher(g["K"]).to(DEV).eval()
+    i1, i2 = _cuda(g["image1"], g["image2"])
+    with torch.no_grad():
+        k1, k2, p = model(i1, i2)
+        s1, o1 = model.detector(i1)
+        s2, o2 = model.detector(i2)
+    ref = {tuple(v) for v in g["kpts1"][0].tolist()}
+    got = {tuple(v) for v in k1[0].cpu().tolist()}
+    assert len(ref & got) >= 0.9 * len(ref)
+    rk1, rk2, rp = O.maps_matcher(g["image1"], g["image2"], s1.cpu(), s2.cpu(), o1.cpu(), o2.cpu(), g["K"])
+    assert PR.keypoint_mismatches(k1, rk1) == 0 and PR.keypoint_mismatches(k2, rk2) == 0
+    pm = PR.prob_metrics(p, rp)
+    assert PR.probs_ok(pm), pm
+
+
+@pytest.mark.parametrize("name", G.names("ingest"))
+def test_frame_ingest_golden(name):
+    g = G.load(name)
+    frame = g["frame"].to(DEV)
+    ref = g["out"]
+    as_f32 = om.load_image_from_array(frame, g["height"], g["width"]).cpu()
+    as_u8 = om.FrameIngest(g["height"], g["width"])(frame.unsqueeze(0)).cpu()
+    assert as_f32.dtype == torch.float32 and as_u8.dtype == torch.uint8 and as_f32.shape == ref.shape
+    assert torch.equal(as_u8.float(), as_f32)
+    assert torch.equal(as_f32, torch.from_numpy(O.load_image_from_array(g["frame"].numpy(), g["height"], g["width"])))
+    assert torch.equal(as_f32, ref)
+
+
+def test_ingest_feeds_the_matcher_natively():
+    """BGR frames -> FrameIngest (uint8) -> matcher equals the float32 path of the reference's callers, bit for bit."""
+    gen = torch.Generator().manual_seed(11)
+    frames = torch.randint(0, 256, (2, 300, 400, 3), generator=gen, dtype=torch.uint8)
+    frames2 = torch.roll(frames, (2, 3), (1, 2))
+    ing = om.FrameIngest(240, 320).to(DEV)
+    a8, b8 = ing(frames.to(DEV)), ing(frames2.to(DEV))
+    model = om.ShiTomasiSparseBADSinkhornMatcher(128).to(DEV).eval()
+    with torch.no_grad():
+        out8 = model(a8, b8)
+        outf = model(a8.float(), b8.float())
+    host = torch.stack([torch.from_numpy(O.load_image_from_array(f.numpy(), 240, 320))[0] for f in frames])
+    assert torch.equal(a8.cpu().float(), host)
+    for x, y in zip(out8, outf):
+        assert torch.equal(x, y)

@@ -210,3 +210,40 @@ def test_sinkhorn_with_scores():
     N, M = g["desc1"].shape[1], g["desc2"].shape[1]
     assert torch.equal(p, g["P"])
     assert torch.equal(p[:, :N, :M].max(dim=-1).values, g["scores0"]) and torch.equal(p[:, :N, :M].max(dim=-2).values, g["scores1"])
+
+
+@pytest.mark.parametrize("name", G.names("akaze"))
+def test_akaze_maps_and_matcher(name):
+    """the AKAZE matcher's detector maps (restated operator by operator) and everything behind them."""
+    g = G.load(name)
+    kw = g["kwargs"]
+    with torch.no_grad():
+        s1, o1 = O.akaze_maps(g["image1"])
+        s2, o2 = O.akaze_maps(g["image2"])
+        k1, k2, p, d1, d2 = O.maps_matcher(g["image1"], g["image2"], g["scores1"], g["scores2"], g["orient1"], g["orient2"],
+                                           g["K"], return_descriptors=True, **kw)
+    assert torch.equal(s1, g["scores1"]) and torch.equal(s2, g["scores2"])
+    assert torch.equal(o1, g["orient1"]) and torch.equal(o2, g["orient2"])
+    assert torch.equal(k1, g["kpts1"]) and torch.equal(k2, g["kpts2"])
+    assert (d1 - g["desc1"]).abs().max() <= 2e-6 and (d2 - g["desc2"]).abs().max() <= 2e-6
+    K = g["K"]
+    assert (p - g["P"])[:, :K, :].abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", G.names("ingest"))
+def test_ingest_restatement_equals_opencv(name):
+    """sample/visual_odometry.py:65-92 restated in integer numpy against what cv2 produced (golden minted with cv2)."""
+    g = G.load(name)
+    out = O.load_image_from_array(g["frame"].numpy(), g["height"], g["width"])
+    ref = g["out"].numpy()
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    assert (out == ref).all()
+
+
+def test_akaze_module_mirror_matches_oracle_on_cpu():
+    """The product's AKAZE map module (torch operators, off the hot path) is the same arithmetic as the oracle restatement."""
+    import onnx_image_processing_b200 as om
+    g = G.load("akaze_small_default")
+    with torch.no_grad():
+        s, o = om.AKAZE()(g["image1"])
+    assert torch.equal(s, g["scores1"]) and torch.equal(o, g["orient1"])
