@@ -527,10 +527,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         del keep
 
     # ---- end to end through the host API -----------------------------------------------------
-    def time_e2e(a1, a2, join, chunk, mdl=None):
-        hb = HostBatchMatcher(mdl if mdl is not None else model, chunk=max(1, min(chunk, B)), n_streams=4, depth=2, join=join)
+    def time_e2e(a1, a2, join, chunk, mdl=None, n_streams=4):
+        hb = HostBatchMatcher(mdl if mdl is not None else model, chunk=max(1, min(chunk, B)), n_streams=n_streams, depth=2, join=join)
         res = None
-        for _ in range(3):
+        for _ in range(2 * n_streams):           # every stream of the ring and both result sets see a call before the timed region
             res = hb(a1, a2)                     # results kept alive as in the timed loop (allocator steady state)
         hb.synchronize()
         barrier()
@@ -549,15 +549,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     link = None
     if not args.no_e2e:
         link = measure_host_link(dev, stream, world, barrier, max_over_ranks)
-        # chunk sizes from tools/e2e_sweep.py: float32 input is PCIe-bound (fewer, larger copies win), uint8 is not
+        # chunk / stream settings from tools/e2e_sweep.py (float32 in and P out are PCIe-bound in either direction; uint8 in /
+        # matches out is close to the H2D limit of the link as well: 39 MB of pixels per 64 pairs)
         ms_e2e, res = time_e2e(h1, h2, join=False, chunk=32)
         ms_join, _ = time_e2e(h1, h2, join=True, chunk=32)
         u1, u2 = h1.to(torch.uint8).pin_memory(), h2.to(torch.uint8).pin_memory()
-        ms_u8, res8 = time_e2e(u1, u2, join=False, chunk=16)
+        ms_u8, res8 = time_e2e(u1, u2, join=False, chunk=64, n_streams=3)
         # matches only (MatchExtractionWrapper, the form 4 of the reference's 8 exported models use): the (K+1)^2 matrix
         # stays on the device, 100 matches per pair come back
         wrapped = om.MatchExtractionWrapper(model, max_matches=100, match_threshold=0.0035).to(dev).eval()   # P ~ 4e-3 at epsilon = 1, K = 512
-        ms_mx, res_mx = time_e2e(u1, u2, join=False, chunk=16, mdl=wrapped)
+        ms_mx, res_mx = time_e2e(u1, u2, join=False, chunk=32, mdl=wrapped)
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "pairs/s",
                "h2d_bytes_per_step": 2 * B * H * W * 4,
                "d2h_bytes_per_step": B * (2 * K * 2 * 4 + (K + 1) * (K + 1) * 4),
@@ -576,7 +577,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                         "h2d_bytes_per_step": 2 * B * H * W,
                                         "d2h_bytes_per_step": B * 100 * (2 * 2 * 4 + 4 + 1),
                                         "api": "HostBatchMatcher(MatchExtractionWrapper(model, max_matches=100, match_threshold=0.0035), "
-                                               "chunk=16, n_streams=4, depth=2, join=False)(image1_host_u8, image2_host_u8)",
+                                               "chunk=32, n_streams=4, depth=2, join=False)(image1_host_u8, image2_host_u8)",
                                         "note": "mutual nearest-neighbour matches instead of the (K+1)^2 matrix: what 4 of the "
                                                 "reference's 8 exported models return",
                                         "valid_matches_pair0": int(res_mx[3][0].sum())},

@@ -360,6 +360,9 @@ void om_debug_sinkhorn_variant(int variant);
  * (NULL switches tracing off).  Used by tools/sinkhorn_trace.py only. */
 void om_debug_sinkhorn_trace(long long* device_buffer);
 
+/* cudaOccupancyMaxActiveClusters of the hybrid Sinkhorn kernel: big = 0 the 4-CTA form (K <= 512), 1 the 16-CTA form. */
+int om_debug_hy_max_clusters(int big);
+
 /* Single-kernel slices of om_detect_f32 / om_dense_bad_at_kpts_f32 so that bench.py can time each
  * kernel with CUDA events.  stage 0 = first kernel(s), stage 1 = the last kernel (needs stage 0's
  * workspace contents). */

@@ -952,4 +952,38 @@ int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, in
     return epi ? launch_hy<16, 1024, 2, true>(a, B, st) : launch_hy<16, 1024, 2, false>(a, B, st);
 }
 
+// debug: how many clusters of the hybrid kernel the device can hold at once (cudaOccupancyMaxActiveClusters)
+int hy_max_active_clusters(int big) {
+    int n = -1;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(NT, 1, 1);
+    if (big) {
+        using C = Hy<16, 1024, 2>;
+        auto kern = sinkhorn_hy_kernel<16, 1024, 2, false>;
+        cfg.dynamicSmemBytes = (size_t)C::SMEM_FLOATS * sizeof(float);
+        if (set_smem(kern, cfg.dynamicSmemBytes) != OM_OK) return -2;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cfg.gridDim = dim3(16 * 64, 1, 1);
+        at[0].val.clusterDim.x = 16;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
+    } else {
+        using C = Hy<4, 512, HY_RR4>;
+        auto kern = sinkhorn_hy_kernel<4, 512, HY_RR4, false>;
+        cfg.dynamicSmemBytes = (size_t)C::SMEM_FLOATS * sizeof(float);
+        if (set_smem(kern, cfg.dynamicSmemBytes) != OM_OK) return -2;
+        cfg.gridDim = dim3(4 * 64, 1, 1);
+        at[0].val.clusterDim.x = 4;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
+    }
+    return n;
+}
+
 }  // namespace om
+
+extern "C" int om_debug_hy_max_clusters(int big) { return om::hy_max_active_clusters(big); }

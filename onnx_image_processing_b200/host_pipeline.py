@@ -66,6 +66,7 @@ class HostBatchMatcher:
         self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
         self._out = [None] * self.depth
         self._calls = 0
+        self._chunks = 0          # chunks issued so far: the stream ring keeps turning across calls
 
     def _outputs(self, slot: int, B: int, outs, n: int):
         """Pinned host buffers of result set `slot`, shaped (B, ...) after the device outputs of one chunk of n pairs."""
@@ -103,7 +104,10 @@ class HostBatchMatcher:
                 s.wait_stream(cur)
         for ci, lo in enumerate(range(0, B, self.chunk)):
             hi = min(lo + self.chunk, B)
-            s = self.streams[ci % len(self.streams)]
+            # the ring does not restart with every call: with one chunk per call (chunk >= batch) consecutive calls still
+            # land on different streams, so the copies of call k+1 overlap the kernels of call k
+            s = self.streams[self._chunks % len(self.streams)]
+            self._chunks += 1
             with torch.cuda.stream(s):
                 d1 = image1[lo:hi].to(self.device, non_blocking=True)
                 d2 = image2[lo:hi].to(self.device, non_blocking=True)

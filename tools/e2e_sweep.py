@@ -12,9 +12,10 @@ h1, h2 = O.texture_images(B, 480, 640, seed=5)
 h1, h2 = h1.pin_memory(), h2.pin_memory()
 u1, u2 = h1.to(torch.uint8).pin_memory(), h2.to(torch.uint8).pin_memory()
 st = torch.cuda.current_stream()
-for name, a1, a2 in (("f32", h1, h2), ("u8", u1, u2)):
-    for chunk, ns in ((4, 4), (8, 4), (8, 6), (16, 4), (14, 4), (32, 2), (32, 4), (64, 2)):
-        hb = HostBatchMatcher(model, chunk=chunk, n_streams=ns, depth=2, join=False)
+wrapped = om.MatchExtractionWrapper(model, max_matches=100, match_threshold=0.0035).cuda().eval()
+for name, a1, a2, mdl in (("f32", h1, h2, model), ("u8", u1, u2, model), ("u8-matches", u1, u2, wrapped)):
+    for chunk, ns in ((8, 4), (16, 4), (16, 6), (32, 2), (32, 4), (64, 2), (64, 3), (64, 4)):
+        hb = HostBatchMatcher(mdl, chunk=chunk, n_streams=ns, depth=max(2, ns), join=False)
         for _ in range(3): hb(a1, a2)
         hb.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
