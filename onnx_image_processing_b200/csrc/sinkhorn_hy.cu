@@ -1,12 +1,16 @@
 // Matching stage, "hybrid-resident" cluster kernel: the whole (N x M) kernel matrix K = exp(-cost/eps) of a descriptor
-// pair stays on the chip for all Sinkhorn iterations, half of every CTA's rows in REGISTERS and half in SHARED MEMORY,
-// so that one SM holds twice the rows of sinkhorn_tc_kernel (sinkhorn_tc.cu) and a pair needs half the SMs:
+// pair stays on the chip for all Sinkhorn iterations, part of every CTA's rows in REGISTERS and the rest in TENSOR MEMORY
+// (used as a per-thread scratchpad once the similarity GEMM's accumulators are dead: 128 private words per thread, read
+// at ~800 B/clk per SM against 128 B/clk for shared memory), so that one SM holds twice the rows of sinkhorn_tc_kernel
+// (sinkhorn_tc.cu) and a pair needs half the SMs:
 //
-//   * up to 512 x 512:   4-CTA cluster, 128 rows per CTA (64 in registers + 64 in shared memory)  -> ~37 pairs in flight
-//     on a B200 instead of ~14 with the 8-CTA kernel, and half the cross-CTA exchange partners;
+//   * up to 512 x 512:   4-CTA cluster, 128 rows per CTA (per thread 48 values in registers + 80 in tensor memory)
+//     -> 33 pairs in flight on a B200 instead of ~14 with the 8-CTA kernel, and half the cross-CTA exchange partners;
 //   * up to 1024 x 1024 (the reference's export defaults, onnx_export/export_shi_tomasi_sparse_bad_sinkhorn.py:52-127):
-//     16-CTA (non-portable) cluster, 64 rows x 1024 columns per CTA (32 + 32) -- the matrix no longer makes 20 round
-//     trips through global memory as on the generic path.
+//     16-CTA (non-portable) cluster, 64 rows x 1024 columns per CTA (64 + 64 values per thread; 7 clusters resident) --
+//     the matrix no longer makes 20 round trips through global memory as on the generic path.
+// History of the K <= 512 form, 64 pairs: K rows in shared memory, two-hop exchange 250 us -> no spilled K values, one-hop
+// exchange 193 us -> K rows in tensor memory 169 us (K = 1024: 1405 -> 1047 us).
 //
 // Replaces matching/sinkhorn.py:79-208 in the scaling form (a = mu / (K b), b = nu / (K^T a), P = a K b; see the block
 // comment in sinkhorn_tc.cu for the derivation and its range condition).
@@ -27,9 +31,8 @@ namespace om {
 
 namespace {
 
-// 4-CTA form: rows per warp (of 8) whose K values live in registers.  Measured (64 pairs, K = 512): 4 rows = 64 values per
-// thread leave the loop 20 spilled values short of registers (re-read from local memory every sweep: 244 us), 3 rows = 48
-// values and 5 rows in shared memory run without spills (202 us)
+// 4-CTA form: rows per warp (of 8) whose K values live in registers; the others live in tensor memory (3 and 4 measure the
+// same; with the other rows in SHARED memory 4 rows spilled 20 values per thread: 244 us against 202 us for 3 rows)
 #define HY_RR4 3
 constexpr int NW = 16;              // warps per CTA
 constexpr int NT = NW * 32;
@@ -133,6 +136,18 @@ __device__ __forceinline__ void tmem_ld32x32(uint32_t taddr, uint32_t (&r)[32]) 
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// tensor memory as a per-thread scratchpad: four 32-bit columns of the calling thread's own lane (lane quadrant of its warp)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float4& v) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
+    v.x = __uint_as_float(a); v.y = __uint_as_float(b); v.z = __uint_as_float(c); v.w = __uint_as_float(d);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
+                 "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float dot4(const float4& k, const float4& b, float acc) {
     return fmaf(k.w, b.w, fmaf(k.z, b.z, fmaf(k.y, b.y, fmaf(k.x, b.x, acc))));
 }
@@ -389,9 +404,22 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
             __syncthreads();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (warp == 0)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        __syncthreads();                                                // every accumulator has been read
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // The accumulators are dead: tensor memory becomes the home of the K rows that do not fit the registers.  A warp can
+    // reach the 32 lanes of its quadrant (warp % 4); the four warps of a quadrant take 128 columns each, i.e. 128 private
+    // 32-bit words per thread, read back at ~800 B/clk per SM (shared memory: 128 B/clk) -- measured, tools/probes/tmem_probe.cu.
+    // Word (k * RS + sr) * 4 + q of a thread = K[row RR + sr][column 128 k + 4 lane + q].
+    const uint32_t tpriv = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * (warp >> 2));
+    static_assert(RS * 4 * NK <= 128, "a thread's private tensor-memory words");
+    {
+        const float4* src = reinterpret_cast<const float4*>(sKs) + (size_t)warp * RS * (MAXM / 4) + lane;
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+#pragma unroll
+            for (int sr = 0; sr < RS; ++sr) tmem_st4(tpriv + (uint32_t)((k * RS + sr) * 4), src[sr * (MAXM / 4) + 32 * k]);
+        tmem_wait_st();
     }
     HY_STAMP(3);
 
@@ -408,7 +436,6 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     const uint32_t part_bytes = (uint32_t)CL * (has_dust ? (uint32_t)OWN + 1u : (uint32_t)OWN) * 4u;
     const uint32_t b_bytes = (uint32_t)(MAXM + 1) * 4u;
     const float4* sB4 = reinterpret_cast<const float4*>(sB);
-    const float4* sKs4 = reinterpret_cast<const float4*>(sKs) + (size_t)warp * RS * (MAXM / 4) + lane;
     float4* sCW4 = reinterpret_cast<float4*>(sCW) + (size_t)warp * (MAXM / 4) + lane;
     cluster.sync();      // every CTA is past its GEMM and has initialised its barriers and its b
     HY_STAMP(4);
@@ -440,8 +467,12 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
             sb += (b4.x + b4.y) + (b4.z + b4.w);
 #pragma unroll
             for (int rr = 0; rr < RR; ++rr) rs[rr] = dot4(kreg[rr][k], b4, rs[rr]);
+            float4 kt[RS];
 #pragma unroll
-            for (int sr = 0; sr < RS; ++sr) rs[RR + sr] = dot4(sKs4[sr * (MAXM / 4) + 32 * k], b4, rs[RR + sr]);
+            for (int sr = 0; sr < RS; ++sr) tmem_ld4(tpriv + (uint32_t)((k * RS + sr) * 4), kt[sr]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int sr = 0; sr < RS; ++sr) rs[RR + sr] = dot4(kt[sr], b4, rs[RR + sr]);
         }
         bM = sB[MAXM];
         float asum = 0.0f;
@@ -505,9 +536,13 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                 t4.x = fmaf(kreg[rr][k].x, av[rr], t4.x); t4.y = fmaf(kreg[rr][k].y, av[rr], t4.y);
                 t4.z = fmaf(kreg[rr][k].z, av[rr], t4.z); t4.w = fmaf(kreg[rr][k].w, av[rr], t4.w);
             }
+            float4 kt[RS];
+#pragma unroll
+            for (int sr = 0; sr < RS; ++sr) tmem_ld4(tpriv + (uint32_t)((k * RS + sr) * 4), kt[sr]);
+            tmem_wait_ld();
 #pragma unroll
             for (int sr = 0; sr < RS; ++sr) {
-                const float4 ks = sKs4[sr * (MAXM / 4) + 32 * k];
+                const float4 ks = kt[sr];
                 t4.x = fmaf(ks.x, av[RR + sr], t4.x); t4.y = fmaf(ks.y, av[RR + sr], t4.y);
                 t4.z = fmaf(ks.z, av[RR + sr], t4.z); t4.w = fmaf(ks.w, av[RR + sr], t4.w);
             }
@@ -615,7 +650,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                     const float4 b4 = sB4[32 * k + lane];
                     float4 kv;
                     if (r < RR) kv = kreg[r < RR ? r : 0][k];
-                    else kv = sKs4[(r - RR) * (MAXM / 4) + 32 * k];
+                    else { tmem_ld4(tpriv + (uint32_t)((k * RS + (r >= RR ? r - RR : 0)) * 4), kv); tmem_wait_ld(); }
                     float4 p4;
                     p4.x = av[r] * kv.x * b4.x; p4.y = av[r] * kv.y * b4.y; p4.z = av[r] * kv.z * b4.z; p4.w = av[r] * kv.w * b4.w;
                     *reinterpret_cast<float4*>(stage + 128 * k + 4 * lane) = p4;
@@ -672,7 +707,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                 const float4 b4 = sB4[32 * k + lane];
                 float4 kv;
                 if (r < RR) kv = kreg[r < RR ? r : 0][k];
-                else kv = sKs4[(r - RR) * (MAXM / 4) + 32 * k];
+                else { tmem_ld4(tpriv + (uint32_t)((k * RS + (r >= RR ? r - RR : 0)) * 4), kv); tmem_wait_ld(); }
                 p[k].x = av[r] * kv.x * b4.x; p[k].y = av[r] * kv.y * b4.y; p[k].z = av[r] * kv.z * b4.z; p[k].w = av[r] * kv.w * b4.w;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -863,7 +898,10 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
         }
     }
     HY_STAMP(6);
-    cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster.sync();      // no CTA may exit while a peer can still write into its shared memory; every warp is done with tensor memory
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
 }
 
 template <int CL, int MAXM, int RRT, bool EPI>
