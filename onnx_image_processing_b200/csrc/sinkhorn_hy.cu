@@ -109,6 +109,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
+// the same to the same shared-memory offset of every CTA in `mask` (completion on each one's mbarrier at that offset)
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     dst_smem), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
 // UMMA shared-memory descriptor, no swizzle, K-major (cute/arch/mma_sm100_desc.hpp layout)
 __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
@@ -123,6 +128,11 @@ __device__ __forceinline__ void umma_f16_n(uint32_t d_tmem, uint64_t adesc, uint
 }
 __device__ __forceinline__ void umma_commit_to(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -148,6 +158,15 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4& v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// packed f32x2 forms (FFMA2): two lanes of FP32 work per issue slot -- the FP32 rate is the same, the issue slots halve
+__device__ __forceinline__ float2 dot4x2(const float4& k, const float4& b, float2 acc) {
+    acc = __ffma2_rn(make_float2(k.x, k.y), make_float2(b.x, b.y), acc);
+    return __ffma2_rn(make_float2(k.z, k.w), make_float2(b.z, b.w), acc);
+}
+__device__ __forceinline__ void axpy4x2(const float4& k, float2 a2, float2& lo, float2& hi) {
+    lo = __ffma2_rn(make_float2(k.x, k.y), a2, lo);
+    hi = __ffma2_rn(make_float2(k.z, k.w), a2, hi);
+}
 __device__ __forceinline__ float dot4(const float4& k, const float4& b, float acc) {
     return fmaf(k.w, b.w, fmaf(k.z, b.z, fmaf(k.y, b.y, fmaf(k.x, b.x, acc))));
 }
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < 10; ++i) mbar_init(smem_u32(&bars[i]), (i == 2 || i == 3) ? (uint32_t)CL : 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    cluster.sync();      // peers multicast into this CTA's staging area and arrive on its barriers from here on
     HY_STAMP(0);
 
     // ---------------- similarity GEMM on tcgen05: D[j][i] = sum_k d2[j][k] d1[i][k] ------------------
@@ -293,15 +313,20 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
         const uint32_t bytesA = 2u * a_term, bytesB = 2u * b_term;
         const uint32_t stage0 = smem_u32(sm);
         if (warp == 0 && lane == 0) {
-            // ===== copy issuer: two bulk copies per stage (the d2 terms of the chunk, this CTA's d1 terms) =====
+            // ===== copy issuer: this CTA's d1 terms of the chunk, and ITS SLICE of the d2 terms multicast to the whole cluster
+            // (every CTA needs all of d2: each of the CL issuers fetches 1 / CL of a chunk from L2 once for everybody) =====
+            constexpr uint16_t ALL = (uint16_t)((1u << CL) - 1u);
             const unsigned char* gA = a.d2p + (size_t)z * (4ull * D * Mp);
             const unsigned char* gB = a.d1p + ((size_t)z * CL + rank) * (4ull * D * RPC);
+            const uint32_t sliceA = bytesA / (uint32_t)CL;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c & 1;
-                if (c >= 2) mbar_wait(smem_u32(&bars[2 + s]), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 done
+                // stage s is free in EVERY CTA: each one's MMA issuer commits chunk c-2 to all the cluster's barriers
+                if (c >= 2) mbar_wait(smem_u32(&bars[2 + s]), (uint32_t)(((c >> 1) - 1) & 1));
                 const uint32_t full = smem_u32(&bars[s]);
                 mbar_arrive_expect_tx(full, bytesA + bytesB);
-                bulk_g2s(stage0 + s * C::STAGE, gA + (size_t)c * bytesA, bytesA, full);
+                bulk_g2s_mc(stage0 + s * C::STAGE + (uint32_t)rank * sliceA, gA + (size_t)c * bytesA + (size_t)rank * sliceA, sliceA,
+                            full, ALL);
                 bulk_g2s(stage0 + s * C::STAGE + 2 * C::A_TERM, gB + (size_t)c * bytesB, bytesB, full);
             }
         } else if (warp == 1 && lane == 0) {
@@ -326,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                         umma_f16_n(d, alo, bhi, IDESC, 1u);
                     }
                 }
-                umma_commit_to(smem_u32(&bars[2 + s]));                 // frees stage s when these MMAs retire
+                umma_commit_mc(smem_u32(&bars[2 + s]), (uint16_t)((1u << CL) - 1u));   // stage s of this CTA is free: tell every issuer
                 if (c == nchunks - 1) umma_commit_to(smem_u32(&bars[4]));
             }
         }
@@ -459,21 +484,24 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
         }
         // ---- a_i = mu_i / rowsum_i ----
         float rs[RPW], sb = 0.0f;
+        float2 rs2[RPW];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) rs[r] = 0.0f;
+        for (int r = 0; r < RPW; ++r) rs2[r] = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
             const float4 b4 = sB4[32 * k + lane];
             sb += (b4.x + b4.y) + (b4.z + b4.w);
-#pragma unroll
-            for (int rr = 0; rr < RR; ++rr) rs[rr] = dot4(kreg[rr][k], b4, rs[rr]);
             float4 kt[RS];
 #pragma unroll
             for (int sr = 0; sr < RS; ++sr) tmem_ld4(tpriv + (uint32_t)((k * RS + sr) * 4), kt[sr]);
+#pragma unroll
+            for (int rr = 0; rr < RR; ++rr) rs2[rr] = dot4x2(kreg[rr][k], b4, rs2[rr]);      // while the tensor-memory loads land
             tmem_wait_ld();
 #pragma unroll
-            for (int sr = 0; sr < RS; ++sr) rs[RR + sr] = dot4(kt[sr], b4, rs[RR + sr]);
+            for (int sr = 0; sr < RS; ++sr) rs2[RR + sr] = dot4x2(kt[sr], b4, rs2[RR + sr]);
         }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) rs[r] = rs2[r].x + rs2[r].y;
         bM = sB[MAXM];
         float asum = 0.0f;
         if constexpr (RPW == 8) {
@@ -527,26 +555,21 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
         }
         aN = __fdividef(Mf, kd * (sb + bM));                            // dustbin row: mu_N = M (sinkhorn.py:197-198)
         // ---- column sums: warp partials -> CTA partials -> owners ----
+        float2 av2[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) av2[r] = make_float2(av[r], av[r]);
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
-            float4 t4;
-            t4.x = kreg[0][k].x * av[0]; t4.y = kreg[0][k].y * av[0]; t4.z = kreg[0][k].z * av[0]; t4.w = kreg[0][k].w * av[0];
-#pragma unroll
-            for (int rr = 1; rr < RR; ++rr) {
-                t4.x = fmaf(kreg[rr][k].x, av[rr], t4.x); t4.y = fmaf(kreg[rr][k].y, av[rr], t4.y);
-                t4.z = fmaf(kreg[rr][k].z, av[rr], t4.z); t4.w = fmaf(kreg[rr][k].w, av[rr], t4.w);
-            }
             float4 kt[RS];
 #pragma unroll
             for (int sr = 0; sr < RS; ++sr) tmem_ld4(tpriv + (uint32_t)((k * RS + sr) * 4), kt[sr]);
+            float2 lo = make_float2(0.0f, 0.0f), hi = lo;
+#pragma unroll
+            for (int rr = 0; rr < RR; ++rr) axpy4x2(kreg[rr][k], av2[rr], lo, hi);
             tmem_wait_ld();
 #pragma unroll
-            for (int sr = 0; sr < RS; ++sr) {
-                const float4 ks = kt[sr];
-                t4.x = fmaf(ks.x, av[RR + sr], t4.x); t4.y = fmaf(ks.y, av[RR + sr], t4.y);
-                t4.z = fmaf(ks.z, av[RR + sr], t4.z); t4.w = fmaf(ks.w, av[RR + sr], t4.w);
-            }
-            sCW4[32 * k] = t4;
+            for (int sr = 0; sr < RS; ++sr) axpy4x2(kt[sr], av2[RR + sr], lo, hi);
+            sCW4[32 * k] = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
         if (lane == 0) sAs[warp] = asum;
         bar_all();
