@@ -399,6 +399,15 @@ struct WinGeom {
     static constexpr int GSTRIDE = (WR * WP + 31) / 32 * 32;   // words per window buffer (128-byte aligned)
 };
 
+// The eight window byte offsets of a pair's taps (two boxes x four corners, bad.py:98 order), 16 bits each, in ONE 16-byte
+// word per slot: a warp reads it as one conflict-free LDS.128 (two uint4 per slot at a 32-byte lane stride cost 16
+// wavefronts instead of 4; the tables were 40 % of the descriptor kernels' shared-memory wavefronts).
+__device__ __forceinline__ uint4 pack_taps(const unsigned (&o)[8]) {
+    return make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+}
+__device__ __forceinline__ unsigned tap_lo(unsigned v) { return v & 0xFFFFu; }
+__device__ __forceinline__ unsigned tap_hi(unsigned v) { return v >> 16; }
+
 // keypoint -> does it need a window here?  (valid, and its image is integer-valued)
 __device__ __forceinline__ bool win_needed(const SparseArgs& a, long long kidx, float& ky, float& kx, int& z) {
     z = (int)(kidx / a.K);
@@ -535,10 +544,10 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+                const uint4 tp = sTap[p];
                 const float2 tb = sThr[p];
-                const unsigned int s1 = (ldw(ta.x) - ldw(ta.y)) - (ldw(ta.z) - ldw(ta.w));
-                const unsigned int s2 = (ldw(tc.x) - ldw(tc.y)) - (ldw(tc.z) - ldw(tc.w));
+                const unsigned int s1 = (ldw(tap_lo(tp.x)) - ldw(tap_hi(tp.x))) - (ldw(tap_lo(tp.y)) - ldw(tap_hi(tp.y)));
+                const unsigned int s2 = (ldw(tap_lo(tp.z)) - ldw(tap_hi(tp.z))) - (ldw(tap_lo(tp.w)) - ldw(tap_hi(tp.w)));
                 const float diff = __fsub_rn(__fmul_rn((float)s1, tb.y), __fmul_rn((float)s2, tb.y));   // bad.py:557
                 d[q] = finish_value(diff, tb.x, a.mode, a.temperature);
                 ss = fmaf(d[q], d[q], ss);
@@ -583,8 +592,8 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
     __shared__ float sTheta[GROUPS];
     __shared__ __align__(8) unsigned long long bars[GROUPS * 2];
     unsigned int* sWin = reinterpret_cast<unsigned int*>(smem_raw);             // GROUPS x NBUF x GSTRIDE
-    uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * NBUF * G::GSTRIDE);  // fast path: 2 x 4 window byte offsets per pair
-    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? 2 * a.P : 0));      //            {threshold, 1/area}
+    uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * NBUF * G::GSTRIDE);  // fast path: 2 x 4 window byte offsets per pair (16 bits each)
+    float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));          //            {threshold, 1/area}
     unsigned short* sIdx = reinterpret_cast<unsigned short*>(sThr + (FAST ? a.P : 0));   //     slot -> pair (pair_order.inc)
 
     const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
@@ -603,10 +612,10 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
             const int r = (int)row.r;
             const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
             auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * G::WP + x) * 4u; };
-            sTap[2 * p] = make_uint4(off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r),
-                                     off(cy1 - r, cx1 - r));
-            sTap[2 * p + 1] = make_uint4(off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r),
-                                         off(cy2 - r, cx2 - r));
+            static_assert(G::WR * G::WP * 4 < 65536, "window byte offsets must fit 16 bits");
+            const unsigned o[8] = {off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r), off(cy1 - r, cx1 - r),
+                                   off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r), off(cy2 - r, cx2 - r)};
+            sTap[p] = pack_taps(o);
             const float side = (float)(2 * r + 1);
             sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
         }
@@ -657,7 +666,7 @@ int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t s
     OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, G::WP, G::WR));
     constexpr int NBUF = 1;
     const size_t smem = (size_t)GROUPS * NBUF * G::GSTRIDE * 4 +
-                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (2 * sizeof(uint4) + sizeof(float2) + sizeof(unsigned short)) : 0);
+                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2) + sizeof(unsigned short)) : 0);
     const long long total = (long long)a.B * a.K;
     const long long nblk = (total + GROUPS - 1) / GROUPS;
     const int per_sm = (int)(228 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (228 KB, 1 KB reserved per CTA)
@@ -1334,10 +1343,10 @@ __device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long k
             const int p = t + q * TPG;                                  // slot; sThr[p].w holds its pair index
             d[q] = 0.0f; pidx[q] = -1;
             if (p >= a.P) continue;                                     // only when P is not a multiple of 64
-            const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+            const uint4 tp = sTap[p];
             const float4 tb = sThr[p];
-            const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(ta.x), ldl(ta.y)), ldl(ta.z)), ldl(ta.w));
-            const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(tc.x), ldl(tc.y)), ldl(tc.z)), ldl(tc.w));
+            const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(tap_lo(tp.x)), ldl(tap_hi(tp.x))), ldl(tap_lo(tp.y))), ldl(tap_hi(tp.y)));
+            const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(tap_lo(tp.z)), ldl(tap_hi(tp.z))), ldl(tap_lo(tp.w))), ldl(tap_hi(tp.w)));
             const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));               // bad.py:99, :110
             d[q] = __fadd_rn(0.0f, finish_value(diff, tb.x, a.mode, a.temperature));
             pidx[q] = __float_as_int(tb.w);
@@ -1348,17 +1357,17 @@ __device__ __forceinline__ void dense_kp_group(const DenseKpArgs& a, long long k
             const int p = t + q * TPG;
             d[q] = 0.0f; pidx[q] = -1;
             if (p >= a.P) continue;
-            const uint4 ta = sTap[2 * p], tc = sTap[2 * p + 1];
+            const uint4 tp = sTap[p];
             const float4 tb = sThr[p];
+            const unsigned a0 = tap_lo(tp.x), a1 = tap_hi(tp.x), a2 = tap_lo(tp.y), a3 = tap_hi(tp.y);
+            const unsigned c0 = tap_lo(tp.z), c1 = tap_hi(tp.z), c2 = tap_lo(tp.w), c3 = tap_hi(tp.w);
             float v = 0.0f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (wgt[k] != 0.0f) {                                   // group-uniform
                     const unsigned int lk = ((k >> 1) * SPAN + (k & 1)) * 4;
-                    const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + ta.x), ldl(lk + ta.y)), ldl(lk + ta.z)),
-                                               ldl(lk + ta.w));
-                    const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + tc.x), ldl(lk + tc.y)), ldl(lk + tc.z)),
-                                               ldl(lk + tc.w));
+                    const float s1 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + a0), ldl(lk + a1)), ldl(lk + a2)), ldl(lk + a3));
+                    const float s2 = __fadd_rn(__fsub_rn(__fsub_rn(ldl(lk + c0), ldl(lk + c1)), ldl(lk + c2)), ldl(lk + c3));
                     const float diff = __fsub_rn(div_area(s1, tb.y, tb.z), div_area(s2, tb.y, tb.z));       // bad.py:99, :110
                     v += finish_value(diff, tb.x, a.mode, a.temperature) * wgt[k];
                 }
@@ -1396,8 +1405,8 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) dense_at_kpts_kernel(const __
     extern __shared__ __align__(128) float sI[];
     __shared__ float red[GROUPS * 2];
     __shared__ __align__(8) unsigned long long bars[GROUPS * 2];
-    uint4* sTap = reinterpret_cast<uint4*>(sI + GROUPS * NBUF * WBUF);   // 2 x 4 window byte offsets per pair
-    float4* sThr = reinterpret_cast<float4*>(sTap + 2 * a.P);         // {threshold, area, float(1/area), -}
+    uint4* sTap = reinterpret_cast<uint4*>(sI + GROUPS * NBUF * WBUF);   // 2 x 4 window byte offsets per pair, 16 bits each
+    float4* sThr = reinterpret_cast<float4*>(sTap + a.P);             // {threshold, area, float(1/area), pair index}
     const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -1416,10 +1425,10 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) dense_at_kpts_kernel(const __
         const int cy2 = LO + MAXR + (int)row.oy2, cx2 = LO + MAXR + (int)row.ox2;
         auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * SPAN + x) * 4u; };
         // order of bad.py:98: (y1,x1) - (y0,x1) - (y1,x0) + (y0,x0)
-        sTap[2 * p] = make_uint4(off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r),
-                                 off(cy1 - r, cx1 - r));
-        sTap[2 * p + 1] = make_uint4(off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r),
-                                     off(cy2 - r, cx2 - r));
+        static_assert((DK_ROWS + 1) * DK_SPAN * 4 < 65536, "window byte offsets (+ one neighbour row) must fit 16 bits");
+        const unsigned o[8] = {off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r), off(cy1 - r, cx1 - r),
+                               off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r), off(cy2 - r, cx2 - r)};
+        sTap[p] = pack_taps(o);
         const float side = (float)(2 * r + 1);
         sThr[p] = make_float4(row.thr, side * side, __fdiv_rn(1.0f, side * side), __int_as_float(pair));
     }
@@ -1495,7 +1504,7 @@ int launch_dense_kp(const DenseKpArgs& a, cudaStream_t st) {
     OM_TRY(make_tmap_3d(&tmap, true, a.I, (uint64_t)IP, (uint64_t)(a.H + 2 * MAXR + 1), (uint64_t)a.B, (uint64_t)IP, DK_SPAN,
                         DK_ROWS));
     constexpr int NBUF = 1;
-    const size_t smem = (size_t)GROUPS * NBUF * DK_ROWS * DK_SPAN * sizeof(float) + (size_t)a.P * (2 * sizeof(uint4) + sizeof(float4));
+    const size_t smem = (size_t)GROUPS * NBUF * DK_ROWS * DK_SPAN * sizeof(float) + (size_t)a.P * (sizeof(uint4) + sizeof(float4));
     const long long total = (long long)a.B * a.K;
     const long long nblk = (total + GROUPS - 1) / GROUPS;
     const int per_sm = (int)(228 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (228 KB, 1 KB reserved per CTA)
