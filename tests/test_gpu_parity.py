@@ -44,7 +44,9 @@ def test_score_map_bit_exact(block_size, shape):
     nbad = int((got != exact).sum())
     assert nbad == 0, f"{nbad} of {ref.numel()} score pixels differ from the IEEE-sqrt oracle, max abs {float((got - exact).abs().max())}"
     off = got != ref
-    assert float(off.float().mean()) <= 0.02
+    # how often the host's vectorised sqrt is off by an ulp depends on the host CPU (measured 1 % ... 4.3 % on this pool's
+    # boxes): the fraction is only sanity-checked, the SIZE of every difference is what is asserted
+    assert float(off.float().mean()) <= 0.15
     if off.any():
         # one ulp of the sqrt term; the term is bounded by the largest possible trace of the block
         trace_max = 2.0 * block_size ** 2 * (4.0 * amp) ** 2
