@@ -282,6 +282,18 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
     cudaStream_t chain[2] = {st, st};           // detector + descriptors of image 1 / image 2
     cudaStream_t pre[2] = {st, st};             // integral image of image 1 / image 2
     const int ns = g_match_streams;
+    // hybrid Sinkhorn kernel ahead: its operand packing of image s runs on image s's own chain, right behind its descriptors
+    const bool hy = sinkhorn_routes_to_hy(p->B, p->K, p->K, p->P, p->epsilon, p->unused_score, p->distance_l1, w.sink, w.sink_bytes) &&
+                    p->iterations > 0 && (!ex || epi->any());
+    if (hy && ex) {                                       // what sinkhorn_ex_launch would reject
+        const SinkhornEpilogue& e = *epi;
+        if (e.matches && (e.kpts1 == nullptr || e.kpts2 == nullptr || e.mk1 == nullptr || e.mk2 == nullptr || e.mscores == nullptr ||
+                          e.mvalid == nullptr))
+            return OM_ERR_NULL;
+        if (e.matches && e.max_matches <= 0) return OM_ERR_SHAPE;
+        if (e.filters && e.filter_valid == nullptr) return OM_ERR_NULL;
+    }
+    if (hy) OM_TRY(sinkhorn_hy_prepare(p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, st));   // before the fork: ordered ahead of both chains
     SideSet* set = nullptr;
     std::unique_lock<std::mutex> busy;
     int nside = 0;                              // side streams that were forked and must be joined, on every path
@@ -329,6 +341,7 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
             } else {
                 OM_TRY(descriptors(s, chain[s], 0));
             }
+            if (hy) OM_TRY(sinkhorn_hy_pack(s, ds[s], p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, chain[s]));
         }
         return OM_OK;
     };
@@ -339,6 +352,9 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
         if (e2 != cudaSuccess && rc == OM_OK) rc = OM_ERR_CUDA_BASE + (int)e2;
     }
     if (rc != OM_OK) return rc;
+    if (hy)
+        return sinkhorn_hy_run(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, probs, ex ? epi : nullptr,
+                               w.sink, w.sink_bytes, st);
     if (ex)
         return sinkhorn_ex_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
                                   probs, *epi, w.sink, w.sink_bytes, st);

@@ -188,6 +188,14 @@ bool sinkhorn_hy_eligible(int N, int M, int D, float eps, float unused, int dist
 size_t sinkhorn_hy_workspace_bytes(int B, int N, int M, int D);
 int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
                        float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st);
+// the three steps of sinkhorn_hy_launch, and the router's answer to "will sinkhorn_launch / sinkhorn_ex_launch take the hybrid
+// kernel for this problem?" (the fused matcher then packs each image's descriptors on that image's stream)
+int sinkhorn_hy_prepare(int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st);
+int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st);
+int sinkhorn_hy_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                    float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st);
+bool sinkhorn_routes_to_hy(int B, int N, int M, int D, float epsilon, float unused_score, int distance_l1, const void* ws,
+                           size_t ws_bytes);
 size_t sinkhorn_ex_workspace_bytes(int B, int N, int M, int D);
 // Sinkhorn + optional outputs; P may be null when the epilogue is fused (otherwise it is kept in the workspace)
 int sinkhorn_ex_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,

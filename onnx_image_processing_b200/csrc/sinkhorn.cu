@@ -656,6 +656,13 @@ static size_t generic_workspace_bytes(int B, int N, int M) {
            align_up((size_t)B * ((N + 1 + XR - 1) / XR) * (M + 1) * sizeof(float));
 }
 
+bool sinkhorn_routes_to_hy(int B, int N, int M, int D, float epsilon, float unused_score, int distance_l1, const void* ws,
+                           size_t ws_bytes) {
+    return g_sinkhorn_variant == 0 && B > 0 && B <= 65535 && (long long)B * 16 < (1ll << 31) &&
+           sinkhorn_hy_eligible(N, M, D, epsilon, unused_score, distance_l1) && ws != nullptr &&
+           ws_bytes >= sinkhorn_hy_workspace_bytes(B, N, M, D);
+}
+
 int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
                     float unused_score, int distance_l1, float* P, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (d1 == nullptr || d2 == nullptr || P == nullptr) return OM_ERR_NULL;

@@ -981,36 +981,78 @@ size_t sinkhorn_hy_workspace_bytes(int B, int N, int M, int D) {
            align_up((size_t)B * Mp * sizeof(float)) + align_up((size_t)B * sizeof(unsigned int));
 }
 
-int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
-                       float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st) {
+namespace {
+struct HyWs {
+    unsigned char* d1p;
+    unsigned char* d2p;
+    float* n1;
+    float* n2;
+    unsigned int* ovf;
+    int CLv, RPCv, Mp, G;
+};
+HyWs hy_carve(void* ws, int B, int N, int M, int D) {
+    HyWs w{};
+    hy_geometry(N, M, w.CLv, w.RPCv, w.Mp);
+    const size_t np = (size_t)w.CLv * w.RPCv;
+    char* c = (char*)ws;
+    w.d1p = (unsigned char*)c; c += align_up((size_t)B * np * D * 4);
+    w.d2p = (unsigned char*)c; c += align_up((size_t)B * w.Mp * D * 4);
+    w.n1 = (float*)c; c += align_up((size_t)B * np * sizeof(float));
+    w.n2 = (float*)c; c += align_up((size_t)B * w.Mp * sizeof(float));
+    w.ovf = (unsigned int*)c;
+    w.G = w.CLv == 4 ? 4 : 2;
+    return w;
+}
+}  // namespace
+
+// The three steps of a hybrid-kernel call, separately launchable so that the fused matcher can pack each image's descriptors
+// on that image's own stream as soon as they exist (the packing of one image then runs under the other image's kernels):
+// prepare (clears the per-pair range flags), pack (which = 0: desc1 rows, 1: desc2 rows), run (the cluster kernel).
+int sinkhorn_hy_prepare(int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws == nullptr || ws_bytes < sinkhorn_hy_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    const HyWs w = hy_carve(ws, B, N, M, D);
+    OM_CUDA(cudaMemsetAsync(w.ovf, 0, (size_t)B * sizeof(unsigned int), st));
+    return OM_OK;
+}
+
+int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (d == nullptr) return OM_ERR_NULL;
+    if (ws == nullptr || ws_bytes < sinkhorn_hy_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    const HyWs w = hy_carve(ws, B, N, M, D);
+    const size_t np = (size_t)w.CLv * w.RPCv;
+    if (which == 0)
+        pack_f16_kernel<<<dim3((unsigned)((np / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d, N, D, w.RPCv, w.CLv, w.G, w.d1p, w.n1, w.ovf);
+    else
+        pack_f16_kernel<<<dim3((unsigned)((w.Mp / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d, M, D, w.Mp, 1, w.G, w.d2p, w.n2, w.ovf);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+int sinkhorn_hy_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                    float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (!sinkhorn_hy_eligible(N, M, D, eps, unused, 0)) return OM_ERR_PARAM;
     if (ws == nullptr || ws_bytes < sinkhorn_hy_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
-    int CLv, RPCv, Mp;
-    hy_geometry(N, M, CLv, RPCv, Mp);
-    const size_t np = (size_t)CLv * RPCv;
-    char* c = (char*)ws;
-    unsigned char* d1p = (unsigned char*)c; c += align_up((size_t)B * np * D * 4);
-    unsigned char* d2p = (unsigned char*)c; c += align_up((size_t)B * Mp * D * 4);
-    float* n1 = (float*)c; c += align_up((size_t)B * np * sizeof(float));
-    float* n2 = (float*)c; c += align_up((size_t)B * Mp * sizeof(float));
-    unsigned int* ovf = (unsigned int*)c;
-    OM_CUDA(cudaMemsetAsync(ovf, 0, (size_t)B * sizeof(unsigned int), st));
-    const int G = CLv == 4 ? 4 : 2;
-    pack_f16_kernel<<<dim3((unsigned)((np / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d1, N, D, RPCv, CLv, G, d1p, n1, ovf);
-    OM_AFTER_LAUNCH();
-    pack_f16_kernel<<<dim3((unsigned)((Mp / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d2, M, D, Mp, 1, G, d2p, n2, ovf);
-    OM_AFTER_LAUNCH();
+    const HyWs w = hy_carve(ws, B, N, M, D);
     HyArgs a{};
-    a.d1p = d1p; a.d2p = d2p; a.n1 = n1; a.n2 = n2; a.ovf = ovf; a.d1 = d1; a.d2 = d2;
-    a.N = N; a.M = M; a.D = D; a.Mp = Mp; a.iterations = iterations; a.P = P;
+    a.d1p = w.d1p; a.d2p = w.d2p; a.n1 = w.n1; a.n2 = w.n2; a.ovf = w.ovf; a.d1 = d1; a.d2 = d2;
+    a.N = N; a.M = M; a.D = D; a.Mp = w.Mp; a.iterations = iterations; a.P = P;
     a.trace = g_tc_trace;
     const double log2e = 1.4426950408889634;
     a.scale2 = (float)(log2e / (double)eps);
     a.dustbin2 = (float)((-(double)unused / (double)eps) * log2e);
     const bool epi = e != nullptr && e->any();
     if (epi) a.e = *e;
-    if (CLv == 4) return epi ? launch_hy<4, 512, HY_RR4, true>(a, B, st) : launch_hy<4, 512, HY_RR4, false>(a, B, st);
+    if (w.CLv == 4) return epi ? launch_hy<4, 512, HY_RR4, true>(a, B, st) : launch_hy<4, 512, HY_RR4, false>(a, B, st);
     return epi ? launch_hy<16, 1024, 2, true>(a, B, st) : launch_hy<16, 1024, 2, false>(a, B, st);
+}
+
+int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                       float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!sinkhorn_hy_eligible(N, M, D, eps, unused, 0)) return OM_ERR_PARAM;
+    OM_TRY(sinkhorn_hy_prepare(B, N, M, D, ws, ws_bytes, st));
+    OM_TRY(sinkhorn_hy_pack(0, d1, B, N, M, D, ws, ws_bytes, st));
+    OM_TRY(sinkhorn_hy_pack(1, d2, B, N, M, D, ws, ws_bytes, st));
+    return sinkhorn_hy_run(d1, d2, B, N, M, D, iterations, eps, unused, P, e, ws, ws_bytes, st);
 }
 
 // debug: how many clusters of the hybrid kernel the device can hold at once (cudaOccupancyMaxActiveClusters)
