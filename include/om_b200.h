@@ -354,8 +354,14 @@ void om_debug_force_generic_sinkhorn(int on);
  * 1: FP32-FFMA cluster kernel, 2: generic kernels, 3: tcgen05 kernel with the log-domain loop forced,
  * 4: tcgen05 kernel with the 3xTF32 similarity GEMM forced (default: two-term fp16 split),
  * 5: generic kernels with the log-domain loop forced (2: scaling form when safe),
- * 7: generic kernels with the FP32 FFMA cost GEMM (2 and 5 run the cost GEMM on tcgen05 when D % 32 == 0). */
+ * 7: generic kernels with the FP32 FFMA cost GEMM (2 and 5 run the cost GEMM on tcgen05 when D % 32 == 0),
+ * 8: the 8-CTA tcgen05 kernel (K <= 512) / generic kernels where 0 takes the hybrid-resident kernel,
+ * 9: the streaming kernels of the beyond-1024-keypoint path (sinkhorn_xl.cu) at any size they are eligible for
+ *    (query the workspace size with the variant already set). */
 void om_debug_sinkhorn_variant(int variant);
+/* Streaming path: bit 0 set (default 1): odd iterations sweep the matrix backwards (L2 reuse), clear: every sweep runs
+ * forwards; bit 1 set: plain stream order instead of programmatic dependent launch between its kernels. */
+void om_debug_xl_reverse(int on);
 /* Device buffer of (B*8 CTAs) x 12 int64: the tcgen05 kernel stores clock64 stamps of its phases there
  * (NULL switches tracing off).  Used by tools/sinkhorn_trace.py only. */
 void om_debug_sinkhorn_trace(long long* device_buffer);

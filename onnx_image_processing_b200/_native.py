@@ -106,6 +106,7 @@ SIGNATURES = {
     "om_debug_score_variant": (None, [c_int]),
     "om_debug_force_generic_sinkhorn": (None, [c_int]),
     "om_debug_sinkhorn_variant": (None, [c_int]),
+    "om_debug_xl_reverse": (None, [c_int]),
     "om_debug_sinkhorn_trace": (None, [c_void_p]),
     "om_debug_hy_max_clusters": (c_int, [c_int]),
 }

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libom_b200.so")
-SOURCES = ["api.cu", "detect.cu", "bad.cu", "sinkhorn.cu", "sinkhorn_tc.cu", "sinkhorn_hy.cu", "matches.cu", "essential.cu", "ingest.cu"]
+SOURCES = ["api.cu", "detect.cu", "bad.cu", "sinkhorn.cu", "sinkhorn_tc.cu", "sinkhorn_hy.cu", "sinkhorn_xl.cu", "matches.cu", "essential.cu", "ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -61,9 +61,11 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* d, long long r
 constexpr int CT = 128, CK = 16, CPITCH = CT + 4;
 __global__ void __launch_bounds__(256, 2) cost_l2_kernel(const float* d1, const float* d2, const float* n1, const float* n2,
                                                       int N, int M, int D, float eps, float dustbin, int as_exp, float* S,
-                                                      const unsigned int* only_if) {
+                                                      const unsigned int* only_if, int ld, size_t zs, int n1s, int n2s,
+                                                      int flag_per_pair) {
     __shared__ __align__(16) float As[2][CK][CPITCH];
-    if (only_if != nullptr && *only_if == 0u) return;                 // the tensor-core kernel did this launch's work
+    // the tensor-core kernel did this launch's (flag_per_pair: this pair's) work unless the flag is set
+    if (only_if != nullptr && only_if[flag_per_pair ? blockIdx.z : 0] == 0u) return;
     __shared__ __align__(16) float Bs[2][CK][CPITCH];
     const int z = blockIdx.z, i0 = blockIdx.y * CT, j0 = blockIdx.x * CT;
     const float* A = d1 + (size_t)z * N * D;
@@ -127,22 +129,22 @@ __global__ void __launch_bounds__(256, 2) cost_l2_kernel(const float* d1, const 
         if (c + 1 < nchunk) stash(buf ^ 1);
         __syncthreads();
     }
-    float* Sz = S + (size_t)z * (N + 1) * (M + 1);
+    float* Sz = S + (size_t)z * zs;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int i = i0 + (r >> 2) * 64 + ty * 4 + (r & 3);
         if (i > N) continue;
-        const float n1i = i < N ? n1[(size_t)z * N + i] : 0.0f;
+        const float n1i = i < N ? n1[(size_t)z * n1s + i] : 0.0f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = j0 + (q >> 2) * 64 + tx * 4 + (q & 3);
             if (j > M) continue;
             float v = dustbin;
             if (i < N && j < M) {
-                const float cost = fmaxf(__fsub_rn(__fadd_rn(n1i, n2[(size_t)z * M + j]), __fmul_rn(2.0f, acc[r][q])), 0.0f);
+                const float cost = fmaxf(__fsub_rn(__fadd_rn(n1i, n2[(size_t)z * n2s + j]), __fmul_rn(2.0f, acc[r][q])), 0.0f);
                 v = __fdiv_rn(-cost, eps);
             }
-            Sz[(size_t)i * (M + 1) + j] = as_exp ? expf(v) : v;
+            Sz[(size_t)i * ld + j] = as_exp ? expf(v) : v;
         }
     }
 }
@@ -337,7 +339,8 @@ int sinkhorn_generic(const float* d1, const float* d2, int B, int N, int M, int 
         sqnorm_kernel<<<(unsigned)(((long long)B * M + 7) / 8), 256, 0, st>>>(d2, (long long)B * M, D, w.n2, ovf);
         OM_AFTER_LAUNCH();
         if (tc) OM_TRY(cost_tc_launch(d1, d2, w.n1, w.n2, B, N, M, D, eps, dustbin, scaling, P, ovf, st));
-        cost_l2_kernel<<<dim3((M + CT) / CT, (N + CT) / CT, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, scaling, P, ovf);
+        cost_l2_kernel<<<dim3((M + CT) / CT, (N + CT) / CT, B), 256, 0, st>>>(d1, d2, w.n1, w.n2, N, M, D, eps, dustbin, scaling, P, ovf,
+                                                                               M + 1, (size_t)(N + 1) * (M + 1), N, M, 0);
         OM_AFTER_LAUNCH();
     }
     if (scaling) {
@@ -651,9 +654,31 @@ int sinkhorn_cluster(const float* d1, const float* d2, int B, int N, int M, int 
 // 7: generic kernels with the FP32 FFMA cost GEMM (2 / 5: cost GEMM on tcgen05 when D % 32 == 0)
 // 0 takes the hybrid-resident cluster kernel (sinkhorn_hy.cu) whenever it is eligible; 8: the 8-CTA tcgen05 kernel as 0 did
 // before the hybrid kernel existed (K <= 512) / the generic kernels (K > 512)
+// 9: the streaming kernels of sinkhorn_xl.cu at any size they are eligible for (0 takes them beyond the hybrid kernel's sizes)
 int g_sinkhorn_variant = 0;
 
 }  // namespace
+
+bool sinkhorn_xl_eligible(int N, int M, int D, float eps, float unused, int distance_l1);
+size_t sinkhorn_xl_workspace_bytes(int B, int N, int M, int D);
+int sinkhorn_xl_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                       float* P, void* ws, size_t ws_bytes, cudaStream_t st);
+extern int g_hy_allow_16;
+
+int cost_l2_fallback_launch(const float* d1, const float* d2, const float* n1, int n1_stride, const float* n2, int n2_stride, int B,
+                            int N, int M, int D, float eps, float dustbin, float* S, int ld, size_t zstride,
+                            const unsigned int* per_pair_flag, cudaStream_t st) {
+    cost_l2_kernel<<<dim3((M + CT) / CT, (N + CT) / CT, B), 256, 0, st>>>(d1, d2, n1, n2, N, M, D, eps, dustbin, 1, S, per_pair_flag, ld,
+                                                                           zstride, n1_stride, n2_stride, 1);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
+// does this problem size ask for the streaming kernels' workspace (beyond the hybrid kernel's sizes, or forced by the test hook)?
+static bool xl_sized(int N, int M, int D) {
+    if (D % 32 != 0) return false;
+    return g_sinkhorn_variant == 9 || N > 1024 || M > 1024 || (!g_hy_allow_16 && (N > 512 || M > 512));
+}
 
 size_t sinkhorn_workspace_bytes(int B, int N, int M, int D) {
     (void)D;
@@ -662,7 +687,9 @@ size_t sinkhorn_workspace_bytes(int B, int N, int M, int D) {
            align_up((size_t)B * (N + 1) * sizeof(float)) + align_up((size_t)B * (M + 1) * sizeof(float)) +
            align_up((size_t)B * ((N + 1 + XR - 1) / XR) * (M + 1) * sizeof(float));   // column partials of the scaling-form generic path
     const size_t hy = D % 32 == 0 ? sinkhorn_hy_workspace_bytes(B, N, M, D) : 0;       // packed fp16 operands of the hybrid kernel
-    return generic > hy ? generic : hy;
+    const size_t xl = xl_sized(N, M, D) ? sinkhorn_xl_workspace_bytes(B, N, M, D) : 0; // packed operands + aligned K of the streaming kernels
+    const size_t m = generic > hy ? generic : hy;
+    return m > xl ? m : xl;
 }
 
 static size_t generic_workspace_bytes(int B, int N, int M) {
@@ -685,7 +712,7 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
     if (iterations <= 0 || !(epsilon > 0.0f)) return OM_ERR_PARAM;        // sinkhorn.py:66-69
     if (B > 65535) return OM_ERR_LIMIT;
     const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && g_sinkhorn_variant != 2 &&
-                      g_sinkhorn_variant != 5 && g_sinkhorn_variant != 7 && (long long)B * CL < (1ll << 31);
+                      g_sinkhorn_variant != 5 && g_sinkhorn_variant != 7 && g_sinkhorn_variant != 9 && (long long)B * CL < (1ll << 31);
     g_generic_allow_scaling = g_sinkhorn_variant != 5;
     g_generic_tc = g_sinkhorn_variant != 7;
     if (g_sinkhorn_variant == 0 && (long long)B * 16 < (1ll << 31) &&
@@ -698,6 +725,9 @@ int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D
         return sinkhorn_cluster_tc(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
     }
     if (fast) return sinkhorn_cluster(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, st);
+    if ((g_sinkhorn_variant == 0 || g_sinkhorn_variant == 9) && sinkhorn_xl_eligible(N, M, D, epsilon, unused_score, distance_l1) &&
+        ws != nullptr && ws_bytes >= sinkhorn_xl_workspace_bytes(B, N, M, D))
+        return sinkhorn_xl_launch(d1, d2, B, N, M, D, iterations, epsilon, unused_score, P, ws, ws_bytes, st);
     if (ws == nullptr || ws_bytes < generic_workspace_bytes(B, N, M)) return OM_ERR_WORKSPACE;
     // dustbin score is computed in double by the reference (python floats) and cast once, sinkhorn.py:182
     const float dustbin = (float)(-(double)unused_score / (double)epsilon);

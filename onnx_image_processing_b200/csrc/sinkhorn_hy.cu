@@ -953,6 +953,15 @@ int launch_hy(const HyArgs& a, int B, cudaStream_t st) {
 
 }  // namespace
 
+// the packing kernel for other callers (sinkhorn_xl.cu): `tiles` tiles of Rp rows per pair, G 16-byte K groups per chunk
+int pack_f16_launch(const float* d, int B, int rows, int D, int Rp, int tiles, int G, unsigned char* out, float* norms,
+                    unsigned int* ovf, cudaStream_t st) {
+    const size_t np = (size_t)tiles * Rp;
+    pack_f16_kernel<<<dim3((unsigned)((np / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d, rows, D, Rp, tiles, G, out, norms, ovf);
+    OM_AFTER_LAUNCH();
+    return OM_OK;
+}
+
 extern long long* g_tc_trace;       // sinkhorn_tc.cu (debug stamps)
 int g_hy_allow_16 = 1;              // test hook: 0 keeps K in (512, 1024] on the generic path
 

@@ -213,7 +213,7 @@ def test_gather_functions():
 # Sinkhorn
 # ------------------------------------------------------------------------------------------
 VARIANTS = {0: "hybrid", 1: "ffma", 2: "generic", 3: "tcgen05-log", 4: "tcgen05-tf32", 5: "generic-log", 7: "generic-ffma-cost",
-            8: "tcgen05-8cta"}
+            8: "tcgen05-8cta", 9: "streaming"}
 
 
 def _with_variant(variant, fn):
@@ -226,7 +226,7 @@ def _with_variant(variant, fn):
 
 
 @pytest.mark.parametrize("name", G.names("sinkhorn"))
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 8], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 8, 9], ids=lambda v: VARIANTS[v])
 def test_sinkhorn_golden(name, variant):
     g = G.load(name)
     got = _with_variant(variant, lambda: om.SinkhornMatcher(**g["kwargs"]).to(DEV)(*_cuda(g["desc1"], g["desc2"])))
@@ -236,7 +236,7 @@ def test_sinkhorn_golden(name, variant):
     assert m64["core"] <= PR.PROB_TOL, m64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 8], ids=lambda v: VARIANTS[v])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 8, 9], ids=lambda v: VARIANTS[v])
 @pytest.mark.parametrize("N,M,eps,unused", [(512, 512, 1.0, 1.0), (512, 512, 0.05, 1.0), (300, 512, 0.1, 0.5),
                                             (512, 77, 0.05, 2.0), (1, 1, 1.0, 1.0), (64, 64, 0.02, 2.0),
                                             (509, 511, 0.03, 1.0), (512, 512, 0.2, 0.0)])
@@ -262,7 +262,7 @@ def test_sinkhorn_variants_agree_on_matched_descriptors():
     d1 = torch.nn.functional.normalize(torch.randn(3, 512, 256, generator=g), dim=-1)
     d2 = torch.nn.functional.normalize(d1[:, torch.randperm(512, generator=g)] + 0.02 * torch.randn(3, 512, 256, generator=g), dim=-1)
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.05, 1.0).float()
-    for variant in (0, 1, 2, 3, 4, 5, 7, 8):
+    for variant in (0, 1, 2, 3, 4, 5, 7, 8, 9):
         got = _with_variant(variant, lambda: om.SinkhornMatcher(20, 0.05).to(DEV)(*_cuda(d1, d2)))
         m = PR.prob_metrics(got, ref)
         assert PR.probs_ok(m), (VARIANTS[variant], m)
@@ -278,14 +278,24 @@ def test_sinkhorn_descriptors_beyond_fp16_range():
     ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.5, 1.0).float()
     got = om.SinkhornMatcher(20, eps, unused).to(DEV)(*_cuda(d1 * scale, d2 * scale))
     assert PR.probs_ok(PR.prob_metrics(got, ref)), PR.prob_metrics(got, ref)
+    # streaming path: an out-of-range pair goes to the FP32 cost kernel, an in-range pair of the same call stays on tcgen05
+    got9 = _with_variant(9, lambda: om.SinkhornMatcher(20, eps, unused).to(DEV)(*_cuda(d1 * scale, d2 * scale)))
+    assert PR.probs_ok(PR.prob_metrics(got9, ref)), PR.prob_metrics(got9, ref)
+    mixed1, mixed2 = torch.cat([d1[:1] * scale, d1[1:]]), torch.cat([d2[:1] * scale, d2[1:]])
+    ref_mixed = torch.cat([ref[:1], O.sinkhorn(d1[1:].double(), d2[1:].double(), 20, float(eps), float(unused)).float()])
+    got9m = _with_variant(9, lambda: om.SinkhornMatcher(20, eps, unused).to(DEV)(*_cuda(mixed1, mixed2)))
+    assert PR.probs_ok(PR.prob_metrics(got9m, ref_mixed)), PR.prob_metrics(got9m, ref_mixed)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 5, 7], ids=lambda v: {0: "hybrid16-or-scaling", 2: "scaling", 5: "log-domain", 7: "ffma-cost"}[v])
+@pytest.mark.parametrize("variant", [0, 2, 5, 7, 9], ids=lambda v: {0: "hybrid16-or-streaming", 2: "scaling", 5: "log-domain", 7: "ffma-cost",
+                                                                    9: "streaming"}[v])
 @pytest.mark.parametrize("N,M,eps,dist", [(700, 700, 0.05, "l2"), (1024, 1024, 0.05, "l2"), (600, 901, 1.0, "l2"), (530, 520, 0.2, "l1"),
-                                          (1024, 300, 0.1, "l2"), (513, 1000, 0.05, "l2"), (1100, 900, 0.1, "l2")])
+                                          (1024, 300, 0.1, "l2"), (513, 1000, 0.05, "l2"), (1100, 900, 0.1, "l2"),
+                                          (1500, 2048, 0.05, "l2"), (2147, 1025, 0.2, "l2")])
 def test_sinkhorn_large_k_generic_path(N, M, eps, dist, variant):
     """Beyond 512 x 512 (the export default K = 1024 and config 5's K = 2048 live here): the 16-CTA hybrid-resident cluster
-    kernel up to 1024 x 1024 (variant 0), the global-memory kernels in scaling form and in log-domain form against the oracle."""
+    kernel up to 1024 x 1024 and the streaming kernels of sinkhorn_xl.cu beyond (variant 0; 9: the streaming kernels at every
+    size), the older global-memory kernels in scaling form and in log-domain form, all against the oracle."""
     g = torch.Generator().manual_seed(5)
     d1 = torch.nn.functional.normalize(torch.randn(2, N, 256, generator=g), dim=-1)
     pick = (torch.randperm(max(N, M), generator=g) % N)[:M]
@@ -294,6 +304,29 @@ def test_sinkhorn_large_k_generic_path(N, M, eps, dist, variant):
     got = _with_variant(variant, lambda: om.SinkhornMatcher(20, eps, 1.0, dist).to(DEV)(*_cuda(d1, d2)))
     m = PR.prob_metrics(got, ref)
     assert PR.probs_ok(m), m
+
+
+def test_sinkhorn_streaming_path_is_batch_invariant_and_deterministic():
+    """sinkhorn_xl.cu: a pair's P must not depend on the batch it came in (units of 16 rows, fixed combination order), on the
+    sweep direction's L2 history or on programmatic dependent launch; bit-identical across runs."""
+    g = torch.Generator().manual_seed(11)
+    d1 = torch.nn.functional.normalize(torch.randn(5, 1300, 128, generator=g), dim=-1)
+    d2 = torch.nn.functional.normalize(d1[:, torch.randperm(1300, generator=g)][:, :1201] + 0.2 * torch.randn(5, 1201, 128, generator=g), dim=-1)
+    m = om.SinkhornMatcher(20, 0.1, 1.0).to(DEV)
+    full = m(*_cuda(d1, d2)).cpu()
+    again = m(*_cuda(d1, d2)).cpu()
+    assert torch.equal(full, again)
+    for i in (0, 3, 4):
+        assert torch.equal(m(*_cuda(d1[i:i + 1], d2[i:i + 1])).cpu()[0], full[i]), i
+    lib = _native.lib()
+    try:
+        for mode in (0, 2, 3):                       # forwards-only sweeps, no dependent launch, both
+            lib.om_debug_xl_reverse(mode)
+            assert torch.equal(m(*_cuda(d1, d2)).cpu(), full), mode
+    finally:
+        lib.om_debug_xl_reverse(1)
+    ref = O.sinkhorn(d1.double(), d2.double(), 20, 0.1, 1.0).float()
+    assert PR.probs_ok(PR.prob_metrics(full, ref))
 
 
 # ------------------------------------------------------------------------------------------
