@@ -42,6 +42,25 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     dst_smem), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+// L2 policy of the matrix reads: a fixed (address-hashed) fraction of the lines is kept with priority, the rest streams
+// through -- with a matrix larger than L2 the kept part survives from one sweep to the next whatever the order
+__device__ __forceinline__ uint64_t l2_policy(int id) {
+    uint64_t pol = 0;
+    switch (id) {
+        case 1: asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); break;
+        case 2: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(pol)); break;
+        case 3: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.75;" : "=l"(pol)); break;
+        case 4: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.25;" : "=l"(pol)); break;
+        case 5: asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); break;
+        case 6: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.625;" : "=l"(pol)); break;
+        default: break;
+    }
+    return pol;
+}
 // UMMA shared-memory descriptor, no swizzle, K-major (cute/arch/mma_sm100_desc.hpp layout)
 __device__ __forceinline__ uint64_t xdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
@@ -248,6 +267,7 @@ struct SweepArgs {
     float* a;                                      // [z][Np8]
     float* Tpart;                                  // [z][upp][Mp]
     int N, Np8, Mp, upp, total, reverse;
+    int policy;                                    // L2 policy of the matrix reads (l2_policy); bit 3: one bulk copy per row
     size_t zstride;
     float mu_dust;                                 // mu_N = M (sinkhorn.py:197-198)
 };
@@ -258,27 +278,33 @@ __global__ void __launch_bounds__(XS_THREADS, 1) xs_sweep_kernel(SweepArgs p) {
     float* sK = ssm;                                               // [XS_SLOTS][XS_ROWS][Mp]
     float* sBb = ssm + (size_t)XS_SLOTS * XS_ROWS * Mp;            // [3][Mp]: b of the unit being processed (by unit count % 3)
     float* sA = sBb + (size_t)3 * Mp;                              // [2][XS_ROWS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 16);         // [0..2] slot full, [3..5] slot free
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 16);         // [0..2] slot full, [3..5] slot free, [6..8] b landed
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < XS_SLOTS; ++i) {
             mbar_init(smem_u32(&bars[i]), 1u);
             mbar_init(smem_u32(&bars[XS_SLOTS + i]), (uint32_t)XS_ROWS);
+            mbar_init(smem_u32(&bars[2 * XS_SLOTS + i]), 1u);
         }
         mbar_fence_init();
     }
     __syncthreads();
-    // programmatic dependent launch: the next kernel of the stream may be scheduled now (it waits the same way before it
-    // touches memory); this grid's own reads start once the previous kernel has completed
+    // programmatic dependent launch: the next kernel of the stream may be scheduled now.  The matrix is read-only during the
+    // iterations, so its first stages are fetched at once, under the column kernel that is still finishing b; everything that
+    // depends on the previous kernels (b) or that they still read (the partial rows) waits for them (griddepcontrol.wait).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t stage_bytes = (uint32_t)(XS_ROWS * Mp * 4);
+    // a CTA owns a contiguous run of units and walks it forwards (even iterations) or backwards (odd): the same SM re-reads
+    // what it read last
+    const int u_begin = (int)((long long)p.total * blockIdx.x / gridDim.x), u_end = (int)((long long)p.total * (blockIdx.x + 1) / gridDim.x);
 
     if (warp == XS_ROWS) {
         if (lane == 0) {
+            const uint64_t pol = l2_policy(p.policy & 7);
+            bool waited = false;
             int k = 0, n = 0;
-            for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++n) {
-                const int uu = p.reverse ? p.total - 1 - u : u;
+            for (int u = u_begin; u < u_end; ++u, ++n) {
+                const int uu = p.reverse ? u_end - 1 - (u - u_begin) : u;
                 const int z = uu / p.upp, q = uu - z * p.upp;
                 const int row0 = q * (XS_UNIT * XS_ROWS);
                 const int nst = min(XS_UNIT, (p.Np8 - row0) / XS_ROWS);
@@ -287,25 +313,41 @@ __global__ void __launch_bounds__(XS_THREADS, 1) xs_sweep_kernel(SweepArgs p) {
                     const int slot = k % XS_SLOTS;
                     if (k >= XS_SLOTS) mbar_wait(smem_u32(&bars[XS_SLOTS + slot]), (uint32_t)((k / XS_SLOTS - 1) & 1));
                     const uint32_t full = smem_u32(&bars[slot]);
-                    mbar_arrive_expect_tx(full, stage_bytes + (s == 0 ? (uint32_t)(Mp * 4) : 0u));
-                    bulk_load(smem_u32(sK + (size_t)slot * XS_ROWS * Mp), Kz + (size_t)s * XS_ROWS * Mp, stage_bytes, full);
-                    if (s == 0) bulk_load(smem_u32(sBb + (size_t)(n % 3) * Mp), p.b + (size_t)z * Mp, (uint32_t)(Mp * 4), full);
+                    mbar_arrive_expect_tx(full, stage_bytes);
+                    if ((p.policy & 7) != 0) {
+                        bulk_load_hint(smem_u32(sK + (size_t)slot * XS_ROWS * Mp), Kz + (size_t)s * XS_ROWS * Mp, stage_bytes, full, pol);
+                    } else {
+                        bulk_load(smem_u32(sK + (size_t)slot * XS_ROWS * Mp), Kz + (size_t)s * XS_ROWS * Mp, stage_bytes, full);
+                    }
+                    if (s == 0) {
+                        // b of the unit's pair (buffer n % 3: free once the unit three back is done, which the slot wait above
+                        // implies); the first one of the kernel waits for the column kernel
+                        if (!waited) {
+                            asm volatile("griddepcontrol.wait;" ::: "memory");
+                            waited = true;
+                        }
+                        const uint32_t bb = smem_u32(&bars[2 * XS_SLOTS + n % 3]);
+                        mbar_arrive_expect_tx(bb, (uint32_t)(Mp * 4));
+                        bulk_load(smem_u32(sBb + (size_t)(n % 3) * Mp), p.b + (size_t)z * Mp, (uint32_t)(Mp * 4), bb);
+                    }
                 }
             }
         }
         return;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     float4 acc[3];
 #pragma unroll
     for (int jj = 0; jj < 3; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
     int k = 0, n = 0;
-    for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++n) {
-        const int uu = p.reverse ? p.total - 1 - u : u;
+    for (int u = u_begin; u < u_end; ++u, ++n) {
+        const int uu = p.reverse ? u_end - 1 - (u - u_begin) : u;
         const int z = uu / p.upp, q = uu - z * p.upp;
         const int row0 = q * (XS_UNIT * XS_ROWS);
         const int nst = min(XS_UNIT, (p.Np8 - row0) / XS_ROWS);
         const float4* b4 = reinterpret_cast<const float4*>(sBb + (size_t)(n % 3) * Mp);
+        mbar_wait(smem_u32(&bars[2 * XS_SLOTS + n % 3]), (uint32_t)((n / 3) & 1));
         for (int s = 0; s < nst; ++s, ++k) {
             const int slot = k % XS_SLOTS;
             mbar_wait(smem_u32(&bars[slot]), (uint32_t)((k / XS_SLOTS) & 1));
@@ -359,6 +401,141 @@ __global__ void __launch_bounds__(XS_THREADS, 1) xs_sweep_kernel(SweepArgs p) {
             if (g < Mp4) tp[g] = acc[jj];
             acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// xr_sweep_kernel: the same sweep with the rows in REGISTERS.  A warp owns rows w and w + 8 of every unit of its CTA: it
+// loads a whole row with coalesced 16-byte loads (one row ahead), forms the row sum against b (shared memory), knows a_i at
+// once -- no CTA barrier -- and adds a_i K_ij into its own column sums, also in registers.  At the end of a unit the eight
+// warps' column sums go through shared memory once and are added in a fixed order.  Shared-memory traffic per 8 rows: the
+// b reads and that exchange, half of what the bulk-copy form moves (stage written once, read twice), which was what bound
+// it (6.2 TB/s whether the matrix came from L2 or from HBM).
+// ------------------------------------------------------------------------------------------
+constexpr int XR_WARPS = 8;
+constexpr int XR_THREADS = XR_WARPS * 32;
+constexpr int XR_NQ = (XS_MAX_MP / 4 + 31) / 32;   // float4 column groups per lane (17)
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+struct RowRegs {
+    float4 v[XR_NQ];
+};
+
+__device__ __forceinline__ void xr_load_row(RowRegs& r, const float* row, int lane, int Mp4, bool live) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int i = 0; i < XR_NQ; ++i) {
+        const int c = lane + 32 * i;
+        r.v[i] = (live && c < Mp4) ? ldg_stream(r4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// row sum against b, a_i, column sums += a_i K_ij; returns a_i
+__device__ __forceinline__ float xr_process_row(const RowRegs& r, RowRegs& acc, const float4* b4, int lane, int Mp4, float mu, bool real) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < XR_NQ; ++i) {
+        const int c = lane + 32 * i;
+        if (c < Mp4) {
+            const float4 bv = b4[c];
+            s0 = fmaf(r.v[i].x, bv.x, s0); s1 = fmaf(r.v[i].y, bv.y, s1);
+            s2 = fmaf(r.v[i].z, bv.z, s2); s3 = fmaf(r.v[i].w, bv.w, s3);
+        }
+    }
+    const float rs = warp_sum((s0 + s1) + (s2 + s3));
+    const float av = real ? __fdividef(mu, rs) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < XR_NQ; ++i) {
+        acc.v[i].x = fmaf(r.v[i].x, av, acc.v[i].x); acc.v[i].y = fmaf(r.v[i].y, av, acc.v[i].y);
+        acc.v[i].z = fmaf(r.v[i].z, av, acc.v[i].z); acc.v[i].w = fmaf(r.v[i].w, av, acc.v[i].w);
+    }
+    return av;
+}
+
+__global__ void __launch_bounds__(XR_THREADS, 1) xr_sweep_kernel(SweepArgs p) {
+    extern __shared__ __align__(128) float rsm[];
+    const int Mp = p.Mp, Mp4 = Mp >> 2;
+    float* sB = rsm;                                               // [Mp] b of the current pair
+    float* sX = rsm + Mp;                                          // [XR_WARPS][Mp] the warps' column sums of a unit
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int u_begin = (int)((long long)p.total * blockIdx.x / gridDim.x), u_end = (int)((long long)p.total * (blockIdx.x + 1) / gridDim.x);
+    if (u_begin >= u_end) return;
+    const int step = p.reverse ? -1 : 1;
+    const int u_first = p.reverse ? u_end - 1 : u_begin;
+    const int nu = u_end - u_begin;
+    const float4* b4 = reinterpret_cast<const float4*>(sB);
+
+    auto row_ptr = [&](int uu, int h, int& gi) -> const float* {       // row (unit uu, half h) of this warp
+        const int z = uu / p.upp, q = uu - z * p.upp;
+        gi = q * (2 * XR_WARPS) + h * XR_WARPS + warp;
+        return p.Kmat + (size_t)z * p.zstride + (size_t)gi * Mp;
+    };
+
+    RowRegs ra, rb, acc;
+#pragma unroll
+    for (int i = 0; i < XR_NQ; ++i) acc.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int gia = 0, gib = 0, zprev = -1;
+    {
+        const float* pa = row_ptr(u_first, 0, gia);
+        xr_load_row(ra, pa, lane, Mp4, gia < p.Np8);
+    }
+    for (int n = 0; n < nu; ++n) {
+        const int uu = u_first + step * n;
+        const int z = uu / p.upp, q = uu - z * p.upp;
+        {
+            const float* pb = row_ptr(uu, 1, gib);
+            xr_load_row(rb, pb, lane, Mp4, gib < p.Np8);           // second row of the unit: in flight under the first
+        }
+        if (z != zprev) {                                          // a new pair: its b into shared memory
+            __syncthreads();
+            const float4* g4 = reinterpret_cast<const float4*>(p.b + (size_t)z * Mp);
+            for (int c = tid; c < Mp4; c += XR_THREADS) reinterpret_cast<float4*>(sB)[c] = __ldcg(g4 + c);
+            __syncthreads();
+            zprev = z;
+        }
+        {
+            const float av = xr_process_row(ra, acc, b4, lane, Mp4, gia == p.N ? p.mu_dust : 1.0f, gia <= p.N);
+            if (lane == 0 && gia < p.Np8) p.a[(size_t)z * p.Np8 + gia] = av;
+        }
+        if (n + 1 < nu) {                                          // first row of the next unit: in flight under the second
+            const float* pa = row_ptr(uu + step, 0, gia);
+            xr_load_row(ra, pa, lane, Mp4, gia < p.Np8);
+        }
+        {
+            const float av = xr_process_row(rb, acc, b4, lane, Mp4, gib == p.N ? p.mu_dust : 1.0f, gib <= p.N);
+            if (lane == 0 && gib < p.Np8) p.a[(size_t)z * p.Np8 + gib] = av;
+        }
+        // ---- the unit's column sums: warp sums -> shared memory -> fixed-order sum -> one partial row ----
+        {
+            float4* x4 = reinterpret_cast<float4*>(sX + (size_t)warp * Mp);
+#pragma unroll
+            for (int i = 0; i < XR_NQ; ++i) {
+                const int c = lane + 32 * i;
+                if (c < Mp4) x4[c] = acc.v[i];
+                acc.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        {
+            float4* tp = reinterpret_cast<float4*>(p.Tpart + ((size_t)z * p.upp + q) * Mp);
+            for (int g = tid; g < Mp4; g += XR_THREADS) {
+                float4 t = reinterpret_cast<const float4*>(sX)[g];
+#pragma unroll
+                for (int w = 1; w < XR_WARPS; ++w) {
+                    const float4 v = reinterpret_cast<const float4*>(sX + (size_t)w * Mp)[g];
+                    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+                }
+                tp[g] = t;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -472,6 +649,7 @@ int sm_count() {
 
 int g_xl_reverse = 1;               // test / tuning hook: 0 = every sweep walks the units forwards
 int g_xl_pdl = 1;                   // test / tuning hook: 0 = plain stream order between the sweep and column kernels
+int g_xl_policy = 0;                // tuning hook: L2 policy of the sweeps' matrix reads (l2_policy)
 
 // limits: squared-L2 cost, scaling form in range (as the generic path's test), D % 32 == 0, M + 1 <= XS_MAX_MP
 bool sinkhorn_xl_eligible(int N, int M, int D, float eps, float unused, int distance_l1) {
@@ -526,7 +704,8 @@ int sinkhorn_xl_launch(const float* d1, const float* d2, int B, int N, int M, in
     SweepArgs s{};
     s.Kmat = w.Kmat; s.b = w.b; s.a = w.a; s.Tpart = w.Tpart;
     s.N = N; s.Np8 = w.Np8; s.Mp = w.Mp; s.upp = w.upp; s.total = B * w.upp; s.zstride = zstride; s.mu_dust = (float)M;
-    const size_t ssmem = ((size_t)(XS_SLOTS * (XS_ROWS + 1)) * w.Mp + 16) * 4 + 64;
+    s.policy = g_xl_policy;
+    const size_t ssmem = ((size_t)(XS_SLOTS * (XS_ROWS + 1)) * w.Mp + 16) * 4 + 96;
     OM_TRY(set_smem(xs_sweep_kernel, ssmem));
     const int sgrid = s.total < nsm ? s.total : nsm;
     // sweep and column kernels are launched with programmatic stream serialization: each is scheduled while its
@@ -539,9 +718,15 @@ int sinkhorn_xl_launch(const float* d1, const float* d2, int B, int N, int M, in
     cs.attrs = pdl; cs.numAttrs = 1;
     cc.gridDim = dim3((unsigned)((M + 32) / 32), (unsigned)B, 1); cc.blockDim = dim3(256, 1, 1); cc.dynamicSmemBytes = 0; cc.stream = st;
     cc.attrs = pdl; cc.numAttrs = 1;
+    const bool rows_in_regs = (g_xl_policy & 8) != 0;                  // tuning hook bit 3 (default: the bulk-copy form, 7 % faster)
+    const size_t rsmem = (size_t)(XR_WARPS + 1) * w.Mp * sizeof(float);
+    OM_TRY(set_smem(xr_sweep_kernel, rsmem));
+    cudaLaunchConfig_t cr = cs;
+    cr.blockDim = dim3(XR_THREADS, 1, 1); cr.dynamicSmemBytes = rsmem;
     for (int it = 0; it < iterations; ++it) {
         s.reverse = g_xl_reverse ? (it & 1) : 0;
-        OM_CUDA(cudaLaunchKernelEx(&cs, xs_sweep_kernel, s));
+        if (rows_in_regs) OM_CUDA(cudaLaunchKernelEx(&cr, xr_sweep_kernel, s));
+        else OM_CUDA(cudaLaunchKernelEx(&cs, xs_sweep_kernel, s));
         OM_AFTER_LAUNCH();
         OM_CUDA(cudaLaunchKernelEx(&cc, xs_col_kernel, (const float*)w.Tpart, w.b, w.upp, M, w.Mp, (float)N));
         OM_AFTER_LAUNCH();
@@ -563,4 +748,5 @@ int sinkhorn_xl_launch(const float* d1, const float* d2, int B, int N, int M, in
 extern "C" void om_debug_xl_reverse(int on) {
     om::g_xl_reverse = on & 1;
     om::g_xl_pdl = (on & 2) ? 0 : 1;       // bit 1: switch programmatic dependent launch off
+    om::g_xl_policy = (on >> 4) & 15;      // bits 4..7: L2 policy of the sweeps
 }

@@ -37,6 +37,9 @@ def run(B, K, D, eps, variants, reps=10):
 
 
 if __name__ == "__main__":
+    if "--policies" in sys.argv:
+        run(8, 2048, 256, 1.0, [(0, 1), (0, 0), (0, 1 + 16), (0, 1 + 32), (0, 1 + 48), (0, 1 + 64), (0, 1 + 80), (0, 1 + 96), (0, 0 + 32), (0, 0 + 48), (0, 0 + 96)])
+        sys.exit(0)
     run(8, 2048, 256, 1.0, [(2, 1), (0, 1), (0, 0), (0, 3)])
     run(8, 2048, 256, 0.05, [(2, 1), (0, 1)])
     run(2, 1100, 256, 0.1, [(2, 1), (0, 1)])
