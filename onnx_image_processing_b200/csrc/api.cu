@@ -293,7 +293,11 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
         if (e.matches && e.max_matches <= 0) return OM_ERR_SHAPE;
         if (e.filters && e.filter_valid == nullptr) return OM_ERR_NULL;
     }
+    // the streaming kernels beyond 1024 keypoints pack their operands the same way (plain P output only)
+    const bool xl = !hy && !ex && p->iterations > 0 && probs != nullptr &&
+                    sinkhorn_routes_to_xl(p->B, p->K, p->K, p->P, p->epsilon, p->unused_score, p->distance_l1, w.sink, w.sink_bytes);
     if (hy) OM_TRY(sinkhorn_hy_prepare(p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, st));   // before the fork: ordered ahead of both chains
+    if (xl) OM_TRY(sinkhorn_xl_prepare(p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, st));
     SideSet* set = nullptr;
     std::unique_lock<std::mutex> busy;
     int nside = 0;                              // side streams that were forked and must be joined, on every path
@@ -342,6 +346,7 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
                 OM_TRY(descriptors(s, chain[s], 0));
             }
             if (hy) OM_TRY(sinkhorn_hy_pack(s, ds[s], p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, chain[s]));
+            if (xl) OM_TRY(sinkhorn_xl_pack(s, ds[s], p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, chain[s]));
         }
         return OM_OK;
     };
@@ -355,6 +360,8 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
     if (hy)
         return sinkhorn_hy_run(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, probs, ex ? epi : nullptr,
                                w.sink, w.sink_bytes, st);
+    if (xl)
+        return sinkhorn_xl_run(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, probs, w.sink, w.sink_bytes, st);
     if (ex)
         return sinkhorn_ex_launch(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, p->distance_l1,
                                   probs, *epi, w.sink, w.sink_bytes, st);

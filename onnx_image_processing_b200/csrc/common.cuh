@@ -196,6 +196,13 @@ int sinkhorn_hy_run(const float* d1, const float* d2, int B, int N, int M, int D
                     float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st);
 bool sinkhorn_routes_to_hy(int B, int N, int M, int D, float epsilon, float unused_score, int distance_l1, const void* ws,
                            size_t ws_bytes);
+// streaming kernels beyond the hybrid kernel's sizes (sinkhorn_xl.cu): the same three steps
+bool sinkhorn_routes_to_xl(int B, int N, int M, int D, float epsilon, float unused_score, int distance_l1, const void* ws,
+                           size_t ws_bytes);
+int sinkhorn_xl_prepare(int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st);
+int sinkhorn_xl_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st);
+int sinkhorn_xl_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                    float* P, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t sinkhorn_ex_workspace_bytes(int B, int N, int M, int D);
 // Sinkhorn + optional outputs; P may be null when the epilogue is fused (otherwise it is kept in the workspace)
 int sinkhorn_ex_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,

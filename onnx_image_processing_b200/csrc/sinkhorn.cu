@@ -705,6 +705,19 @@ bool sinkhorn_routes_to_hy(int B, int N, int M, int D, float epsilon, float unus
            ws_bytes >= sinkhorn_hy_workspace_bytes(B, N, M, D);
 }
 
+// will sinkhorn_launch take the streaming kernels (sinkhorn_xl.cu) for this problem?  (the fused matcher then packs each image's
+// descriptors on that image's stream)
+bool sinkhorn_routes_to_xl(int B, int N, int M, int D, float epsilon, float unused_score, int distance_l1, const void* ws,
+                           size_t ws_bytes) {
+    if (B <= 0 || B > 65535 || N <= 0 || M <= 0 || D <= 0 || !(epsilon > 0.0f)) return false;
+    if (sinkhorn_routes_to_hy(B, N, M, D, epsilon, unused_score, distance_l1, ws, ws_bytes)) return false;
+    const bool fast = !distance_l1 && N <= RPC * CL && M <= MAXM && D % KC == 0 && g_sinkhorn_variant != 2 &&
+                      g_sinkhorn_variant != 5 && g_sinkhorn_variant != 7 && g_sinkhorn_variant != 9 && (long long)B * CL < (1ll << 31);
+    if (fast) return false;
+    return (g_sinkhorn_variant == 0 || g_sinkhorn_variant == 9) && sinkhorn_xl_eligible(N, M, D, epsilon, unused_score, distance_l1) &&
+           ws != nullptr && ws_bytes >= sinkhorn_xl_workspace_bytes(B, N, M, D);
+}
+
 int sinkhorn_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float epsilon,
                     float unused_score, int distance_l1, float* P, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (d1 == nullptr || d2 == nullptr || P == nullptr) return OM_ERR_NULL;

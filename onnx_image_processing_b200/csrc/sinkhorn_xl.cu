@@ -669,15 +669,43 @@ int cost_l2_fallback_launch(const float* d1, const float* d2, const float* n1, i
                             int N, int M, int D, float eps, float dustbin, float* S, int ld, size_t zstride,
                             const unsigned int* per_pair_flag, cudaStream_t st);
 
+// The steps of a call, separately launchable so that the fused matcher can pack each image's descriptors on that image's own
+// stream as soon as they exist (as it does for the hybrid kernel): prepare (clears the per-pair range flags), pack (which = 0:
+// desc1 rows, 1: desc2 rows), run (cost matrix, iterations, P).
+int sinkhorn_xl_prepare(int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws == nullptr || ws_bytes < sinkhorn_xl_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    const XlWs w = xl_carve(ws, B, N, M, D);
+    OM_CUDA(cudaMemsetAsync(w.ovf, 0, (size_t)B * sizeof(unsigned int), st));
+    return OM_OK;
+}
+
+int sinkhorn_xl_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (d == nullptr) return OM_ERR_NULL;
+    if (ws == nullptr || ws_bytes < sinkhorn_xl_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    const XlWs w = xl_carve(ws, B, N, M, D);
+    if (which == 0) return pack_f16_launch(d, B, N, D, XB, w.T1, XG, w.d1p, w.n1, w.ovf, st);
+    return pack_f16_launch(d, B, M, D, XA, w.T2, XG, w.d2p, w.n2, w.ovf, st);
+}
+
+int sinkhorn_xl_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                    float* P, void* ws, size_t ws_bytes, cudaStream_t st);
+
 int sinkhorn_xl_launch(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
                        float* P, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (!sinkhorn_xl_eligible(N, M, D, eps, unused, 0)) return OM_ERR_PARAM;
+    OM_TRY(sinkhorn_xl_prepare(B, N, M, D, ws, ws_bytes, st));
+    OM_TRY(sinkhorn_xl_pack(0, d1, B, N, M, D, ws, ws_bytes, st));
+    OM_TRY(sinkhorn_xl_pack(1, d2, B, N, M, D, ws, ws_bytes, st));
+    return sinkhorn_xl_run(d1, d2, B, N, M, D, iterations, eps, unused, P, ws, ws_bytes, st);
+}
+
+int sinkhorn_xl_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
+                    float* P, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!sinkhorn_xl_eligible(N, M, D, eps, unused, 0)) return OM_ERR_PARAM;
+    if (d1 == nullptr || d2 == nullptr || P == nullptr) return OM_ERR_NULL;
     if (ws == nullptr || ws_bytes < sinkhorn_xl_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
     const XlWs w = xl_carve(ws, B, N, M, D);
     const size_t zstride = (size_t)w.Np8 * w.Mp;
-    OM_CUDA(cudaMemsetAsync(w.ovf, 0, (size_t)B * sizeof(unsigned int), st));
-    OM_TRY(pack_f16_launch(d1, B, N, D, XB, w.T1, XG, w.d1p, w.n1, w.ovf, st));
-    OM_TRY(pack_f16_launch(d2, B, M, D, XA, w.T2, XG, w.d2p, w.n2, w.ovf, st));
     const double log2e = 1.4426950408889634;
     const float dustbin = (float)(-(double)unused / (double)eps);          // computed in double by the reference, sinkhorn.py:182
     const int nsm = sm_count();
