@@ -99,7 +99,8 @@ constexpr int XC_STAGES = 4;
 constexpr int XA_TERM = XG * XA * 16;              // bytes of one fp16 term of a d2 chunk (8 KB)
 constexpr int XB_TERM = XG * XB * 16;              // ... of a d1 chunk (16 KB)
 constexpr int XC_STAGE = 2 * XA_TERM + 2 * XB_TERM;   // 48 KB
-constexpr int XC_THREADS = 320;                    // warp 0: copy issuer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int XC_EPI_WARPS = 16;                   // four per tensor-memory lane quadrant, 64 accumulator columns each
+constexpr int XC_THREADS = 64 + 32 * XC_EPI_WARPS;  // warp 0: copy issuer, warp 1: MMA issuer, the others: epilogue
 constexpr size_t XC_SMEM = (size_t)XC_STAGES * XC_STAGE + 128;
 
 struct CostArgs {
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(XC_THREADS, 1) cost_pk_kernel(CostArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < 10; ++i) mbar_init(smem_u32(&bars[i]), 1u);
-        mbar_init(smem_u32(&bars[10]), 8u);
-        mbar_init(smem_u32(&bars[11]), 8u);
+        mbar_init(smem_u32(&bars[10]), (uint32_t)XC_EPI_WARPS);
+        mbar_init(smem_u32(&bars[11]), (uint32_t)XC_EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -191,8 +192,9 @@ __global__ void __launch_bounds__(XC_THREADS, 1) cost_pk_kernel(CostArgs a) {
         }
     } else {
         // epilogue warp (q, h): tensor-memory lanes 32q..32q+31 (the quadrant a warp may read is warp % 4), accumulator columns
-        // 128h..128h+127: lane = column j of K, registers = 32 consecutive rows i -> every store instruction writes 128
+        // CW h .. CW h + CW - 1: lane = column j of K, registers = 32 consecutive rows i -> every store instruction writes 128
         // contiguous bytes of one row
+        constexpr int CW = XB / (XC_EPI_WARPS / 4);
         const int q = warp & 3, h = (warp - 2) >> 2;
         int tl = 0;
         for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
@@ -204,13 +206,13 @@ __global__ void __launch_bounds__(XC_THREADS, 1) cost_pk_kernel(CostArgs a) {
             const int j = jb * XA + 32 * q + lane;
             const bool jok = j < a.M;
             const float n2j = a.n2[((size_t)z * a.T2 + jb) * XA + 32 * q + lane];
-            const float* n1t = a.n1 + ((size_t)z * a.T1 + ib) * XB + 128 * h;
+            const float* n1t = a.n1 + ((size_t)z * a.T1 + ib) * XB + CW * h;
             float* Kz = a.Kmat + (size_t)z * a.zstride + j;
-            const int i_base = ib * XB + 128 * h;
+            const int i_base = ib * XB + CW * h;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < CW / 32; ++cc) {
                 uint32_t acc[32];
-                xtmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * XB + 128 * h + 32 * cc), acc);
+                xtmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * XB + CW * h + 32 * cc), acc);
 #pragma unroll
                 for (int ii = 0; ii < 32; ++ii) {
                     const int i = i_base + 32 * cc + ii;
@@ -596,8 +598,27 @@ __global__ void __launch_bounds__(256) xs_finalize_kernel(const float* Kmat, con
             reinterpret_cast<float4*>(st)[c] = make_float4((ai * kv.x) * bv.x, (ai * kv.y) * bv.y, (ai * kv.z) * bv.z, (ai * kv.w) * bv.w);
         }
         __syncwarp();
-        float* out = P + ((size_t)z * (N + 1) + i) * (M + 1);
-        for (int j = lane; j <= M; j += 32) __stcs(out + j, st[j]);
+        // 16-byte stores: the row starts `o` floats past a 16-byte boundary of P, so the aligned chunks of the output are
+        // chunks of the staged row shifted by j0 = (4 - o) % 4 elements (two aligned shared-memory reads and a select)
+        const size_t rowoff = ((size_t)z * (N + 1) + i) * (M + 1);
+        float* out = P + rowoff;
+        const int j0 = (int)((4 - (rowoff & 3)) & 3);
+        const int nch = (M + 1 - j0) >> 2;                           // whole 4-float chunks out[j0 + 4m .. j0 + 4m + 3], all <= M
+        if (lane < j0 && lane <= M) __stcs(out + lane, st[lane]);
+        const float4* st4 = reinterpret_cast<const float4*>(st);
+        for (int m = lane; m < nch; m += 32) {
+            const float4 A = st4[m];
+            float4 v = A;
+            if (j0 != 0) {
+                const float4 Bv = st4[m + 1];
+                v = j0 == 1 ? make_float4(A.y, A.z, A.w, Bv.x) : (j0 == 2 ? make_float4(A.z, A.w, Bv.x, Bv.y) : make_float4(A.w, Bv.x, Bv.y, Bv.z));
+            }
+            __stcs(reinterpret_cast<float4*>(out + j0 + 4 * m), v);
+        }
+        {
+            const int j = j0 + 4 * nch + lane;
+            if (lane < 4 && j <= M) __stcs(out + j, st[j]);
+        }
         __syncwarp();
     }
 }
