@@ -420,6 +420,31 @@ def measure_other_configs(dev, steps):
     row = {"config": "configs[4] sparse matcher 1080x1920 k=2048", "pairs_per_step": 8, "ms_per_step": ms,
            "pairs_per_s": 8 / ms * 1e3, "steps": n}
     row.update(stage_groups(m5, "sparse", b1, 3))
+    # the streaming Sinkhorn kernels (sinkhorn_xl.cu): one sweep of the (N+1) x (M+1) float32 kernel matrix per iteration;
+    # per-iteration time = slope of the stage time over the iteration count, bytes = the matrix (algorithmic: every entry is
+    # needed once per iteration) -- the HBM-bound kernel of this configuration
+    Kk, Pn = 2048, int(m5.descriptor.num_pairs)
+    desc = torch.nn.functional.normalize(torch.randn(8, Kk, Pn, device=dev), dim=-1)
+    probs = torch.empty((8, Kk + 1, Kk + 1), device=dev)
+    sws = torch.empty(lib.om_sinkhorn_workspace_bytes(8, Kk, Kk, Pn), dtype=torch.uint8, device=dev)
+    mm = m5.matcher
+    t_it = {}
+    for its in (20, 60):
+        t_it[its] = event_time_ms(lambda: nat.check(lib.om_sinkhorn_f32(
+            ptr(desc), ptr(desc), 8, Kk, Kk, Pn, its, float(mm.epsilon), float(mm.unused_score), 0, ptr(probs), ptr(sws),
+            sws.numel(), sp), "om_sinkhorn_f32"), 3, 2, stream)
+    per_it_ms = (t_it[60] - t_it[20]) / 40.0
+    sweep_bytes = 8 * (Kk + 1) * (Kk + 1) * 4
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    row["sinkhorn_sweep_roofline"] = {
+        "kernels": "xs_sweep_kernel + xs_col_kernel (one launch each per iteration)", "bound": "hbm",
+        "algorithmic_bytes_per_iteration": sweep_bytes, "ms_per_iteration": per_it_ms,
+        "achieved": sweep_bytes / per_it_ms / 1e6, "peak": peak, "unit": "GB/s", "frac": sweep_bytes / per_it_ms / 1e6 / peak,
+        "peak_source": peak_src, "how": "slope of the Sinkhorn stage time between 20 and 60 iterations (CUDA events)"}
     rows.append(row)
     return rows
 
