@@ -362,8 +362,7 @@ void om_debug_sinkhorn_variant(int variant);
 /* Streaming path (tuning hook; outputs are bit-identical in every mode): bit 0 set (default 1): odd iterations sweep the
  * matrix backwards, clear: every sweep runs forwards; bit 1 set: plain stream order instead of programmatic dependent
  * launch between its kernels; bits 4..6: L2 eviction policy of the sweeps' bulk copies (0 none, 1 evict-last, 2 / 3 / 4 / 6
- * evict-last on 50 / 75 / 25 / 62.5 % of the lines and evict-first on the rest, 5 evict-first); bit 7: the sweep kernel
- * that keeps the matrix rows in registers instead of staging them in shared memory. */
+ * evict-last on 50 / 75 / 25 / 62.5 % of the lines and evict-first on the rest, 5 evict-first). */
 void om_debug_xl_reverse(int on);
 /* Device buffer of (B*8 CTAs) x 12 int64: the tcgen05 kernel stores clock64 stamps of its phases there
  * (NULL switches tracing off).  Used by tools/sinkhorn_trace.py only. */

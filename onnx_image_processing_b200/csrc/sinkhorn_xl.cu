@@ -262,6 +262,7 @@ constexpr int XS_UNIT = 2;                         // stages per unit (16 rows -
 constexpr int XS_CONS = XS_ROWS * 32;
 constexpr int XS_THREADS = XS_CONS + 32;           // + the copy issuer's warp
 constexpr int XS_MAX_MP = 2148;                    // 27 rows of Mp floats + barriers within 227 KB
+constexpr int XS_NQ = (XS_MAX_MP / 4 + 31) / 32;   // float4 column groups of a row per lane (17)
 
 struct SweepArgs {
     const float* Kmat;
@@ -269,7 +270,7 @@ struct SweepArgs {
     float* a;                                      // [z][Np8]
     float* Tpart;                                  // [z][upp][Mp]
     int N, Np8, Mp, upp, total, reverse;
-    int policy;                                    // L2 policy of the matrix reads (l2_policy); bit 3: one bulk copy per row
+    int policy;                                    // L2 policy of the matrix reads (l2_policy)
     size_t zstride;
     float mu_dust;                                 // mu_N = M (sinkhorn.py:197-198)
 };
@@ -350,6 +351,14 @@ __global__ void __launch_bounds__(XS_THREADS, 1) xs_sweep_kernel(SweepArgs p) {
         const int nst = min(XS_UNIT, (p.Np8 - row0) / XS_ROWS);
         const float4* b4 = reinterpret_cast<const float4*>(sBb + (size_t)(n % 3) * Mp);
         mbar_wait(smem_u32(&bars[2 * XS_SLOTS + n % 3]), (uint32_t)((n / 3) & 1));
+        // this lane's columns of b, in registers for the unit's stages (read from shared memory in every row pass they were
+        // half of its shared-memory traffic)
+        float4 breg[XS_NQ];
+#pragma unroll
+        for (int i = 0; i < XS_NQ; ++i) {
+            const int c = lane + 32 * i;
+            breg[i] = c < Mp4 ? b4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int s = 0; s < nst; ++s, ++k) {
             const int slot = k % XS_SLOTS;
             mbar_wait(smem_u32(&bars[slot]), (uint32_t)((k / XS_SLOTS) & 1));
@@ -358,10 +367,14 @@ __global__ void __launch_bounds__(XS_THREADS, 1) xs_sweep_kernel(SweepArgs p) {
             {
                 const float4* row4 = st4 + (size_t)warp * Mp4;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-                for (int c = lane; c < Mp4; c += 32) {
-                    const float4 kv = row4[c], bv = b4[c];
-                    s0 = fmaf(kv.x, bv.x, s0); s1 = fmaf(kv.y, bv.y, s1); s2 = fmaf(kv.z, bv.z, s2); s3 = fmaf(kv.w, bv.w, s3);
+#pragma unroll
+                for (int i = 0; i < XS_NQ; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < Mp4) {
+                        const float4 kv = row4[c];
+                        s0 = fmaf(kv.x, breg[i].x, s0); s1 = fmaf(kv.y, breg[i].y, s1);
+                        s2 = fmaf(kv.z, breg[i].z, s2); s3 = fmaf(kv.w, breg[i].w, s3);
+                    }
                 }
                 const float rs = warp_sum((s0 + s1) + (s2 + s3));
                 const int gi = row0 + s * XS_ROWS + warp;
@@ -403,141 +416,6 @@ __global__ void __launch_bounds__(XS_THREADS, 1) xs_sweep_kernel(SweepArgs p) {
             if (g < Mp4) tp[g] = acc[jj];
             acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// xr_sweep_kernel: the same sweep with the rows in REGISTERS.  A warp owns rows w and w + 8 of every unit of its CTA: it
-// loads a whole row with coalesced 16-byte loads (one row ahead), forms the row sum against b (shared memory), knows a_i at
-// once -- no CTA barrier -- and adds a_i K_ij into its own column sums, also in registers.  At the end of a unit the eight
-// warps' column sums go through shared memory once and are added in a fixed order.  Shared-memory traffic per 8 rows: the
-// b reads and that exchange, half of what the bulk-copy form moves (stage written once, read twice), which was what bound
-// it (6.2 TB/s whether the matrix came from L2 or from HBM).
-// ------------------------------------------------------------------------------------------
-constexpr int XR_WARPS = 8;
-constexpr int XR_THREADS = XR_WARPS * 32;
-constexpr int XR_NQ = (XS_MAX_MP / 4 + 31) / 32;   // float4 column groups per lane (17)
-
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
-struct RowRegs {
-    float4 v[XR_NQ];
-};
-
-__device__ __forceinline__ void xr_load_row(RowRegs& r, const float* row, int lane, int Mp4, bool live) {
-    const float4* r4 = reinterpret_cast<const float4*>(row);
-#pragma unroll
-    for (int i = 0; i < XR_NQ; ++i) {
-        const int c = lane + 32 * i;
-        r.v[i] = (live && c < Mp4) ? ldg_stream(r4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-// row sum against b, a_i, column sums += a_i K_ij; returns a_i
-__device__ __forceinline__ float xr_process_row(const RowRegs& r, RowRegs& acc, const float4* b4, int lane, int Mp4, float mu, bool real) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < XR_NQ; ++i) {
-        const int c = lane + 32 * i;
-        if (c < Mp4) {
-            const float4 bv = b4[c];
-            s0 = fmaf(r.v[i].x, bv.x, s0); s1 = fmaf(r.v[i].y, bv.y, s1);
-            s2 = fmaf(r.v[i].z, bv.z, s2); s3 = fmaf(r.v[i].w, bv.w, s3);
-        }
-    }
-    const float rs = warp_sum((s0 + s1) + (s2 + s3));
-    const float av = real ? __fdividef(mu, rs) : 0.0f;
-#pragma unroll
-    for (int i = 0; i < XR_NQ; ++i) {
-        acc.v[i].x = fmaf(r.v[i].x, av, acc.v[i].x); acc.v[i].y = fmaf(r.v[i].y, av, acc.v[i].y);
-        acc.v[i].z = fmaf(r.v[i].z, av, acc.v[i].z); acc.v[i].w = fmaf(r.v[i].w, av, acc.v[i].w);
-    }
-    return av;
-}
-
-__global__ void __launch_bounds__(XR_THREADS, 1) xr_sweep_kernel(SweepArgs p) {
-    extern __shared__ __align__(128) float rsm[];
-    const int Mp = p.Mp, Mp4 = Mp >> 2;
-    float* sB = rsm;                                               // [Mp] b of the current pair
-    float* sX = rsm + Mp;                                          // [XR_WARPS][Mp] the warps' column sums of a unit
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int u_begin = (int)((long long)p.total * blockIdx.x / gridDim.x), u_end = (int)((long long)p.total * (blockIdx.x + 1) / gridDim.x);
-    if (u_begin >= u_end) return;
-    const int step = p.reverse ? -1 : 1;
-    const int u_first = p.reverse ? u_end - 1 : u_begin;
-    const int nu = u_end - u_begin;
-    const float4* b4 = reinterpret_cast<const float4*>(sB);
-
-    auto row_ptr = [&](int uu, int h, int& gi) -> const float* {       // row (unit uu, half h) of this warp
-        const int z = uu / p.upp, q = uu - z * p.upp;
-        gi = q * (2 * XR_WARPS) + h * XR_WARPS + warp;
-        return p.Kmat + (size_t)z * p.zstride + (size_t)gi * Mp;
-    };
-
-    RowRegs ra, rb, acc;
-#pragma unroll
-    for (int i = 0; i < XR_NQ; ++i) acc.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int gia = 0, gib = 0, zprev = -1;
-    {
-        const float* pa = row_ptr(u_first, 0, gia);
-        xr_load_row(ra, pa, lane, Mp4, gia < p.Np8);
-    }
-    for (int n = 0; n < nu; ++n) {
-        const int uu = u_first + step * n;
-        const int z = uu / p.upp, q = uu - z * p.upp;
-        {
-            const float* pb = row_ptr(uu, 1, gib);
-            xr_load_row(rb, pb, lane, Mp4, gib < p.Np8);           // second row of the unit: in flight under the first
-        }
-        if (z != zprev) {                                          // a new pair: its b into shared memory
-            __syncthreads();
-            const float4* g4 = reinterpret_cast<const float4*>(p.b + (size_t)z * Mp);
-            for (int c = tid; c < Mp4; c += XR_THREADS) reinterpret_cast<float4*>(sB)[c] = __ldcg(g4 + c);
-            __syncthreads();
-            zprev = z;
-        }
-        {
-            const float av = xr_process_row(ra, acc, b4, lane, Mp4, gia == p.N ? p.mu_dust : 1.0f, gia <= p.N);
-            if (lane == 0 && gia < p.Np8) p.a[(size_t)z * p.Np8 + gia] = av;
-        }
-        if (n + 1 < nu) {                                          // first row of the next unit: in flight under the second
-            const float* pa = row_ptr(uu + step, 0, gia);
-            xr_load_row(ra, pa, lane, Mp4, gia < p.Np8);
-        }
-        {
-            const float av = xr_process_row(rb, acc, b4, lane, Mp4, gib == p.N ? p.mu_dust : 1.0f, gib <= p.N);
-            if (lane == 0 && gib < p.Np8) p.a[(size_t)z * p.Np8 + gib] = av;
-        }
-        // ---- the unit's column sums: warp sums -> shared memory -> fixed-order sum -> one partial row ----
-        {
-            float4* x4 = reinterpret_cast<float4*>(sX + (size_t)warp * Mp);
-#pragma unroll
-            for (int i = 0; i < XR_NQ; ++i) {
-                const int c = lane + 32 * i;
-                if (c < Mp4) x4[c] = acc.v[i];
-                acc.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        __syncthreads();
-        {
-            float4* tp = reinterpret_cast<float4*>(p.Tpart + ((size_t)z * p.upp + q) * Mp);
-            for (int g = tid; g < Mp4; g += XR_THREADS) {
-                float4 t = reinterpret_cast<const float4*>(sX)[g];
-#pragma unroll
-                for (int w = 1; w < XR_WARPS; ++w) {
-                    const float4 v = reinterpret_cast<const float4*>(sX + (size_t)w * Mp)[g];
-                    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-                }
-                tp[g] = t;
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -767,15 +645,9 @@ int sinkhorn_xl_run(const float* d1, const float* d2, int B, int N, int M, int D
     cs.attrs = pdl; cs.numAttrs = 1;
     cc.gridDim = dim3((unsigned)((M + 32) / 32), (unsigned)B, 1); cc.blockDim = dim3(256, 1, 1); cc.dynamicSmemBytes = 0; cc.stream = st;
     cc.attrs = pdl; cc.numAttrs = 1;
-    const bool rows_in_regs = (g_xl_policy & 8) != 0;                  // tuning hook bit 3 (default: the bulk-copy form, 7 % faster)
-    const size_t rsmem = (size_t)(XR_WARPS + 1) * w.Mp * sizeof(float);
-    OM_TRY(set_smem(xr_sweep_kernel, rsmem));
-    cudaLaunchConfig_t cr = cs;
-    cr.blockDim = dim3(XR_THREADS, 1, 1); cr.dynamicSmemBytes = rsmem;
     for (int it = 0; it < iterations; ++it) {
         s.reverse = g_xl_reverse ? (it & 1) : 0;
-        if (rows_in_regs) OM_CUDA(cudaLaunchKernelEx(&cr, xr_sweep_kernel, s));
-        else OM_CUDA(cudaLaunchKernelEx(&cs, xs_sweep_kernel, s));
+        OM_CUDA(cudaLaunchKernelEx(&cs, xs_sweep_kernel, s));
         OM_AFTER_LAUNCH();
         OM_CUDA(cudaLaunchKernelEx(&cc, xs_col_kernel, (const float*)w.Tpart, w.b, w.upp, M, w.Mp, (float)N));
         OM_AFTER_LAUNCH();
@@ -797,5 +669,5 @@ int sinkhorn_xl_run(const float* d1, const float* d2, int B, int N, int M, int D
 extern "C" void om_debug_xl_reverse(int on) {
     om::g_xl_reverse = on & 1;
     om::g_xl_pdl = (on & 2) ? 0 : 1;       // bit 1: switch programmatic dependent launch off
-    om::g_xl_policy = (on >> 4) & 15;      // bits 4..7: L2 policy of the sweeps
+    om::g_xl_policy = (on >> 4) & 7;       // bits 4..6: L2 policy of the sweeps
 }
