@@ -333,6 +333,10 @@ void om_debug_essential_variant(int clustered);
 /* Fused matcher: 4 (default) = image 2's detector / descriptor chain and both integral-image builds run on side streams
  * next to image 1's chain, 2 = only image 2's chain on a side stream, 1 = everything on the caller's stream. */
 void om_debug_match_streams(int n);
+/* 1 (default): in the fused matcher hard-binarised sparse descriptors (every entry 0 or one value per row) feed the Sinkhorn
+ * kernel as ONE 8-bit operand term (popcount similarity on tcgen05 kind::f8f6f4); 0: the two fp16 terms as for any other
+ * descriptor. */
+void om_debug_match_binary(int on);
 /* Keypoint windows of the dense descriptor kernel: bit 0: 1 = one TMA box per keypoint (default), 0 = 16-byte cp.async
  * copies by the keypoint's thread group (cross-check, slower); bit 1 / bit 2 (diagnosis only, wrong results): skip the
  * window fetch / skip the pair arithmetic. */

@@ -101,6 +101,7 @@ SIGNATURES = {
     "om_debug_nms_variant": (None, [c_int]),
     "om_debug_essential_variant": (None, [c_int]),
     "om_debug_match_streams": (None, [c_int]),
+    "om_debug_match_binary": (None, [c_int]),
     "om_debug_dense_window": (None, [c_int]),
     "om_debug_band_rows": (None, [c_int]),
     "om_debug_score_variant": (None, [c_int]),

@@ -95,6 +95,7 @@ struct MatchWs {
 // kernel tails and issue-bound / bandwidth-bound kernels overlap.
 // Side streams and events belong to ONE caller stream: a small per-(device, caller stream) pool, so that calls on
 // different caller streams (HostBatchMatcher's chunk streams, two caller threads) share nothing and overlap freely.
+int g_match_binary = 1;                          // om_debug_match_binary: 0 = hard-binarised descriptors take the fp16 operand terms too
 int g_match_streams = 4;                        // om_debug_match_streams: 1 = everything on the caller's stream, 2 = two chains, 4
 
 struct SideSet {
@@ -199,6 +200,7 @@ int device_count_cached() {
 }  // namespace om
 
 extern "C" void om_debug_match_streams(int n) { g_match_streams = n == 1 ? 1 : (n == 2 ? 2 : 4); }
+extern "C" void om_debug_match_binary(int on) { g_match_binary = on ? 1 : 0; }
 
 extern "C" size_t om_match_workspace_bytes(const om_match_params* p) {
     if (check_params(p) != OM_OK) return 0;
@@ -296,6 +298,9 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
     // the streaming kernels beyond 1024 keypoints pack their operands the same way (plain P output only)
     const bool xl = !hy && !ex && p->iterations > 0 && probs != nullptr &&
                     sinkhorn_routes_to_xl(p->B, p->K, p->K, p->P, p->epsilon, p->unused_score, p->distance_l1, w.sink, w.sink_bytes);
+    // hard-binarised sparse descriptors are 0 / one value per row: the hybrid kernel then takes 8-bit operands (popcount GEMM)
+    const int binary = hy && g_match_binary && p->desc_mode == OM_DESC_HARD && p->flavour != OM_MATCH_DENSE &&
+                       sinkhorn_hy_binary_ok(p->K, p->K, p->P);
     if (hy) OM_TRY(sinkhorn_hy_prepare(p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, st));   // before the fork: ordered ahead of both chains
     if (xl) OM_TRY(sinkhorn_xl_prepare(p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, st));
     SideSet* set = nullptr;
@@ -345,7 +350,7 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
             } else {
                 OM_TRY(descriptors(s, chain[s], 0));
             }
-            if (hy) OM_TRY(sinkhorn_hy_pack(s, ds[s], p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, chain[s]));
+            if (hy) OM_TRY(sinkhorn_hy_pack(s, ds[s], p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, chain[s], binary));
             if (xl) OM_TRY(sinkhorn_xl_pack(s, ds[s], p->B, p->K, p->K, p->P, w.sink, w.sink_bytes, chain[s]));
         }
         return OM_OK;
@@ -359,7 +364,7 @@ int match_pairs_impl(const om_match_params* p, const void* image1, const void* i
     if (rc != OM_OK) return rc;
     if (hy)
         return sinkhorn_hy_run(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, probs, ex ? epi : nullptr,
-                               w.sink, w.sink_bytes, st);
+                               w.sink, w.sink_bytes, st, binary);
     if (xl)
         return sinkhorn_xl_run(d1, d2, p->B, p->K, p->K, p->P, p->iterations, p->epsilon, p->unused_score, probs, w.sink, w.sink_bytes, st);
     if (ex)

@@ -191,9 +191,13 @@ int sinkhorn_hy_launch(const float* d1, const float* d2, int B, int N, int M, in
 // the three steps of sinkhorn_hy_launch, and the router's answer to "will sinkhorn_launch / sinkhorn_ex_launch take the hybrid
 // kernel for this problem?" (the fused matcher then packs each image's descriptors on that image's stream)
 int sinkhorn_hy_prepare(int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st);
-int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st);
+// binary = 1: the rows are known to hold only 0 and one common value (hard-binarised BAD descriptors): one 8-bit operand
+// term, the similarity GEMM as popcounts on tcgen05 kind::f8f6f4 (pack and run must agree; sinkhorn_hy_binary_ok says whether
+// the descriptor length allows it)
+bool sinkhorn_hy_binary_ok(int N, int M, int D);
+int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st, int binary = 0);
 int sinkhorn_hy_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
-                    float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st);
+                    float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st, int binary = 0);
 bool sinkhorn_routes_to_hy(int B, int N, int M, int D, float epsilon, float unused_score, int distance_l1, const void* ws,
                            size_t ws_bytes);
 // streaming kernels beyond the hybrid kernel's sizes (sinkhorn_xl.cu): the same three steps

@@ -62,7 +62,8 @@ struct Hy {
     static constexpr int OFF_PART = OFF_B + MAXM + 32;             // [CL][PSTR] partial column sums of the owned columns
     static constexpr int OFF_AS = OFF_PART + CL * PSTR;            // per-warp sum of a
     static constexpr int OFF_N1 = OFF_AS + 32;                     // squared norms of the local d1 rows
-    static constexpr int OFF_MISC = OFF_N1 + RPC;                  // fused epilogue, written by peers: column argmax [MAXM],
+    static constexpr int OFF_S1 = OFF_N1 + RPC;                    // binary operands: the value of a row's non-zero entries (else 1)
+    static constexpr int OFF_MISC = OFF_S1 + RPC;                  // fused epilogue, written by peers: column argmax [MAXM],
                                                                    // (value, row) words of the owned columns [CL][OWN] x 8 B,
                                                                    // sort keys [CL * RPC] x 8 B (rank 0)
     // all-to-all exchange of the column partials (small clusters only): [2 buffers][CL ranks][XSTR]; slot MAXM of a rank's
@@ -124,6 +125,14 @@ __device__ __forceinline__ void umma_f16_n(uint32_t d_tmem, uint64_t adesc, uint
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+// the same on 8-bit operands (E4M3: 0x38 = 1.0, 0x00 = 0.0), FP32 accumulators: K = 32 elements per instruction
+__device__ __forceinline__ void umma_f8_n(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
         "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit_to(uint32_t bar) {
@@ -231,6 +240,58 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const float* d, int rows,
     if (lane == 0 && !(mx < 60000.0f)) atomicOr(&ovf[z], 1u);
 }
 
+// Binary descriptors (hard-binarised BAD, descriptor/bad.py:560-574: every entry of a row is 0 or one common value s, the
+// reciprocal of the row's norm, or 1 when the rows are not normalised): the similarity is s1 s2 popcount(bits1 & bits2), so the
+// operands shrink to ONE 8-bit term (E4M3 1.0 / 0.0: a quarter of the bytes of the two fp16 terms, a third of the MMAs, exact
+// integer accumulation).  out[z][tile][chunk][g][Rp rows][16 bytes]; squared norms as pack_f16_kernel; scales[row] = s; the
+// per-pair flag is raised when some row is not of that form (the kernel then takes its FP32 dot-product path for the pair).
+__global__ void __launch_bounds__(256) pack_bits_kernel(const float* d, int rows, int D, int Rp, int tiles, int G,
+                                                        unsigned char* out, float* norms, float* scales, unsigned int* ovf) {
+    const int z = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);          // 8 consecutive padded rows
+    const int prow = item * 8 + (lane >> 2);
+    if (item * 8 >= tiles * Rp) return;
+    const int g4 = lane & 3;                                       // 16 of every 64 elements
+    const int tile = prow / Rp, rl = prow - tile * Rp;
+    const int nchunks = D / (16 * G);
+    const bool real = prow < rows;
+    const float* src = d + ((size_t)z * rows + (real ? prow : 0)) * D + 16 * g4;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)z * tiles * nchunks * G * Rp;
+    float acc = 0.0f, mx = 0.0f;
+    // first pass: the row's value s = its largest entry (entries are >= 0)
+    for (int c64 = 0; c64 < D / 64; ++c64) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = real ? __ldg(reinterpret_cast<const float4*>(src + 64 * c64 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    bool odd = false;
+    for (int c64 = 0; c64 < D / 64; ++c64) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = real ? __ldg(reinterpret_cast<const float4*>(src + 64 * c64 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+            odd |= !((v.x == 0.0f || v.x == mx) && (v.y == 0.0f || v.y == mx) && (v.z == 0.0f || v.z == mx) && (v.w == 0.0f || v.w == mx));
+            w[q] = (v.x != 0.0f ? 0x38u : 0u) | (v.y != 0.0f ? 0x3800u : 0u) | (v.z != 0.0f ? 0x380000u : 0u) | (v.w != 0.0f ? 0x38000000u : 0u);
+        }
+        const int kg = 4 * c64 + g4;                                // global K group of 16 elements
+        const int chunk = kg / G, g = kg - chunk * G;
+        dst[(((size_t)tile * nchunks + chunk) * G + g) * Rp + rl] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (g4 == 0) {
+        norms[(size_t)z * tiles * Rp + prow] = acc;
+        scales[(size_t)z * tiles * Rp + prow] = mx;
+    }
+    if (__any_sync(0xffffffffu, odd || !(mx < 60000.0f)) && lane == 0) atomicOr(&ovf[z], 1u);
+}
+
 // out-of-fp16-range fallback of one similarity (rare): kept out of line, the unrolled epilogue calls it from 128 places
 __device__ __noinline__ float dot_f32_slow(const float* x, const float* y, int D) {
     float dot = 0.0f;
@@ -243,7 +304,10 @@ struct HyArgs {
     const unsigned char* d2p;
     const float* n1;            // squared norms, padded rows
     const float* n2;
-    const unsigned int* ovf;    // per pair: some |x| >= 60000 -> FP32 dot products
+    const unsigned int* ovf;    // per pair: some |x| >= 60000 (binary operands: some row is not {0, s}) -> FP32 dot products
+    const float* s1;            // binary operands (pack_bits_kernel): per-row value of the set entries, padded rows; else null
+    const float* s2;
+    int binary;
     const float* d1;
     const float* d2;
     int N, M, D, Mp;
@@ -277,6 +341,7 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     float* sPart = sm + C::OFF_PART;
     float* sAs = sm + C::OFF_AS;
     float* sN1 = sm + C::OFF_N1;
+    float* sS1 = sm + C::OFF_S1;
     // [0,1] stage full (bulk copies landed), [2,3] stage free (MMAs retired), [4] GEMM done, [5] partials landed,
     // [6] b landed, [7] epilogue: sort keys landed (rank 0), [8,9] all-to-all partials landed (even / odd iterations)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
@@ -296,8 +361,10 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                      "n"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < RPC; i += NT)                                 // rows beyond N: +inf (their K becomes exactly 0)
+    for (int i = tid; i < RPC; i += NT) {                               // rows beyond N: +inf (their K becomes exactly 0)
         sN1[i] = r0 + i < N ? a.n1[((size_t)z * CL + rank) * RPC + i] : CUDART_INF_F;
+        sS1[i] = (a.binary && r0 + i < N) ? a.s1[((size_t)z * CL + rank) * RPC + i] : 1.0f;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -308,16 +375,19 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
     // ---------------- similarity GEMM on tcgen05: D[j][i] = sum_k d2[j][k] d1[i][k] ------------------
     const int nmb = Mp / 128;
     {
-        const int nchunks = D / KC;
+        // binary operands: one 8-bit term, 16 elements per 16-byte group (a stage holds 16 G elements instead of 8 G)
+        const bool bin = a.binary != 0;
+        const int nchunks = bin ? D / (16 * G) : D / KC;
         const uint32_t a_term = (uint32_t)G * Mp * 16u, b_term = (uint32_t)C::B_TERM;
-        const uint32_t bytesA = 2u * a_term, bytesB = 2u * b_term;
+        const uint32_t bytesA = (bin ? 1u : 2u) * a_term, bytesB = (bin ? 1u : 2u) * b_term;
         const uint32_t stage0 = smem_u32(sm);
         if (warp == 0 && lane == 0) {
             // ===== copy issuer: this CTA's d1 terms of the chunk, and ITS SLICE of the d2 terms multicast to the whole cluster
             // (every CTA needs all of d2: each of the CL issuers fetches 1 / CL of a chunk from L2 once for everybody) =====
             constexpr uint16_t ALL = (uint16_t)((1u << CL) - 1u);
-            const unsigned char* gA = a.d2p + (size_t)z * (4ull * D * Mp);
-            const unsigned char* gB = a.d1p + ((size_t)z * CL + rank) * (4ull * D * RPC);
+            const size_t per_elem = bin ? 1 : 4;                       // packed bytes per descriptor element
+            const unsigned char* gA = a.d2p + (size_t)z * (per_elem * D * Mp);
+            const unsigned char* gB = a.d1p + ((size_t)z * CL + rank) * (per_elem * D * RPC);
             const uint32_t sliceA = bytesA / (uint32_t)CL;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c & 1;
@@ -331,24 +401,35 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
             }
         } else if (warp == 1 && lane == 0) {
             // ===== MMA issuer =====
-            constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(RPC >> 3) << 17) | ((128u >> 4) << 24);   // D=F32, A=B=F16, K-major, N=RPC, M=128
+            constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(RPC >> 3) << 17) | ((128u >> 4) << 24);   // D=F32, A=B=F16 (E4M3 under kind::f8f6f4), K-major, N=RPC, M=128
             const uint32_t a_lbo = (uint32_t)Mp * 16u, b_lbo = (uint32_t)RPC * 16u;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c & 1;
                 mbar_wait(smem_u32(&bars[s]), (uint32_t)((c >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = stage0 + s * C::STAGE;
+                if (bin) {
 #pragma unroll
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                    const uint64_t bhi = udesc(sa + 2 * C::A_TERM + 2 * ks * b_lbo, b_lbo, 128);
-                    const uint64_t blo = udesc(sa + 2 * C::A_TERM + b_term + 2 * ks * b_lbo, b_lbo, 128);
-                    for (int mb = 0; mb < nmb; ++mb) {
-                        const uint64_t ahi = udesc(sa + 2 * ks * a_lbo + mb * 128 * 16, a_lbo, 128);
-                        const uint64_t alo = udesc(sa + a_term + 2 * ks * a_lbo + mb * 128 * 16, a_lbo, 128);
-                        const uint32_t d = tmem_base + (uint32_t)(mb * RPC);
-                        umma_f16_n(d, ahi, bhi, IDESC, (c | ks) != 0);
-                        umma_f16_n(d, ahi, blo, IDESC, 1u);
-                        umma_f16_n(d, alo, bhi, IDESC, 1u);
+                    for (int ks = 0; ks < G / 2; ++ks) {                // 32 elements = two 16-byte groups per instruction
+                        const uint64_t bd = udesc(sa + 2 * C::A_TERM + 2 * ks * b_lbo, b_lbo, 128);
+                        for (int mb = 0; mb < nmb; ++mb) {
+                            const uint64_t ad = udesc(sa + 2 * ks * a_lbo + mb * 128 * 16, a_lbo, 128);
+                            umma_f8_n(tmem_base + (uint32_t)(mb * RPC), ad, bd, IDESC, (c | ks) != 0);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint64_t bhi = udesc(sa + 2 * C::A_TERM + 2 * ks * b_lbo, b_lbo, 128);
+                        const uint64_t blo = udesc(sa + 2 * C::A_TERM + b_term + 2 * ks * b_lbo, b_lbo, 128);
+                        for (int mb = 0; mb < nmb; ++mb) {
+                            const uint64_t ahi = udesc(sa + 2 * ks * a_lbo + mb * 128 * 16, a_lbo, 128);
+                            const uint64_t alo = udesc(sa + a_term + 2 * ks * a_lbo + mb * 128 * 16, a_lbo, 128);
+                            const uint32_t d = tmem_base + (uint32_t)(mb * RPC);
+                            umma_f16_n(d, ahi, bhi, IDESC, (c | ks) != 0);
+                            umma_f16_n(d, ahi, blo, IDESC, 1u);
+                            umma_f16_n(d, alo, bhi, IDESC, 1u);
+                        }
                     }
                 }
                 umma_commit_mc(smem_u32(&bars[2 + s]), (uint16_t)((1u << CL) - 1u));   // stage s of this CTA is free: tell every issuer
@@ -381,12 +462,14 @@ __global__ void __launch_bounds__(NT, 1) sinkhorn_hy_kernel(HyArgs a) {
                 // rows beyond N and columns beyond M carry a squared norm of +inf (sN1 / n2j): their cost is +inf and their
                 // K is exactly 0 without a per-element test
                 const float n2j = jv ? a.n2[(size_t)z * Mp + j] : CUDART_INF_F;
+                // binary operands: the accumulator is popcount(bits_i & bits_j), the similarity s_i s_j popcount (s = 1 otherwise)
+                const float m2s = -2.0f * ((a.binary && jv) ? a.s2[(size_t)z * Mp + j] : 1.0f);
                 if (!overflow) {
 #pragma unroll
                     for (int ii = 0; ii < 32; ++ii) {
                         const int li = 32 * h + ii;
                         // sinkhorn.py:98-103; 2 * dot is exact, so the fused form rounds exactly like (n1 + n2) - 2 * dot
-                        const float cost = fmaxf(fmaf(-2.0f, __uint_as_float(r[ii]), __fadd_rn(sN1[li], n2j)), 0.0f);
+                        const float cost = fmaxf(fmaf(m2s, __fmul_rn(__uint_as_float(r[ii]), sS1[li]), __fadd_rn(sN1[li], n2j)), 0.0f);
                         const float kv = ex2h(__fmul_rn(cost, nscale2));
                         const int wl = ii / RPW, ri = ii % RPW;         // compile-time after unrolling
                         if (ri >= RR) sKs[((WPB * h + wl) * RS + (ri - RR)) * MAXM + j] = kv;
@@ -986,8 +1069,8 @@ size_t sinkhorn_hy_workspace_bytes(int B, int N, int M, int D) {
     int CLv, RPCv, Mp;
     hy_geometry(N, M, CLv, RPCv, Mp);
     const size_t np = (size_t)CLv * RPCv;
-    return align_up((size_t)B * np * D * 4) + align_up((size_t)B * Mp * D * 4) + align_up((size_t)B * np * sizeof(float)) +
-           align_up((size_t)B * Mp * sizeof(float)) + align_up((size_t)B * sizeof(unsigned int));
+    return align_up((size_t)B * np * D * 4) + align_up((size_t)B * Mp * D * 4) + 2 * align_up((size_t)B * np * sizeof(float)) +
+           2 * align_up((size_t)B * Mp * sizeof(float)) + align_up((size_t)B * sizeof(unsigned int));
 }
 
 namespace {
@@ -996,6 +1079,8 @@ struct HyWs {
     unsigned char* d2p;
     float* n1;
     float* n2;
+    float* s1;                  // binary operands: per-row values
+    float* s2;
     unsigned int* ovf;
     int CLv, RPCv, Mp, G;
 };
@@ -1008,6 +1093,8 @@ HyWs hy_carve(void* ws, int B, int N, int M, int D) {
     w.d2p = (unsigned char*)c; c += align_up((size_t)B * w.Mp * D * 4);
     w.n1 = (float*)c; c += align_up((size_t)B * np * sizeof(float));
     w.n2 = (float*)c; c += align_up((size_t)B * w.Mp * sizeof(float));
+    w.s1 = (float*)c; c += align_up((size_t)B * np * sizeof(float));
+    w.s2 = (float*)c; c += align_up((size_t)B * w.Mp * sizeof(float));
     w.ovf = (unsigned int*)c;
     w.G = w.CLv == 4 ? 4 : 2;
     return w;
@@ -1024,11 +1111,28 @@ int sinkhorn_hy_prepare(int B, int N, int M, int D, void* ws, size_t ws_bytes, c
     return OM_OK;
 }
 
-int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+// binary operands need whole 64-element groups per lane of the packing kernel and whole stages of 16 G elements
+bool sinkhorn_hy_binary_ok(int N, int M, int D) {
+    int CLv, RPCv, Mp;
+    hy_geometry(N, M, CLv, RPCv, Mp);
+    const int G = CLv == 4 ? 4 : 2;
+    return D % 64 == 0 && D % (16 * G) == 0;
+}
+
+int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void* ws, size_t ws_bytes, cudaStream_t st, int binary) {
     if (d == nullptr) return OM_ERR_NULL;
     if (ws == nullptr || ws_bytes < sinkhorn_hy_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    if (binary && !sinkhorn_hy_binary_ok(N, M, D)) return OM_ERR_PARAM;
     const HyWs w = hy_carve(ws, B, N, M, D);
     const size_t np = (size_t)w.CLv * w.RPCv;
+    if (binary) {
+        if (which == 0)
+            pack_bits_kernel<<<dim3((unsigned)((np / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d, N, D, w.RPCv, w.CLv, w.G, w.d1p, w.n1, w.s1, w.ovf);
+        else
+            pack_bits_kernel<<<dim3((unsigned)((w.Mp / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d, M, D, w.Mp, 1, w.G, w.d2p, w.n2, w.s2, w.ovf);
+        OM_AFTER_LAUNCH();
+        return OM_OK;
+    }
     if (which == 0)
         pack_f16_kernel<<<dim3((unsigned)((np / 8 + 7) / 8), (unsigned)B), 256, 0, st>>>(d, N, D, w.RPCv, w.CLv, w.G, w.d1p, w.n1, w.ovf);
     else
@@ -1038,12 +1142,14 @@ int sinkhorn_hy_pack(int which, const float* d, int B, int N, int M, int D, void
 }
 
 int sinkhorn_hy_run(const float* d1, const float* d2, int B, int N, int M, int D, int iterations, float eps, float unused,
-                    float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* P, const SinkhornEpilogue* e, void* ws, size_t ws_bytes, cudaStream_t st, int binary) {
     if (!sinkhorn_hy_eligible(N, M, D, eps, unused, 0)) return OM_ERR_PARAM;
     if (ws == nullptr || ws_bytes < sinkhorn_hy_workspace_bytes(B, N, M, D)) return OM_ERR_WORKSPACE;
+    if (binary && !sinkhorn_hy_binary_ok(N, M, D)) return OM_ERR_PARAM;
     const HyWs w = hy_carve(ws, B, N, M, D);
     HyArgs a{};
     a.d1p = w.d1p; a.d2p = w.d2p; a.n1 = w.n1; a.n2 = w.n2; a.ovf = w.ovf; a.d1 = d1; a.d2 = d2;
+    a.binary = binary ? 1 : 0; a.s1 = w.s1; a.s2 = w.s2;
     a.N = N; a.M = M; a.D = D; a.Mp = w.Mp; a.iterations = iterations; a.P = P;
     a.trace = g_tc_trace;
     const double log2e = 1.4426950408889634;

@@ -933,6 +933,33 @@ def test_sinkhorn_with_scores_golden():
     assert torch.equal(s0, p[:, :N, :M].max(dim=-1).values) and torch.equal(s1, p[:, :N, :M].max(dim=-2).values)
 
 
+@pytest.mark.parametrize("K,P,normalize", [(1024, 512, True), (512, 256, True), (600, 512, True), (512, 256, False), (200, 256, True)])
+def test_hard_binarised_descriptors_take_the_popcount_gemm(K, P, normalize):
+    """Fused matcher, hard-binarised sparse descriptors: every row is {0, s}, so the Sinkhorn kernel gets ONE 8-bit operand term
+    (tcgen05 kind::f8f6f4, popcount similarity).  Against the oracle, and against the two-fp16-term operands of the same kernel
+    (om_debug_match_binary(0)); 4-CTA and 16-CTA clusters, padded rows, un-normalised rows (s = 1)."""
+    i1, i2 = O.texture_images(3, 240, 320, seed=91)
+    kw = dict(num_pairs=P, binarize=True, soft_binarize=False, epsilon=0.05, nms_radius=5, normalize_descriptors=normalize)
+    if not normalize:
+        kw["epsilon"] = 20.0                                        # raw 0/1 descriptors: squared distances up to P
+    model = om.ShiTomasiSparseBADSinkhornMatcher(K, **kw).to(DEV).eval()
+    lib = _native.lib()
+    with torch.no_grad():
+        k1, k2, p, d1, d2 = model.match(*_cuda(i1, i2))
+        lib.om_debug_match_binary(0)
+        try:
+            _, _, p16, _, _ = model.match(*_cuda(i1, i2))
+        finally:
+            lib.om_debug_match_binary(1)
+    rk1, rk2, rp, rd1, rd2 = O.sparse_matcher(i1, i2, K, return_descriptors=True, **kw)
+    assert PR.keypoint_mismatches(k1, rk1) == 0 and PR.keypoint_mismatches(k2, rk2) == 0
+    assert int(((d1.cpu() > 0) != (rd1 > 0)).sum()) == 0
+    m = PR.prob_metrics(p, rp)
+    assert PR.probs_ok(m), m
+    m16 = PR.prob_metrics(p, p16.cpu())
+    assert m16["core"] <= 2e-5 and m16["argmax"] >= 0.999, m16
+
+
 # ------------------------------------------------------------------------------------------
 # robustness: workspace contents, allocation history, errors after a fork, state_dict, devices
 # ------------------------------------------------------------------------------------------
