@@ -412,6 +412,11 @@ def measure_other_configs(dev, steps):
         row = {"config": name, "pairs_per_step": B, "ms_per_step": ms, "pairs_per_s": B / ms * 1e3, "steps": n}
         if B == 64:
             row.update(stage_groups(model, wl, i1, max(3, n // 2)))
+            d = model.descriptor
+            if d.binarize and not d.soft_binarize:
+                row["note"] = ("inside the fused step hard-binarised descriptors feed the Sinkhorn kernel as one 8-bit operand term "
+                               "(popcount GEMM, tcgen05 kind::f8f6f4); the stage timed alone goes through om_sinkhorn_f32, which "
+                               "cannot know the rows are binary and takes the two fp16 terms, so it is slower than its share of the step")
         rows.append(row)
         del i1, i2
     del base
