@@ -258,38 +258,36 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const float* d, int rows
     const bool real = prow < rows;
     const float* src = d + ((size_t)z * rows + (real ? prow : 0)) * D + 16 * g4;
     uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)z * tiles * nchunks * G * Rp;
-    float acc = 0.0f, mx = 0.0f;
-    // first pass: the row's value s = its largest entry (entries are >= 0)
-    for (int c64 = 0; c64 < D / 64; ++c64) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = real ? __ldg(reinterpret_cast<const float4*>(src + 64 * c64 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-        }
-    }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    bool odd = false;
+    // one pass: bits, squared norm, the largest entry and the smallest non-zero entry of the row -- the row has the form
+    // {0, s} exactly when the two agree (or the row is all zeros)
+    float acc = 0.0f, mx = 0.0f, mnz = CUDART_INF_F;
     for (int c64 = 0; c64 < D / 64; ++c64) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 v = real ? __ldg(reinterpret_cast<const float4*>(src + 64 * c64 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
             acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
-            odd |= !((v.x == 0.0f || v.x == mx) && (v.y == 0.0f || v.y == mx) && (v.z == 0.0f || v.z == mx) && (v.w == 0.0f || v.w == mx));
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            mnz = fminf(mnz, fminf(fminf(v.x != 0.0f ? v.x : CUDART_INF_F, v.y != 0.0f ? v.y : CUDART_INF_F),
+                                   fminf(v.z != 0.0f ? v.z : CUDART_INF_F, v.w != 0.0f ? v.w : CUDART_INF_F)));
             w[q] = (v.x != 0.0f ? 0x38u : 0u) | (v.y != 0.0f ? 0x3800u : 0u) | (v.z != 0.0f ? 0x380000u : 0u) | (v.w != 0.0f ? 0x38000000u : 0u);
         }
         const int kg = 4 * c64 + g4;                                // global K group of 16 elements
         const int chunk = kg / G, g = kg - chunk * G;
         dst[(((size_t)tile * nchunks + chunk) * G + g) * Rp + rl] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, 1));
+    mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, 2));
+    const bool odd = !(mnz == CUDART_INF_F || (mnz == mx && mx > 0.0f));   // a negative entry, two different values, NaN
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (g4 == 0) {
         norms[(size_t)z * tiles * Rp + prow] = acc;
         scales[(size_t)z * tiles * Rp + prow] = mx;
     }
-    if (__any_sync(0xffffffffu, odd || !(mx < 60000.0f)) && lane == 0) atomicOr(&ovf[z], 1u);
+    if (__any_sync(0xffffffffu, odd || !(mx < 60000.0f) || !(acc == acc)) && lane == 0) atomicOr(&ovf[z], 1u);
 }
 
 // out-of-fp16-range fallback of one similarity (rare): kept out of line, the unrolled epilogue calls it from 128 places
