@@ -341,7 +341,8 @@ void om_debug_match_binary(int on);
  * copies by the keypoint's thread group (cross-check, slower); bit 1 / bit 2 (diagnosis only, wrong results): skip the
  * window fetch / skip the pair arithmetic. */
 void om_debug_dense_window(int tma);
-/* Banded integral-image build: padded-image rows per band (even, 8..256; default 32). */
+/* Banded integral-image build: padded-image rows per band (even, 8..256; default 32).  -16 / -32: the sparse descriptor path
+ * stores its integral modulo 2^16 (default) / as uint32. */
 void om_debug_band_rows(int rows);
 /* Score kernel of the split sweep form: 1 = score3_sweep_kernel / score5_sweep_kernel (default), 2 = the same at
  * another occupancy (6 / 3 CTAs per SM instead of 5 / 4), 0 = stencil_sweep_kernel<.., NMS = false> (cross-check). */

@@ -17,7 +17,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tmap_3d(CUtensorMap* map, bool is_float, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t pitch_elems, uint32_t box0, uint32_t box1) {
+                 uint64_t pitch_elems, uint32_t box0, uint32_t box1, int elem_bytes) {
     static EncodeTiledFn encode = nullptr;
     if (encode == nullptr) {
         void* fn = nullptr;
@@ -26,12 +26,14 @@ int make_tmap_3d(CUtensorMap* map, bool is_float, const void* base, uint64_t d0,
         if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return OM_ERR_CUDA_BASE + (int)cudaErrorNotSupported;
         encode = (EncodeTiledFn)fn;
     }
-    if (pitch_elems % 4 != 0 || ((uintptr_t)base & 15) != 0 || box0 % 4 != 0 || box0 > 256 || box1 > 256) return OM_ERR_PARAM;
+    if (elem_bytes != 4 && elem_bytes != 2) return OM_ERR_PARAM;
+    const uint64_t per16 = 16 / (uint64_t)elem_bytes;                          // rows and boxes are whole 16-byte pieces
+    if (pitch_elems % per16 != 0 || ((uintptr_t)base & 15) != 0 || box0 % per16 != 0 || box0 > 256 || box1 > 256) return OM_ERR_PARAM;
     const cuuint64_t dims[3] = {d0, d1, d2};
-    const cuuint64_t strides[2] = {pitch_elems * 4, pitch_elems * 4 * d1};     // bytes, dims 1 and 2
+    const cuuint64_t strides[2] = {pitch_elems * elem_bytes, pitch_elems * elem_bytes * d1};     // bytes, dims 1 and 2
     const cuuint32_t box[3] = {box0, box1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode(map, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
+    const CUresult r = encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : (is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32), 3,
                               const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

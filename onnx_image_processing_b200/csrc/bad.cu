@@ -33,6 +33,8 @@ constexpr int MAXR = 7;          // largest box radius in the tables
 // row pitch (elements) of an integral image with replicate padding `pad` and the zero column: a multiple of 4
 // so that rows are 16-byte aligned and a keypoint's window is one TMA box
 __host__ __device__ inline int ipitch(int W, int pad) { return (W + 2 * pad + 1 + 3) / 4 * 4; }
+// pitch of the 16-bit integral: rows are whole 16-byte pieces of eight elements
+__host__ __device__ inline int ipitch16(int W, int pad) { return (W + 2 * pad + 1 + 7) / 8 * 8; }
 
 struct PairRow {
     float ox1, ox2, oy1, oy2, r, thr;
@@ -58,6 +60,10 @@ __device__ __forceinline__ float sample_coord(float pos, float scale, float half
 // slot -> pair index (pair_order.inc): the built-in orders for 256 / 512 pairs, the identity otherwise
 __device__ __forceinline__ int pair_of_slot(int slot, int P) {
     return P == 256 ? (int)OM_PAIR_ORDER_256[slot] : (P == 512 ? (int)OM_PAIR_ORDER_512[slot] : slot);
+}
+// the same for the sparse window kernel on a 16-bit integral (another window pitch, two columns per bank word)
+__device__ __forceinline__ int pair_of_slot_u16(int slot, int P) {
+    return P == 256 ? (int)OM_PAIR_ORDER_256_U16[slot] : (P == 512 ? (int)OM_PAIR_ORDER_512_U16[slot] : slot);
 }
 
 __device__ __forceinline__ float finish_value(float diff, float thr, int mode, float temperature) {
@@ -390,13 +396,17 @@ int launch_sparse(const SparseArgs& a, cudaStream_t st) {
 // offset + two roundings), + radius 7 -> HS = 23, window 48x48; rotated offsets reach 22 + 7 -> HS = 30,
 // window 62 rows x 64 columns (box width must be a multiple of 16 bytes).
 // geometry shared by the kernel and its launcher
-template <int HS>
+// WT: element type of the integral: uint32, or uint16 (the integral modulo 2^16: every box sum is below 2^16 -- at most 15 x 15
+// pixels of at most 255 (the integer-image test bounds the pixels) -- so wrap-around differences are exact in 16 bits too,
+// and the window a keypoint fetches from L2 is half the bytes)
+template <int HS, typename WT = unsigned int>
 struct WinGeom {
     static constexpr int S = 2 * HS + 1;
     static constexpr int WR = S + 1;                    // window rows
-    static constexpr int WP = (S + 1 + 3 + 3) / 4 * 4;  // TMA box width == shared-memory pitch: the box must start on a
-                                                        // 16-byte boundary in global memory, so up to 3 columns early
-    static constexpr int GSTRIDE = (WR * WP + 31) / 32 * 32;   // words per window buffer (128-byte aligned)
+    static constexpr int EPW = 16 / (int)sizeof(WT);    // elements per 16 bytes
+    static constexpr int WP = (S + 1 + 2 * (EPW - 1)) / EPW * EPW;   // TMA box width == shared-memory pitch: the box must start
+                                                        // on a 16-byte boundary in global memory, so up to EPW - 1 columns early
+    static constexpr int GSTRIDE = (WR * WP * (int)sizeof(WT) / 4 + 31) / 32 * 32;   // 32-bit words per window buffer (128-byte aligned)
 };
 
 // The eight window byte offsets of a pair's taps (two boxes x four corners, bad.py:98 order), 16 bits each, in ONE 16-byte
@@ -417,8 +427,9 @@ __device__ __forceinline__ bool win_needed(const SparseArgs& a, long long kidx, 
 }
 
 // per-keypoint context of the general (border / oriented / bilinear) pair evaluation
+template <typename WT>
 struct SparseKpCtx {
-    const unsigned int* Wn;      // window column 0
+    const WT* Wn;                // window column 0
     float yc, xc, ct, st;        // clamped keypoint, cos / sin of its orientation
     int iy0, ix0;                // rounded keypoint
     float sy, sx;                // grid_sample scales
@@ -426,20 +437,22 @@ struct SparseKpCtx {
 };
 
 // One pair at one keypoint through the full sampling pipeline (bad.py:504-557).
-template <int HS, bool ORIENTED, bool BILINEAR>
-__device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx& c, const float* table, int p, int mode, float temperature) {
-    using G = WinGeom<HS>;
+template <int HS, bool ORIENTED, bool BILINEAR, typename WT>
+__device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx<WT>& c, const float* table, int p, int mode, float temperature) {
+    using G = WinGeom<HS, WT>;
     constexpr int S = G::S, WP = G::WP;
     const int H = c.H, W = c.W;
     const float hy = (float)(H - 1) * 0.5f, hx = (float)(W - 1) * 0.5f;
     const float my = (float)(H - 1), mx = (float)(W - 1);
-    const unsigned int* Wn = c.Wn;
+    const WT* Wn = c.Wn;
     auto box_mean = [&](int cy, int cx, int r, float inv_area) -> float {
         // cy,cx: integer sample centre in image coords (already clipped to the image by grid_sample's
         // border mode); the box may reach into the replicate padding, which the integral contains
         const int wy = clampi(cy - c.iy0 + HS, r, S - 1 - r), wx = clampi(cx - c.ix0 + HS, r, S - 1 - r);
         const int y0 = wy - r, y1 = wy + r + 1, x0 = wx - r, x1 = wx + r + 1;
-        const unsigned int s = (Wn[y1 * WP + x1] - Wn[y0 * WP + x1]) - (Wn[y1 * WP + x0] - Wn[y0 * WP + x0]);
+        unsigned int s = ((unsigned int)Wn[y1 * WP + x1] - (unsigned int)Wn[y0 * WP + x1]) -
+                         ((unsigned int)Wn[y1 * WP + x0] - (unsigned int)Wn[y0 * WP + x0]);
+        if (sizeof(WT) == 2) s &= 0xFFFFu;                                  // the integral modulo 2^16
         return __fmul_rn((float)s, inv_area);
     };
     auto sample = [&](float oy, float ox, int r, float inv_area) -> float {
@@ -474,16 +487,16 @@ __device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx& c, 
 // border path, and inlined into the unrolled pair loop next to the fast path it made the kernel several hundred KB of
 // code (stalls on instruction fetch).  The oriented / bilinear kernels have only this path and inline it, so that the
 // pairs of a thread overlap.
-template <int HS, bool ORIENTED, bool BILINEAR>
-__device__ __noinline__ float sparse_pair_general(const SparseKpCtx& c, const float* table, int p, int mode, float temperature) {
-    return sparse_pair_general_impl<HS, ORIENTED, BILINEAR>(c, table, p, mode, temperature);
+template <int HS, bool ORIENTED, bool BILINEAR, typename WT>
+__device__ __noinline__ float sparse_pair_general(const SparseKpCtx<WT>& c, const float* table, int p, int mode, float temperature) {
+    return sparse_pair_general_impl<HS, ORIENTED, BILINEAR, WT>(c, table, p, mode, temperature);
 }
 
 // one keypoint whose window `win` is in flight / has landed on mbarrier `bar` (phase `parity`).  NPP = pairs per
 // thread (ceil(P / 64)): the pair loops are unrolled over exactly NPP slots.
-template <int HS, bool ORIENTED, bool BILINEAR, int NPP>
+template <int HS, bool ORIENTED, bool BILINEAR, int NPP, typename WT>
 __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long kidx, int z, float ky, float kx,
-                                                 const unsigned int* win, uint32_t bar, uint32_t parity, float* red,
+                                                 const WT* win, uint32_t bar, uint32_t parity, float* red,
                                                  float* sTheta, const uint4* sTap, const float2* sThr,
                                                  const unsigned short* sIdx, int g, int t) {
     constexpr bool FAST = !ORIENTED && !BILINEAR;
@@ -493,7 +506,7 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
     const float xc = fminf(fmaxf(kx, 0.0f), (float)(W - 1));
     const int iy0 = (int)nearbyintf(yc), ix0 = (int)nearbyintf(xc);
     const int wx0 = ix0 - HS + a.pad;            // integral column of window column 0 (>= 0)
-    const unsigned int* Wn = win + (wx0 & 3);    // the box starts on a 16-byte boundary, up to 3 columns early
+    const WT* Wn = win + (wx0 & (WinGeom<HS, WT>::EPW - 1));    // the box starts on a 16-byte boundary, up to 3 (7) columns early
 
     float ct = 1.0f, st = 0.0f;
     if (ORIENTED) {
@@ -537,7 +550,8 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
     const bool fast = FAST && ky == (float)iy0 && kx == (float)ix0 && iy0 >= 15 && iy0 + 14 <= H - 1 && ix0 >= 15 &&
                       ix0 + 14 <= W - 1;
     const char* wbytes = reinterpret_cast<const char*>(Wn);
-    auto ldw = [&](unsigned int byte_off) -> unsigned int { return *reinterpret_cast<const unsigned int*>(wbytes + byte_off); };
+    auto ldw = [&](unsigned int byte_off) -> unsigned int { return (unsigned int)*reinterpret_cast<const WT*>(wbytes + byte_off); };
+    constexpr unsigned int WMASK = sizeof(WT) == 2 ? 0xFFFFu : 0xFFFFFFFFu;     // 16-bit integral: sums modulo 2^16
     if (fast) {
 #pragma unroll
         for (int q = 0; q < NPP; ++q) {
@@ -546,23 +560,23 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
             if (p < a.P) {
                 const uint4 tp = sTap[p];
                 const float2 tb = sThr[p];
-                const unsigned int s1 = (ldw(tap_lo(tp.x)) - ldw(tap_hi(tp.x))) - (ldw(tap_lo(tp.y)) - ldw(tap_hi(tp.y)));
-                const unsigned int s2 = (ldw(tap_lo(tp.z)) - ldw(tap_hi(tp.z))) - (ldw(tap_lo(tp.w)) - ldw(tap_hi(tp.w)));
+                const unsigned int s1 = ((ldw(tap_lo(tp.x)) - ldw(tap_hi(tp.x))) - (ldw(tap_lo(tp.y)) - ldw(tap_hi(tp.y)))) & WMASK;
+                const unsigned int s2 = ((ldw(tap_lo(tp.z)) - ldw(tap_hi(tp.z))) - (ldw(tap_lo(tp.w)) - ldw(tap_hi(tp.w)))) & WMASK;
                 const float diff = __fsub_rn(__fmul_rn((float)s1, tb.y), __fmul_rn((float)s2, tb.y));   // bad.py:557
                 d[q] = finish_value(diff, tb.x, a.mode, a.temperature);
                 ss = fmaf(d[q], d[q], ss);
             }
         }
     } else {
-        SparseKpCtx c;
+        SparseKpCtx<WT> c;
         c.Wn = Wn; c.yc = yc; c.xc = xc; c.ct = ct; c.st = st; c.iy0 = iy0; c.ix0 = ix0; c.sy = a.sy; c.sx = a.sx; c.H = H; c.W = W;
 #pragma unroll
         for (int q = 0; q < NPP; ++q) {
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                d[q] = FAST ? sparse_pair_general<HS, ORIENTED, BILINEAR>(c, a.table, p, a.mode, a.temperature)
-                            : sparse_pair_general_impl<HS, ORIENTED, BILINEAR>(c, a.table, p, a.mode, a.temperature);
+                d[q] = FAST ? sparse_pair_general<HS, ORIENTED, BILINEAR, WT>(c, a.table, p, a.mode, a.temperature)
+                            : sparse_pair_general_impl<HS, ORIENTED, BILINEAR, WT>(c, a.table, p, a.mode, a.temperature);
                 ss = fmaf(d[q], d[q], ss);
             }
         }
@@ -583,9 +597,9 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
 // pipeline, the TMA box of keypoint n+1 is in flight while keypoint n is evaluated; NBUF = 1: one window per group
 // and twice the resident groups instead (measured faster on B200: the kernel is bound by shared-memory wavefronts
 // of the random taps, not by the TMA latency, so more warps beat prefetching).
-template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR, int NBUF, int NPP>
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR, int NBUF, int NPP, typename WT>
 __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __grid_constant__ CUtensorMap tmap, SparseArgs a) {
-    using G = WinGeom<HS>;
+    using G = WinGeom<HS, WT>;
     constexpr bool FAST = !ORIENTED && !BILINEAR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ float red[GROUPS * 2];
@@ -606,13 +620,13 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
         for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
             // slot p takes pair pair_of_slot(p): the 32 lanes of a tap read are 32 consecutive slots, ordered for few bank
             // conflicts (the window geometry differs from the dense kernel's by a constant offset: same order)
-            const int pair = pair_of_slot(p, a.P);
+            const int pair = sizeof(WT) == 2 ? pair_of_slot_u16(p, a.P) : pair_of_slot(p, a.P);
             sIdx[p] = (unsigned short)pair;
             const PairRow row = load_pair(a.table, pair);
             const int r = (int)row.r;
             const int cy1 = HS + (int)row.oy1, cx1 = HS + (int)row.ox1, cy2 = HS + (int)row.oy2, cx2 = HS + (int)row.ox2;
-            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * G::WP + x) * 4u; };
-            static_assert(G::WR * G::WP * 4 < 65536, "window byte offsets must fit 16 bits");
+            auto off = [&](int y, int x) -> unsigned { return (unsigned)(y * G::WP + x) * (unsigned)sizeof(WT); };
+            static_assert(G::WR * G::WP * sizeof(WT) < 65536, "window byte offsets must fit 16 bits");
             const unsigned o[8] = {off(cy1 + r + 1, cx1 + r + 1), off(cy1 - r, cx1 + r + 1), off(cy1 + r + 1, cx1 - r), off(cy1 - r, cx1 - r),
                                    off(cy2 + r + 1, cx2 + r + 1), off(cy2 - r, cx2 + r + 1), off(cy2 + r + 1, cx2 - r), off(cy2 - r, cx2 - r)};
             sTap[p] = pack_taps(o);
@@ -633,8 +647,8 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
         if (t == 0 && win_needed(a, k, ky, kx, z)) {
             const int iy0 = (int)nearbyintf(fminf(ky, (float)(a.H - 1))), ix0 = (int)nearbyintf(fminf(fmaxf(kx, 0.0f), (float)(a.W - 1)));
             const uint32_t bar = bar0 + 8u * buf;
-            mbar_arrive_expect_tx(bar, G::WR * G::WP * 4);
-            tma_load_3d(smem_u32(wbuf + buf * G::GSTRIDE), &tmap, bar, (ix0 - HS + a.pad) & ~3, iy0 - HS + a.pad, z);
+            mbar_arrive_expect_tx(bar, G::WR * G::WP * (int)sizeof(WT));
+            tma_load_3d(smem_u32(wbuf + buf * G::GSTRIDE), &tmap, bar, (ix0 - HS + a.pad) & ~(G::EPW - 1), iy0 - HS + a.pad, z);
         }
     };
     long long kidx = (long long)blockIdx.x * GROUPS + g;
@@ -646,8 +660,8 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
         float ky, kx;
         int z;
         if (win_needed(a, kidx, ky, kx, z)) {
-            sparse_win_group<HS, ORIENTED, BILINEAR, NPP>(a, kidx, z, ky, kx, wbuf + buf * G::GSTRIDE, bar0 + 8u * buf, phase[buf],
-                                                     red, sTheta, sTap, sThr, sIdx, g, t);
+            sparse_win_group<HS, ORIENTED, BILINEAR, NPP, WT>(a, kidx, z, ky, kx, reinterpret_cast<const WT*>(wbuf + buf * G::GSTRIDE),
+                                                              bar0 + 8u * buf, phase[buf], red, sTheta, sTap, sThr, sIdx, g, t);
             phase[buf] ^= 1u;
         } else if (!(ky >= 0.0f)) {                                 // bad.py:461, :570 -> the row is all zeros
             float* out = a.desc + (size_t)kidx * a.P;
@@ -658,12 +672,12 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
     }
 }
 
-template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR>
-int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t st) {
-    using G = WinGeom<HS>;
-    const int Hi = a.H + 2 * a.pad + 1, IP = ipitch(a.W, a.pad);
+template <int HS, int GROUPS, bool ORIENTED, bool BILINEAR, typename WT>
+int launch_sparse_win(const SparseArgs& a, const void* I, cudaStream_t st) {
+    using G = WinGeom<HS, WT>;
+    const int Hi = a.H + 2 * a.pad + 1, IP = sizeof(WT) == 2 ? ipitch16(a.W, a.pad) : ipitch(a.W, a.pad);
     CUtensorMap tmap;
-    OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, G::WP, G::WR));
+    OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, G::WP, G::WR, (int)sizeof(WT)));
     constexpr int NBUF = 1;
     const size_t smem = (size_t)GROUPS * NBUF * G::GSTRIDE * 4 +
                         ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2) + sizeof(unsigned short)) : 0);
@@ -677,8 +691,8 @@ int launch_sparse_win(const SparseArgs& a, const unsigned int* I, cudaStream_t s
         kernel<<<grid, GROUPS * TPG, smem, st>>>(tmap, a);
         return OM_OK;
     };
-    if (a.P <= 4 * TPG) OM_TRY(go(sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF, 4>));   // pairs per thread
-    else OM_TRY(go(sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF, 8>));
+    if (a.P <= 4 * TPG) OM_TRY(go(sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF, 4, WT>));   // pairs per thread
+    else OM_TRY(go(sparse_win_kernel<HS, GROUPS, ORIENTED, BILINEAR, NBUF, 8, WT>));
     OM_AFTER_LAUNCH();
     return OM_OK;
 }
@@ -901,6 +915,7 @@ int build_prefix(const float* image, int B, int H, int W, int pad, void* T, void
 // float -> integer conversions use the 2^23 trick (v + 2^23 holds the integer v in its low mantissa bits for
 // 0 <= v < 2^23; (v + 2^23) - 2^23 == v exactly when v is such an integer): no conversion instructions, no branches.
 int g_band_rows = 32;              // padded-image rows per band (om_debug_band_rows)
+int g_sparse_i16 = 1;              // sparse path: integral stored modulo 2^16 (om_debug_band_rows(-16) / (-32) switch it on / off)
 constexpr int IB_G = 2;            // rows per group
 constexpr int IB_PX = 8;           // output columns per thread
 constexpr float IB_MAGIC = 8388608.0f;
@@ -1043,7 +1058,10 @@ integral_band_kernel(const TIn* image, int H, int W, int pad, int nb, int IB_ROW
             for (int j = 0; j < IB_PX; ++j) o[j] = (unsigned int)j < first_zero ? a[j] : 0u;
         }
         TOut* dst = Iz + (size_t)irow * IP + IB_PX * t;
-        if constexpr (std::is_same<TOut, float>::value) {
+        if constexpr (sizeof(TOut) == 2) {                      // the integral modulo 2^16 (IP is a multiple of eight here)
+            *reinterpret_cast<uint4*>(dst) = make_uint4((o[0] & 0xFFFFu) | (o[1] << 16), (o[2] & 0xFFFFu) | (o[3] << 16),
+                                                        (o[4] & 0xFFFFu) | (o[5] << 16), (o[6] & 0xFFFFu) | (o[7] << 16));
+        } else if constexpr (std::is_same<TOut, float>::value) {
             *reinterpret_cast<float4*>(dst) = make_float4(__uint2float_rn(o[0]), __uint2float_rn(o[1]), __uint2float_rn(o[2]), __uint2float_rn(o[3]));
             if (live_hi)
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint2float_rn(o[4]), __uint2float_rn(o[5]), __uint2float_rn(o[6]), __uint2float_rn(o[7]));
@@ -1164,7 +1182,7 @@ inline int band_colsum_pitch(int W, int pad) { return (ipitch(W, pad) + IB_PX - 
 template <typename TIn, typename TOut>
 int build_integral_banded(const TIn* image, int B, int H, int W, int pad, float maxv, unsigned int* colsum, TOut* I,
                           unsigned int* flags, cudaStream_t st) {
-    const int Hp = H + 2 * pad, IP = ipitch(W, pad), CP = band_colsum_pitch(W, pad);
+    const int Hp = H + 2 * pad, IP = sizeof(TOut) == 2 ? ipitch16(W, pad) : ipitch(W, pad), CP = band_colsum_pitch(W, pad);
     const int IB_ROWS = g_band_rows;
     const int nb = (Hp + IB_ROWS - 1) / IB_ROWS;
     if (CP > IB_PX * 1024 || B > 65535) return OM_ERR_LIMIT;
@@ -1653,12 +1671,22 @@ int sparse_bad_launch(const void* image, int image_u8, int B, int H, int W, cons
     const bool oriented = theta_mode != OM_THETA_NONE;
     const int pad = oriented ? PAD_ORI : PAD_PLAIN;
     const SparseWs w = carve_sparse(ws, B, H, W, pad);
+    // 16-bit integral (modulo 2^16) whenever the banded build applies (a pure function of the sizes: phases 1 and 2 of a call
+    // agree): pixels are then held to [0, 255] by the integer-image test (anything else raises the image's flag and goes to
+    // the general kernel), so that a 15 x 15 box sum stays below 2^16
+    const bool i16 = g_sparse_i16 && band_colsum_pitch(W, pad) <= IB_PX * 1024 && B <= 65535;
     if (phase != 2) {
         OM_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)(B + 1) * sizeof(unsigned int), st));
         int rc;
-        if (image_u8) rc = build_integral_banded<unsigned char, unsigned int>((const unsigned char*)image, B, H, W, pad, 65535.0f, w.colsum, w.I, w.flags, st);
-        else rc = build_integral_banded<float, unsigned int>((const float*)image, B, H, W, pad, 65535.0f, w.colsum, w.I, w.flags, st);
-        if (rc == OM_ERR_LIMIT && !image_u8) rc = build_prefix<true>((const float*)image, B, H, W, pad, w.T, w.I, w.flags, st);
+        if (i16) {
+            unsigned short* I16 = reinterpret_cast<unsigned short*>(w.I);
+            if (image_u8) rc = build_integral_banded<unsigned char, unsigned short>((const unsigned char*)image, B, H, W, pad, 255.0f, w.colsum, I16, w.flags, st);
+            else rc = build_integral_banded<float, unsigned short>((const float*)image, B, H, W, pad, 255.0f, w.colsum, I16, w.flags, st);
+        } else {
+            if (image_u8) rc = build_integral_banded<unsigned char, unsigned int>((const unsigned char*)image, B, H, W, pad, 65535.0f, w.colsum, w.I, w.flags, st);
+            else rc = build_integral_banded<float, unsigned int>((const float*)image, B, H, W, pad, 65535.0f, w.colsum, w.I, w.flags, st);
+            if (rc == OM_ERR_LIMIT && !image_u8) rc = build_prefix<true>((const float*)image, B, H, W, pad, w.T, w.I, w.flags, st);
+        }
         OM_TRY(rc);
     }
     if (phase == 1) return OM_OK;
@@ -1672,11 +1700,15 @@ int sparse_bad_launch(const void* image, int image_u8, int B, int H, int W, cons
     a.flags = w.flags; a.pad = pad;
     const bool bil = a.bilinear != 0;
     // integer-valued images: window kernel on the exact integral; every other image: the general kernel
+    using U32 = unsigned int;
+    using U16 = unsigned short;
     if (!oriented) {
-        OM_TRY((bil ? launch_sparse_win<HS_PLAIN, KPG, false, true>(a, w.I, st) : launch_sparse_win<HS_PLAIN, KPG, false, false>(a, w.I, st)));
+        if (i16) OM_TRY((bil ? launch_sparse_win<HS_PLAIN, KPG, false, true, U16>(a, w.I, st) : launch_sparse_win<HS_PLAIN, KPG, false, false, U16>(a, w.I, st)));
+        else OM_TRY((bil ? launch_sparse_win<HS_PLAIN, KPG, false, true, U32>(a, w.I, st) : launch_sparse_win<HS_PLAIN, KPG, false, false, U32>(a, w.I, st)));
         return bil ? launch_sparse<HS_PLAIN, 4, false, true>(a, st) : launch_sparse<HS_PLAIN, 4, false, false>(a, st);
     }
-    OM_TRY((bil ? launch_sparse_win<HS_ORI, 4, true, true>(a, w.I, st) : launch_sparse_win<HS_ORI, 4, true, false>(a, w.I, st)));
+    if (i16) OM_TRY((bil ? launch_sparse_win<HS_ORI, 4, true, true, U16>(a, w.I, st) : launch_sparse_win<HS_ORI, 4, true, false, U16>(a, w.I, st)));
+    else OM_TRY((bil ? launch_sparse_win<HS_ORI, 4, true, true, U32>(a, w.I, st) : launch_sparse_win<HS_ORI, 4, true, false, U32>(a, w.I, st)));
     return bil ? launch_sparse<HS_ORI, 3, true, true>(a, st) : launch_sparse<HS_ORI, 3, true, false>(a, st);
 }
 
@@ -1710,7 +1742,10 @@ int dense_bad_at_kpts_launch(const void* image, int image_u8, int B, int H, int 
 using namespace om;
 
 extern "C" void om_debug_dense_window(int tma) { g_dense_window_tma = tma; }
-extern "C" void om_debug_band_rows(int rows) { g_band_rows = rows >= 8 && rows <= 256 ? rows / 2 * 2 : 32; }
+extern "C" void om_debug_band_rows(int rows) {
+    if (rows == -16 || rows == -32) { g_sparse_i16 = rows == -16; return; }     // sparse path: 16-bit / 32-bit integral
+    g_band_rows = rows >= 8 && rows <= 256 ? rows / 2 * 2 : 32;
+}
 
 extern "C" int om_angle_map_f32(const float* image, int B, int H, int W, const float* moment_kernels, int patch_size,
                                 float* angle_map, void* stream) {

@@ -119,11 +119,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
             dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-// Host: rank-3 tiled tensor map over a dense (d2, d1, d0) array of 4-byte elements whose rows are
-// `pitch_elems` apart (pitch_elems % 4 == 0, base 16-byte aligned); box = (1, box1, box0), no swizzle,
+// Host: rank-3 tiled tensor map over a dense (d2, d1, d0) array of 4-byte (or 2-byte: elem_bytes) elements whose rows are
+// `pitch_elems` apart (whole 16-byte pieces, base 16-byte aligned); box = (1, box1, box0), no swizzle,
 // out-of-bounds elements read as zero.  Defined in api.cu (driver entry point resolved at run time).
 int make_tmap_3d(CUtensorMap* map, bool is_float, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t pitch_elems, uint32_t box0, uint32_t box1);
+                 uint64_t pitch_elems, uint32_t box0, uint32_t box1, int elem_bytes = 4);
 
 // ---- internal stage launchers shared between the per-stage C ABI and the fused matcher -------
 struct DetectCfg {

@@ -933,6 +933,46 @@ def test_sinkhorn_with_scores_golden():
     assert torch.equal(s0, p[:, :N, :M].max(dim=-1).values) and torch.equal(s1, p[:, :N, :M].max(dim=-2).values)
 
 
+@pytest.mark.parametrize("flavour", ["sparse", "angle", "bilinear", "export"])
+def test_sparse_integral_modulo_2_16_equals_uint32(flavour):
+    """The sparse descriptor path stores its integral modulo 2^16 (box sums of at most 15 x 15 pixels <= 255 are exact in 16
+    bits; half the bytes per keypoint window).  Same descriptors as with the uint32 integral (om_debug_band_rows(-32)) up to
+    the rounding of the norm; an image with pixels beyond 255 is flagged and takes the general kernel, within tolerance of
+    the oracle."""
+    i1, i2 = O.texture_images(3, 200, 264, seed=17)
+    kw = {}
+    if flavour == "angle":
+        model = om.ShiTomasiAngleSparseBADSinkhornMatcher(300)
+    else:
+        if flavour == "bilinear":
+            kw = dict(sampling_mode="bilinear")
+        elif flavour == "export":
+            kw = dict(num_pairs=512, binarize=True, soft_binarize=False, epsilon=0.05, nms_radius=5)
+        model = om.ShiTomasiSparseBADSinkhornMatcher(300, **kw)
+    model = model.to(DEV).eval()
+    lib = _native.lib()
+    with torch.no_grad():
+        got16 = [t.clone() for t in model.match(*_cuda(i1, i2))]
+        lib.om_debug_band_rows(-32)
+        try:
+            got32 = [t.clone() for t in model.match(*_cuda(i1, i2))]
+        finally:
+            lib.om_debug_band_rows(-16)
+    # the un-normalised descriptor elements are identical; the two layouts hand the pairs to the threads in different orders
+    # (bank conflicts), so the squared norm is summed in another order and the normalised values may differ in the last bit
+    assert torch.equal(got16[0], got32[0]) and torch.equal(got16[1], got32[1])
+    for a, b in ((got16[3], got32[3]), (got16[4], got32[4])):
+        assert torch.equal(a != 0, b != 0) and float((a - b).abs().max()) <= 2e-7
+    assert float((got16[2] - got32[2]).abs().max()) <= 1e-5 * float(got32[2].abs().max())
+    if flavour == "sparse":
+        big1, big2 = i1 * 3.0, i2 * 3.0                              # integer-valued, up to 765: beyond the 16-bit build's pixel bound
+        with torch.no_grad():
+            k1, k2, p, d1, d2 = model.match(*_cuda(big1, big2))
+        rk1, rk2, rp, rd1, rd2 = O.sparse_matcher(big1, big2, 300, return_descriptors=True)
+        assert PR.keypoint_mismatches(k1, rk1) == 0 and PR.keypoint_mismatches(k2, rk2) == 0
+        assert PR.desc_metrics(d1, rd1)["max_abs"] <= PR.DESC_TOL and PR.probs_ok(PR.prob_metrics(p, rp))
+
+
 @pytest.mark.parametrize("K,P,normalize", [(1024, 512, True), (512, 256, True), (600, 512, True), (512, 256, False), (200, 256, True)])
 def test_hard_binarised_descriptors_take_the_popcount_gemm(K, P, normalize):
     """Fused matcher, hard-binarised sparse descriptors: every row is {0, s}, so the Sinkhorn kernel gets ONE 8-bit operand term
