@@ -1050,6 +1050,22 @@ def test_bad_parameters_fail_before_any_work_is_forked():
             assert torch.equal(w, x)
 
 
+def test_streaming_sinkhorn_path_captures_into_a_cuda_graph():
+    """Beyond 1024 keypoints the sweep / column kernels are launched with programmatic stream serialization; the step must
+    still capture into a CUDA graph and replay to the eager result."""
+    from onnx_image_processing_b200.host_pipeline import GraphedMatcher
+    i1, i2 = (t.to(DEV) for t in O.texture_images(2, 360, 480, seed=5))
+    model = om.ShiTomasiSparseBADSinkhornMatcher(1200).to(DEV).eval()
+    with torch.no_grad():
+        want = [t.clone() for t in model(i1, i2)]
+        graphed = GraphedMatcher(model, i1, i2)
+        for _ in range(2):
+            got = graphed(i1, i2)
+            torch.cuda.synchronize()
+            for w, x in zip(want, got):
+                assert torch.equal(w, x)
+
+
 def test_caller_streams_do_not_share_side_streams():
     """Two caller streams issuing matcher steps concurrently (what HostBatchMatcher's chunk streams do): each gets its own
     side streams and events; results equal the single-stream ones."""
