@@ -429,8 +429,14 @@ def grid_points(n, image_shape, K_inv):
     return (h @ K_inv.T)[:n, :2]
 
 
+# False: detect() takes the square root exactly as the reference does on this host (torch.sqrt: MKL VML, host-dependent in
+# the last bit, see shi_tomasi_score).  The GPU parity tests switch it on (fixture in tests/test_gpu_parity.py) so that the
+# expected keypoints do not depend on the CPU of the GPU box; the CPU tests pin the verbatim form to the goldens.
+DETECT_IEEE_SQRT = False
+
+
 def detect(image, max_keypoints, block_size=3, nms_radius=3, score_threshold=0.0, border_margin=0):
-    sc = shi_tomasi_score(image, block_size).squeeze(1)
+    sc = shi_tomasi_score(image, block_size, ieee_sqrt=DETECT_IEEE_SQRT).squeeze(1)
     return select_topk(sc, nms_mask(sc, nms_radius), max_keypoints, score_threshold, border_margin)
 
 

@@ -2,6 +2,8 @@
 (a) the golden vectors minted from the live reference and (b) the CPU oracle on seeded inputs.
 Run on the B200 box with `pytest -m gpu`.
 """
+import warnings
+
 import pytest
 import torch
 
@@ -13,6 +15,17 @@ from tests import parity as PR
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _host_independent_oracle_sqrt():
+    """The oracle's detector takes the correctly rounded square root in this module (oracle.DETECT_IEEE_SQRT): the host's
+    torch.sqrt differs from it in the last bit on a few per cent of the pixels, differently from CPU to CPU, and the
+    kernels are required to equal the IEEE form bit for bit (test_score_map_bit_exact)."""
+    old = O.DETECT_IEEE_SQRT
+    O.DETECT_IEEE_SQRT = True
+    yield
+    O.DETECT_IEEE_SQRT = old
 
 # measured on B200 (tools/measure_parity.py -> profiles/r2_parity_measured.json); thresholds = measured + a small margin
 EXPORT_MAX_FLIPPED_BITS = 0          # measured 0 of 1 048 576 hard bits (same integer arithmetic on every B200)
@@ -43,14 +56,17 @@ def test_score_map_bit_exact(block_size, shape):
     assert got.shape == ref.shape
     nbad = int((got != exact).sum())
     assert nbad == 0, f"{nbad} of {ref.numel()} score pixels differ from the IEEE-sqrt oracle, max abs {float((got - exact).abs().max())}"
+    # Against the reference verbatim.  With got == exact established above, got - ref IS exact - ref: a property of the
+    # HOST's vectorised torch.sqrt, not of the kernel.  It is off by one ulp of the sqrt term on 1 % ... 4.3 % of the pixels
+    # on this pool's boxes, and one box (2026-10-19, first torch.sqrt call of the process, block size 1) returned a
+    # root 732 ulps off in a few elements.  So the host's deviation is reported, not asserted.
     off = got != ref
-    # how often the host's vectorised sqrt is off by an ulp depends on the host CPU (measured 1 % ... 4.3 % on this pool's
-    # boxes): the fraction is only sanity-checked, the SIZE of every difference is what is asserted
-    assert float(off.float().mean()) <= 0.15
     if off.any():
-        # one ulp of the sqrt term; the term is bounded by the largest possible trace of the block
-        trace_max = 2.0 * block_size ** 2 * (4.0 * amp) ** 2
-        assert float((got - ref).abs().max()) <= trace_max * 2.0 ** -22
+        trace_max = 2.0 * block_size ** 2 * (4.0 * amp) ** 2          # bounds the sqrt term; one ulp of it = trace_max * 2**-23
+        dev = float((got - ref).abs().max())
+        if float(off.float().mean()) > 0.15 or dev > trace_max * 2.0 ** -22:
+            warnings.warn(f"host torch.sqrt deviates from IEEE sqrt: {float(off.float().mean()):.4f} of the pixels, max abs {dev} "
+                          f"(block {block_size}, shape {shape}); the kernel equals the IEEE-sqrt oracle bit for bit")
 
 
 @pytest.mark.parametrize("block_size,nms_radius", [(3, 3), (3, 5), (5, 3), (5, 5)])
