@@ -467,8 +467,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.init_process_group("nccl", device_id=dev)
     import onnx_image_processing_b200 as om
     from onnx_image_processing_b200 import _native as nat
-    from onnx_image_processing_b200.host_pipeline import HostBatchMatcher
+    from onnx_image_processing_b200.host_pipeline import HostBatchMatcher, bind_host_to_gpu
 
+    numa = bind_host_to_gpu(local_rank) if world > 1 else {"bound": False, "note": "one rank: not applied"}
     cls = {"dense": om.ShiTomasiBADSinkhornMatcher, "sparse": om.ShiTomasiSparseBADSinkhornMatcher,
            "angle": om.ShiTomasiAngleSparseBADSinkhornMatcher}[args.workload]
     model = cls(K).to(dev).eval()
@@ -618,6 +619,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         h2d_gbs = e2e["h2d_bytes_per_step"] / (ms_e2e * 1e-3) / 1e9
         d2h_gbs = e2e["d2h_bytes_per_step"] / (ms_e2e * 1e-3) / 1e9
         e2e["host_link_gbs"] = link
+        e2e["host_numa"] = numa          # rank 0's placement (bind_host_to_gpu: CPUs + pinned buffers on the GPU's NUMA node)
         e2e["achieved_h2d_gbs_per_gpu"] = h2d_gbs
         e2e["achieved_d2h_gbs_per_gpu"] = d2h_gbs
         e2e["frac_of_link"] = max(h2d_gbs / link["h2d_gbs_per_gpu"], d2h_gbs / link["d2h_gbs_per_gpu"])

@@ -4,10 +4,47 @@ per GPU, no collective on the data path -- image pairs are independent, SURVEY.m
 """
 from __future__ import annotations
 
+import os
+import re
 from typing import List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def _cpu_list(text: str) -> set:
+    out = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            out.update(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def bind_host_to_gpu(device_index: int) -> dict:
+    """One process per GPU: run this process on the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned staging
+    buffers are allocated (first touch then places them on that node, so the H2D / D2H copies of the ranks do not cross
+    the socket interconnect).  Does nothing where the box exposes no such topology (one node, or numa_node = -1 as in a
+    VM).  Returns what it found and did (for the bench line)."""
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        info["pci"] = bus
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if re.fullmatch(r"node\d+", d)]
+        info["numa_nodes"] = len(nodes)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        info["gpu_numa_node"] = node
+        if node >= 0 and len(nodes) > 1:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = _cpu_list(f.read()) & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"], info["cpus"] = True, len(cpus)
+    except (OSError, ValueError, AttributeError, RuntimeError) as e:
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
 
 
 def shard_bounds(num_pairs: int, rank: int, world_size: int) -> Tuple[int, int]:

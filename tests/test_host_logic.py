@@ -176,3 +176,16 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_numa_binding_helper_is_harmless_without_topology():
+    """bind_host_to_gpu: parses sysfs CPU lists; without a GPU / NUMA topology it reports and changes nothing."""
+    import os
+    from onnx_image_processing_b200.host_pipeline import _cpu_list, bind_host_to_gpu
+    assert _cpu_list("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _cpu_list("") == set()
+    before = os.sched_getaffinity(0)
+    info = bind_host_to_gpu(0)
+    assert info["bound"] is False or info.get("cpus", 0) > 0
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
