@@ -1371,3 +1371,33 @@ def test_ingest_feeds_the_matcher_natively():
     assert torch.equal(a8.cpu().float(), host)
     for x, y in zip(out8, outf):
         assert torch.equal(x, y)
+
+
+def test_config0_detector_480x640_k1000_golden():
+    """BASELINE configs[0] at its own size: one 480x640 image, max_keypoints=1000, both detector forms, against the live
+    reference's outputs (tests/golden/make_golden_config0.py)."""
+    g = G.load("config0_detector_480x640_k1000")
+    img, K = g["image1"].to(DEV), g["K"]
+    # (A) ShiTomasiAngleSparseBADDetector(max_keypoints=1000)
+    ak, asc, ad = om.ShiTomasiAngleSparseBADDetector(K).to(DEV).eval()(img)
+    assert PR.keypoint_mismatches(ak, g["a_kpts"], g["a_scores"]) == 0
+    assert PR.scores_close(asc, g["a_scores"])
+    dm = PR.desc_metrics(ad, g["a_desc"])
+    print("config0 oriented descriptors:", dm)
+    assert dm["rows_within"] >= ORIENTED_ROWS_MIN, dm
+    # (B) ShiTomasiBADDetector(): score map + dense descriptor map, then the library's selection (NMS 3, threshold 0.01)
+    sc, dmap = om.ShiTomasiBADDetector().to(DEV).eval()(img)
+    assert sc.shape == g["score_map"].shape and dmap.shape == (1, 256, 480, 640)
+    # the golden score map carries the authoring host's torch.sqrt (not correctly rounded, see test_score_map_bit_exact):
+    # at most one ulp of the sqrt term, on a few per cent of the pixels
+    err = (sc.cpu() - g["score_map"]).abs()
+    assert float((err > 0).float().mean()) <= 0.15
+    assert float(err.max()) <= 2.0 * 9 * (4.0 * 256) ** 2 * 2.0 ** -22
+    s3 = sc.squeeze(1)
+    bk, bs = om.select_topk_keypoints(s3, om.apply_nms_maxpool(s3, g["nms_radius"]), K, g["threshold"], 0)
+    assert PR.keypoint_mismatches(bk, g["b_kpts"], g["b_scores"]) == 0
+    assert PR.scores_close(bs, g["b_scores"])
+    pp, py, px = g["probe_idx"].long()
+    assert torch.equal(dmap[0, pp.to(DEV), py.to(DEV), px.to(DEV)].cpu(), g["probe_val"])
+    yi, xi = g["b_kpts"][0, :, 0].long().to(DEV), g["b_kpts"][0, :, 1].long().to(DEV)
+    assert torch.equal(dmap[0][:, yi, xi].T.cpu(), g["b_desc"])

@@ -247,3 +247,23 @@ def test_akaze_module_mirror_matches_oracle_on_cpu():
     with torch.no_grad():
         s, o = om.AKAZE()(g["image1"])
     assert torch.equal(s, g["scores1"]) and torch.equal(o, g["orient1"])
+
+
+def test_config0_detector_480x640_k1000():
+    """BASELINE configs[0] at its own size (one 480x640 image, max_keypoints=1000), both detector forms
+    (tests/golden/make_golden_config0.py): the oracle against the live reference's outputs."""
+    g = G.load("config0_detector_480x640_k1000")
+    img, K = g["image1"], g["K"]
+    with torch.no_grad():
+        ak, asc, ad = O.angle_detector(img, K)
+        sc, dmap = O.dense_detector(img)
+        s3 = sc.squeeze(1)
+        bk, bs = O.select_topk(s3, O.nms_mask(s3, g["nms_radius"]), K, g["threshold"], 0)
+    assert torch.equal(ak, g["a_kpts"]) and torch.equal(asc, g["a_scores"])
+    assert (ad - g["a_desc"]).abs().max() <= 2e-6
+    assert torch.equal(sc, g["score_map"])
+    assert torch.equal(bk, g["b_kpts"]) and torch.equal(bs, g["b_scores"])
+    pp, py, px = g["probe_idx"].long()
+    assert torch.equal(dmap[0, pp, py, px], g["probe_val"])
+    yi, xi = bk[0, :, 0].long(), bk[0, :, 1].long()
+    assert torch.equal(dmap[0][:, yi, xi].T, g["b_desc"])
