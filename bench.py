@@ -16,7 +16,7 @@ synthetic image pairs per GPU.  Prints ONE JSON line (rank 0).  Keys:
                device's: keypoint mismatches, descriptor max-abs, P core max-abs, argmax agreement (rank 0, N=1)
   p0_sha256    sha256 of the bytes of pair 0's P (rank 0): identical for every world size (same seed, same kernels)
   stage_roofline   fused detector+descriptor stage: SURVEY 8(d) algorithmic bytes / sum of its kernels' times vs HBM peak
-  configs_measured the other BASELINE configs (sparse batch 1/64/1024, angle, export defaults, 1080p K=2048) on this box
+  configs_measured the other BASELINE configs (detection only, sparse batch 1/64/1024, angle, export defaults, 1080p K=2048) on this box
   configs_sharded  BASELINE configs[3] (angle matcher, 64 pairs per GPU) and configs[4] (1080p, K=2048, 8 pairs per GPU) on all
                    N ranks: barrier, CUDA events, max over ranks, whole-job pairs/s
 """
@@ -453,6 +453,21 @@ def measure_other_configs(dev, steps):
         "achieved": sweep_bytes / per_it_ms / 1e6, "peak": peak, "unit": "GB/s", "frac": sweep_bytes / per_it_ms / 1e6 / peak,
         "peak_source": peak_src, "how": "slope of the Sinkhorn stage time between 20 and 60 iterations (CUDA events)"}
     rows.append(row)
+    # configs[0]: detection only (no matching), one 480x640 image and a batch of 64, 1000 keypoints; images per second
+    try:
+        det = om.ShiTomasiAngleSparseBADDetector(1000).to(dev).eval()
+        for Bi in (1, 64):
+            img = O.texture_images(Bi, H, W, seed=3)[0].to(dev)
+            with torch.no_grad():
+                for _ in range(3):
+                    r0 = det(img)
+                ms = event_time_ms(lambda: det(img), max(3, steps), 0, stream)
+            del r0
+            rows.insert(0 if Bi == 1 else 1, {
+                "config": "configs[0] Shi-Tomasi + BAD detection (ShiTomasiAngleSparseBADDetector), 480x640, max_keypoints=1000",
+                "images_per_step": Bi, "ms_per_step": ms, "images_per_s": Bi / ms * 1e3, "steps": max(3, steps)})
+    except Exception as e:  # noqa: BLE001 -- an informational row must not take the bench line down
+        rows.append({"config": "configs[0] detection only", "error": f"{type(e).__name__}: {e}"})
     return rows
 
 
