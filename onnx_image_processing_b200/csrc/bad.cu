@@ -437,8 +437,12 @@ struct SparseKpCtx {
 };
 
 // One pair at one keypoint through the full sampling pipeline (bad.py:504-557).
+// `row`, `r`, `inv_area`: the pair's table entry and what follows from it (1 / box area), loaded by the caller (from the
+// global table on the rare border path of the fast kernels, from the CTA's shared-memory copy in the oriented / bilinear
+// kernels, where every pair of every keypoint comes through here).
 template <int HS, bool ORIENTED, bool BILINEAR, typename WT>
-__device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx<WT>& c, const float* table, int p, int mode, float temperature) {
+__device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx<WT>& c, const PairRow& row, int r, float inv_area, int mode,
+                                                          float temperature) {
     using G = WinGeom<HS, WT>;
     constexpr int S = G::S, WP = G::WP;
     const int H = c.H, W = c.W;
@@ -476,10 +480,6 @@ __device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx<WT>&
         const float sw = box_mean(y_s, x_w, r, inv_area), se = box_mean(y_s, x_e, r, inv_area);
         return nw * (n * e) + ne * (n * w) + sw * (s * e) + se * (s * w);
     };
-    const PairRow row = load_pair(table, p);
-    const int r = (int)row.r;
-    const float side = (float)(2 * r + 1);
-    const float inv_area = __fdiv_rn(1.0f, side * side);
     const float diff = __fsub_rn(sample(row.oy1, row.ox1, r, inv_area), sample(row.oy2, row.ox2, r, inv_area));
     return finish_value(diff, row.thr, mode, temperature);
 }
@@ -489,7 +489,10 @@ __device__ __forceinline__ float sparse_pair_general_impl(const SparseKpCtx<WT>&
 // pairs of a thread overlap.
 template <int HS, bool ORIENTED, bool BILINEAR, typename WT>
 __device__ __noinline__ float sparse_pair_general(const SparseKpCtx<WT>& c, const float* table, int p, int mode, float temperature) {
-    return sparse_pair_general_impl<HS, ORIENTED, BILINEAR, WT>(c, table, p, mode, temperature);
+    const PairRow row = load_pair(table, p);
+    const int r = (int)row.r;
+    const float side = (float)(2 * r + 1);
+    return sparse_pair_general_impl<HS, ORIENTED, BILINEAR, WT>(c, row, r, __fdiv_rn(1.0f, side * side), mode, temperature);
 }
 
 // one keypoint whose window `win` is in flight / has landed on mbarrier `bar` (phase `parity`).  NPP = pairs per
@@ -498,7 +501,7 @@ template <int HS, bool ORIENTED, bool BILINEAR, int NPP, typename WT>
 __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long kidx, int z, float ky, float kx,
                                                  const WT* win, uint32_t bar, uint32_t parity, float* red,
                                                  float* sTheta, const uint4* sTap, const float2* sThr,
-                                                 const unsigned short* sIdx, int g, int t) {
+                                                 const unsigned short* sIdx, const float4* sOff, const float4* sPar, int g, int t) {
     constexpr bool FAST = !ORIENTED && !BILINEAR;
     const int H = a.H, W = a.W;
     float* out = a.desc + (size_t)kidx * a.P;
@@ -575,8 +578,14 @@ __device__ __forceinline__ void sparse_win_group(const SparseArgs& a, long long 
             const int p = t + q * TPG;
             d[q] = 0.0f;
             if (p < a.P) {
-                d[q] = FAST ? sparse_pair_general<HS, ORIENTED, BILINEAR, WT>(c, a.table, p, a.mode, a.temperature)
-                            : sparse_pair_general_impl<HS, ORIENTED, BILINEAR, WT>(c, a.table, p, a.mode, a.temperature);
+                if (FAST) {
+                    d[q] = sparse_pair_general<HS, ORIENTED, BILINEAR, WT>(c, a.table, p, a.mode, a.temperature);
+                } else {
+                    const float4 o = sOff[p], pr = sPar[p];                 // {oy1, ox1, oy2, ox2}, {threshold, 1/area, r, -}
+                    PairRow row;
+                    row.oy1 = o.x; row.ox1 = o.y; row.oy2 = o.z; row.ox2 = o.w; row.thr = pr.x; row.r = 0.0f;
+                    d[q] = sparse_pair_general_impl<HS, ORIENTED, BILINEAR, WT>(c, row, __float_as_int(pr.z), pr.y, a.mode, a.temperature);
+                }
                 ss = fmaf(d[q], d[q], ss);
             }
         }
@@ -609,6 +618,9 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
     uint4* sTap = reinterpret_cast<uint4*>(sWin + GROUPS * NBUF * G::GSTRIDE);  // fast path: 2 x 4 window byte offsets per pair (16 bits each)
     float2* sThr = reinterpret_cast<float2*>(sTap + (FAST ? a.P : 0));          //            {threshold, 1/area}
     unsigned short* sIdx = reinterpret_cast<unsigned short*>(sThr + (FAST ? a.P : 0));   //     slot -> pair (pair_order.inc)
+    // oriented / bilinear kernels: the pair table itself (every keypoint evaluates every pair through the general path)
+    float4* sOff = reinterpret_cast<float4*>(sWin + GROUPS * NBUF * G::GSTRIDE);           // {oy1, ox1, oy2, ox2}
+    float4* sPar = sOff + (FAST ? 0 : a.P);                                                // {threshold, 1/area, r, -}
 
     const int g = threadIdx.x / TPG, t = threadIdx.x % TPG;
     if (threadIdx.x == 0) {
@@ -632,6 +644,15 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
             sTap[p] = pack_taps(o);
             const float side = (float)(2 * r + 1);
             sThr[p] = make_float2(row.thr, __fdiv_rn(1.0f, side * side));
+        }
+    }
+    if (!FAST) {
+        for (int p = threadIdx.x; p < a.P; p += GROUPS * TPG) {
+            const PairRow row = load_pair(a.table, p);
+            const int r = (int)row.r;
+            const float side = (float)(2 * r + 1);
+            sOff[p] = make_float4(row.oy1, row.ox1, row.oy2, row.ox2);
+            sPar[p] = make_float4(row.thr, __fdiv_rn(1.0f, side * side), __int_as_float(r), 0.0f);
         }
     }
     __syncthreads();                             // barriers initialised, tables built
@@ -661,7 +682,7 @@ __global__ void __launch_bounds__(GROUPS * TPG, 4) sparse_win_kernel(const __gri
         int z;
         if (win_needed(a, kidx, ky, kx, z)) {
             sparse_win_group<HS, ORIENTED, BILINEAR, NPP, WT>(a, kidx, z, ky, kx, reinterpret_cast<const WT*>(wbuf + buf * G::GSTRIDE),
-                                                              bar0 + 8u * buf, phase[buf], red, sTheta, sTap, sThr, sIdx, g, t);
+                                                              bar0 + 8u * buf, phase[buf], red, sTheta, sTap, sThr, sIdx, sOff, sPar, g, t);
             phase[buf] ^= 1u;
         } else if (!(ky >= 0.0f)) {                                 // bad.py:461, :570 -> the row is all zeros
             float* out = a.desc + (size_t)kidx * a.P;
@@ -680,7 +701,8 @@ int launch_sparse_win(const SparseArgs& a, const void* I, cudaStream_t st) {
     OM_TRY(make_tmap_3d(&tmap, false, I, (uint64_t)IP, (uint64_t)Hi, (uint64_t)a.B, (uint64_t)IP, G::WP, G::WR, (int)sizeof(WT)));
     constexpr int NBUF = 1;
     const size_t smem = (size_t)GROUPS * NBUF * G::GSTRIDE * 4 +
-                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2) + sizeof(unsigned short)) : 0);
+                        ((!ORIENTED && !BILINEAR) ? (size_t)a.P * (sizeof(uint4) + sizeof(float2) + sizeof(unsigned short))
+                                                  : (size_t)a.P * 2 * sizeof(float4));
     const long long total = (long long)a.B * a.K;
     const long long nblk = (total + GROUPS - 1) / GROUPS;
     const int per_sm = (int)(228 * 1024 / (smem + 1024));          // resident CTAs per SM by shared memory (228 KB, 1 KB reserved per CTA)
